@@ -1,0 +1,1508 @@
+// pawpyseed_b200 engine: device-resident wavefunction state + the C ABI of include/pawpyseed_b200.h.
+// There is deliberately no CPU compute path in this file: every overlap / projection / FFT is a
+// kernel launch, and entry points fail with an error message when no sm_100 device is usable.
+#include <cuda_runtime.h>
+#include <cufft.h>
+#include <omp.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/pawpyseed_b200.h"
+#include "host_paw.h"
+#include "kernels.cuh"
+#include "zgemm.cuh"
+
+using namespace pawb200;
+
+// ---------------------------------------------------------------------------------------
+// errors, CUDA helpers, timers
+// ---------------------------------------------------------------------------------------
+namespace {
+
+thread_local std::string g_error;
+thread_local bool g_has_error = false;
+
+void set_error(const std::string& m) {
+  g_error = m;
+  g_has_error = true;
+  if (getenv("PAWB200_VERBOSE")) fprintf(stderr, "[pawb200] error: %s\n", m.c_str());
+}
+
+#define CUDA_OK(expr)                                                                       \
+  do {                                                                                      \
+    cudaError_t e_ = (expr);                                                                \
+    if (e_ != cudaSuccess)                                                                  \
+      throw std::runtime_error(std::string("CUDA: ") + cudaGetErrorString(e_) + " at " +    \
+                               __FILE__ + ":" + std::to_string(__LINE__));                  \
+  } while (0)
+#define CUFFT_OK(expr)                                                                      \
+  do {                                                                                      \
+    cufftResult r_ = (expr);                                                                \
+    if (r_ != CUFFT_SUCCESS)                                                                \
+      throw std::runtime_error("cuFFT error " + std::to_string((int)r_) + " at " + __FILE__ + \
+                               ":" + std::to_string(__LINE__));                             \
+  } while (0)
+#define API_BEGIN \
+  g_has_error = false; \
+  try {
+#define API_END(ret)                      \
+  }                                       \
+  catch (const std::exception& e) {       \
+    set_error(e.what());                  \
+    return ret;                           \
+  }
+#define API_END_VOID                      \
+  }                                       \
+  catch (const std::exception& e) {       \
+    set_error(e.what());                  \
+    return;                               \
+  }
+
+cudaStream_t g_stream = 0;   // legacy default stream: ordered with torch's default stream
+std::atomic<long long> g_launches{0};
+int g_num_sms = 0;
+
+void require_device() {
+  static int state = 0;   // 0 unknown, 1 ok, -1 failed
+  static std::string why;
+  if (state == 0) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+      state = -1;
+      why = std::string("no CUDA device available (") +
+            (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0") +
+            "); pawpyseed_b200 has no CPU fallback";
+      cudaGetLastError();
+    } else {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceProp p;
+      cudaGetDeviceProperties(&p, dev);
+      if (p.major < 10) {
+        state = -1;
+        why = "GPU '" + std::string(p.name) + "' is sm_" + std::to_string(p.major) +
+              std::to_string(p.minor) + "; this library is built for sm_100a (B200) only";
+      } else {
+        state = 1;
+        g_num_sms = p.multiProcessorCount;
+      }
+    }
+  }
+  if (state < 0) throw std::runtime_error(why);
+}
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  DevBuf() = default;
+  explicit DevBuf(size_t n) { alloc(n); }
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept : p(o.p), bytes(o.bytes) { o.p = nullptr; o.bytes = 0; }
+  DevBuf& operator=(DevBuf&& o) noexcept {
+    if (this != &o) { release(); p = o.p; bytes = o.bytes; o.p = nullptr; o.bytes = 0; }
+    return *this;
+  }
+  ~DevBuf() { release(); }
+  void alloc(size_t n) {
+    release();
+    if (n == 0) return;
+    CUDA_OK(cudaMalloc(&p, n));
+    bytes = n;
+  }
+  void ensure(size_t n) { if (n > bytes) alloc(n); }
+  void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+  void zero() { if (p) CUDA_OK(cudaMemsetAsync(p, 0, bytes, g_stream)); }
+  template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+template <typename T>
+DevBuf upload(const std::vector<T>& v) {
+  DevBuf b(v.size() * sizeof(T));
+  if (!v.empty())
+    CUDA_OK(cudaMemcpyAsync(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, g_stream));
+  CUDA_OK(cudaStreamSynchronize(g_stream));   // v may be a temporary
+  return b;
+}
+
+// ---- stage timers (CUDA events on the launch stream) ---------------------------------------
+enum Stage { ST_H2D, ST_SCATTER, ST_FFT, ST_PROJECT, ST_TABLE, ST_GEMM_PS, ST_GEMM_AUG, ST_AUGMENT,
+             ST_D2H, ST_COUNT };
+struct EventPair { cudaEvent_t a, b; int stage; };
+std::vector<EventPair> g_pending;
+std::vector<cudaEvent_t> g_event_pool;
+double g_stage_ms[ST_COUNT] = {0};
+bool g_timing = true;
+
+cudaEvent_t get_event() {
+  if (!g_event_pool.empty()) {
+    cudaEvent_t e = g_event_pool.back();
+    g_event_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  CUDA_OK(cudaEventCreate(&e));
+  return e;
+}
+struct ScopedStage {
+  EventPair ep;
+  bool on;
+  explicit ScopedStage(int stage) : on(g_timing) {
+    if (!on) return;
+    ep.a = get_event();
+    ep.b = get_event();
+    ep.stage = stage;
+    cudaEventRecord(ep.a, g_stream);
+  }
+  ~ScopedStage() {
+    if (!on) return;
+    cudaEventRecord(ep.b, g_stream);
+    g_pending.push_back(ep);
+  }
+};
+void drain_timers() {
+  for (auto& ep : g_pending) {
+    cudaEventSynchronize(ep.b);
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, ep.a, ep.b) == cudaSuccess) g_stage_ms[ep.stage] += ms;
+    g_event_pool.push_back(ep.a);
+    g_event_pool.push_back(ep.b);
+  }
+  g_pending.clear();
+}
+
+inline void count_launch(int n = 1) { g_launches += n; }
+inline void check_launch() { CUDA_OK(cudaGetLastError()); }
+
+// ---- cuFFT plan cache -------------------------------------------------------------------------
+struct PlanKey {
+  int n0, n1, n2, batch;
+  bool operator<(const PlanKey& o) const {
+    return std::tie(n0, n1, n2, batch) < std::tie(o.n0, o.n1, o.n2, o.batch);
+  }
+};
+std::map<PlanKey, cufftHandle> g_plans;
+DevBuf g_fft_work;
+
+cufftHandle get_plan(const int* fftg, int batch) {
+  PlanKey k{fftg[0], fftg[1], fftg[2], batch};
+  auto it = g_plans.find(k);
+  if (it != g_plans.end()) return it->second;
+  cufftHandle h;
+  CUFFT_OK(cufftCreate(&h));
+  CUFFT_OK(cufftSetAutoAllocation(h, 0));
+  int n[3] = {fftg[0], fftg[1], fftg[2]};
+  size_t ws = 0;
+  long long nn[3] = {n[0], n[1], n[2]};
+  long long dist = (long long)n[0] * n[1] * n[2];
+  CUFFT_OK(cufftMakePlanMany64(h, 3, nn, nullptr, 1, dist, nullptr, 1, dist, CUFFT_Z2Z, batch, &ws));
+  CUFFT_OK(cufftSetStream(h, g_stream));
+  if (ws > g_fft_work.bytes) {
+    CUDA_OK(cudaStreamSynchronize(g_stream));
+    g_fft_work.alloc(ws);
+    for (auto& kv : g_plans) CUFFT_OK(cufftSetWorkArea(kv.second, g_fft_work.p));
+  }
+  CUFFT_OK(cufftSetWorkArea(h, g_fft_work.p));
+  g_plans[k] = h;
+  return h;
+}
+
+size_t fft_budget_bytes() {
+  const char* e = getenv("PAWB200_FFT_BYTES");
+  if (e) return (size_t)atoll(e);
+  return (size_t)6 << 30;
+}
+
+// ---------------------------------------------------------------------------------------
+// site table sets
+// ---------------------------------------------------------------------------------------
+struct ElementList {   // what pawb200_ppot_t points to
+  std::vector<Element> el;
+};
+
+struct ElemDevStore {   // device copies of the radial data for one table mode
+  std::vector<DevBuf> bufs;
+  DevBuf dev;           // ElemDev[nelem]
+};
+
+// mode 0: projectors, 1: filtered phi-phit on the linear grid, 2: phi-phit on the log grid
+ElemDevStore upload_elements(const std::vector<Element>& els, int mode) {
+  ElemDevStore st;
+  std::vector<ElemDev> host(els.size());
+  for (size_t e = 0; e < els.size(); e++) {
+    const Element& el = els[e];
+    const std::vector<double>& grid = mode == 0 ? el.proj_grid : (mode == 1 ? el.smooth_grid : el.wave_grid);
+    const int n = (int)grid.size();
+    std::vector<double> f((size_t)el.num_projs * n), spl((size_t)el.num_projs * 3 * n);
+    for (int k = 0; k < el.num_projs; k++) {
+      const RadialFunc& rf = el.funcs[k];
+      const std::vector<double>& v = mode == 0 ? rf.proj : (mode == 1 ? rf.smooth_diffwave : rf.diffwave);
+      const Spline& s = mode == 0 ? rf.proj_s : (mode == 1 ? rf.smooth_s : rf.diffwave_s);
+      std::copy(v.begin(), v.end(), f.begin() + (size_t)k * n);
+      for (int r = 0; r < 3; r++)
+        std::copy(s.c[r].begin(), s.c[r].end(), spl.begin() + ((size_t)k * 3 + r) * n);
+    }
+    std::vector<int> cn, cl, cm;
+    for (auto& c : el.chan) { cn.push_back(c.n); cl.push_back(c.l); cm.push_back(c.m); }
+    st.bufs.push_back(upload(grid));  host[e].grid = st.bufs.back().as<double>();
+    st.bufs.push_back(upload(f));     host[e].f = st.bufs.back().as<double>();
+    st.bufs.push_back(upload(spl));   host[e].spl = st.bufs.back().as<double>();
+    st.bufs.push_back(upload(cn));    host[e].chan_n = st.bufs.back().as<int>();
+    st.bufs.push_back(upload(cl));    host[e].chan_l = st.bufs.back().as<int>();
+    st.bufs.push_back(upload(cm));    host[e].chan_m = st.bufs.back().as<int>();
+    host[e].n = n;
+    host[e].nfunc = el.num_projs;
+    host[e].nchan = el.total_projs;
+    host[e].rmax = mode == 0 ? el.rmax : el.wave_rmax;
+  }
+  st.dev = upload(host);
+  return st;
+}
+
+struct SiteTables {
+  int nsites = 0;
+  int mode = 0;
+  int fftg[3] = {0, 0, 0};
+  std::vector<SiteDev> host;          // per site
+  std::vector<int> site_id;           // index of each site in the structure
+  long total_pts = 0;                 // padded
+  long total_tab = 0;                 // double2 elements
+  int nproj = 0;                      // concatenated channel count
+  DevBuf sites, idx, path, wrap, table, tablek;
+  std::vector<std::vector<int>> by_mt;   // site indices grouped by m-tile count (1..3)
+  std::vector<DevBuf> by_mt_dev;
+  std::vector<std::vector<int32_t>> host_idx;   // kept for the index-parity accessor
+  size_t coord_hash = 0;
+};
+
+size_t hash_bytes(const void* p, size_t n, size_t seed = 1469598103934665603ull) {
+  const unsigned char* b = (const unsigned char*)p;
+  size_t h = seed;
+  for (size_t i = 0; i < n; i++) { h ^= b[i]; h *= 1099511628211ull; }
+  return h;
+}
+
+// Geometry on the host (bit-exact membership), values on the GPU.
+std::unique_ptr<SiteTables> build_site_tables(const std::vector<Element>& els, const int* site_list,
+                                              int nlist, const int* labels, const double* coords,
+                                              const double* lattice, const int* fftg, int mode,
+                                              bool keep_host_idx) {
+  auto T = std::make_unique<SiteTables>();
+  T->nsites = nlist;
+  T->mode = mode;
+  for (int d = 0; d < 3; d++) T->fftg[d] = fftg[d];
+  T->host.resize(nlist);
+  T->site_id.assign(site_list, site_list + nlist);
+  std::vector<SphereGeom> geom(nlist);
+#pragma omp parallel for schedule(dynamic)
+  for (int s = 0; s < nlist; s++) {
+    const int p = site_list[s];
+    const Element& el = els[labels[p]];
+    const double rmax = mode == 0 ? el.rmax : el.wave_rmax;
+    double radius = rmax;
+    if (mode != 2) {
+      // utils.c:651-652: (n-1)*rmax/n with the divisor taken from pps[labels[s]] (loop index)
+      const int ndiv = els[labels[s]].proj_gridsize;
+      radius = (el.proj_gridsize - 1) * rmax / ndiv;
+    }
+    geom[s] = sphere_geometry(coords + 3 * p, lattice, fftg, rmax, radius);
+  }
+  long pt = 0, tab = 0;
+  int lm = 0;
+  for (int s = 0; s < nlist; s++) {
+    const int p = site_list[s];
+    const Element& el = els[labels[p]];
+    SiteDev& sd = T->host[s];
+    sd.elem = labels[p];
+    sd.npts = (int)geom[s].index.size();
+    sd.npts_pad = (sd.npts + 31) / 32 * 32;
+    sd.pt_off = pt;
+    sd.tab_off = tab;
+    sd.nlm = el.total_projs;
+    sd.lm_off = lm;
+    for (int d = 0; d < 3; d++) sd.coord[d] = coords[3 * p + d];
+    pt += sd.npts_pad;
+    tab += (long)sd.nlm * sd.npts_pad;
+    lm += sd.nlm;
+    if (sd.nlm > 24) throw std::runtime_error("more than 24 channels per site is not supported");
+  }
+  T->total_pts = pt;
+  T->total_tab = tab;
+  T->nproj = lm;
+  std::vector<int32_t> idx(pt, 0), wrap(3 * pt, 0);
+  std::vector<double> path(3 * pt, 0.0);
+  for (int s = 0; s < nlist; s++) {
+    const SiteDev& sd = T->host[s];
+    for (int q = 0; q < sd.npts; q++) {
+      idx[sd.pt_off + q] = geom[s].index[q];
+      for (int d = 0; d < 3; d++) {
+        path[d * pt + sd.pt_off + q] = geom[s].path[3 * q + d];
+        wrap[d * pt + sd.pt_off + q] = geom[s].wrap[3 * q + d];
+      }
+    }
+  }
+  if (keep_host_idx) {
+    T->host_idx.resize(nlist);
+    for (int s = 0; s < nlist; s++) T->host_idx[s] = std::move(geom[s].index);
+  }
+  T->sites = upload(T->host);
+  T->idx = upload(idx);
+  T->path = upload(path);
+  if (mode == 2) T->wrap = upload(wrap);
+  T->table.alloc(std::max<size_t>(1, tab) * sizeof(double2));
+  T->by_mt.assign(4, {});
+  for (int s = 0; s < nlist; s++) T->by_mt[(T->host[s].nlm + 7) / 8].push_back(s);
+  T->by_mt_dev.resize(4);
+  for (int m = 1; m <= 3; m++)
+    if (!T->by_mt[m].empty()) T->by_mt_dev[m] = upload(T->by_mt[m]);
+
+  if (nlist > 0 && pt > 0) {
+    ScopedStage tm(ST_TABLE);
+    ElemDevStore ed = upload_elements(els, mode);
+    std::vector<double> lat(lattice, lattice + 9);
+    DevBuf dlat = upload(lat);
+    int maxpts = 0;
+    for (auto& sd : T->host) maxpts = std::max(maxpts, sd.npts_pad);
+    dim3 grid((maxpts + 127) / 128, nlist);
+    site_table_kernel<<<grid, 128, 0, g_stream>>>(
+        T->sites.as<SiteDev>(), ed.dev.as<ElemDev>(), T->idx.as<int>(), T->path.as<double>(), pt,
+        T->table.as<double2>(), dlat.as<double>(), fftg[0], fftg[1], fftg[2], mode == 2 ? 1 : 0);
+    count_launch();
+    check_launch();
+    CUDA_OK(cudaStreamSynchronize(g_stream));   // ed / dlat go out of scope
+  }
+  return T;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------
+// wavefunction state
+// ---------------------------------------------------------------------------------------
+struct pawb200_ppot {
+  ElementList list;
+};
+
+struct HostMatrixCache {
+  uint64_t other_id = 0, other_gen = 0, self_gen = 0;
+  int flip = -1;
+  size_t list_hash = 0;
+  std::vector<cdouble> data;   // [NK][nbS][nbR]
+  bool valid = false;
+};
+
+static std::atomic<uint64_t> g_next_id{1};
+
+struct pawb200_pswf {
+  uint64_t id = g_next_id++;
+  uint64_t gen = 1;
+  int nspin = 0, nwk = 0, nband = 0, ncl = 0;
+  double encut = 0;
+  double lattice[9], reclattice[9];
+  int G_bounds[6] = {0, 0, 0, 0, 0, 0};
+  std::vector<KPointInfo> kp;          // per kappa
+  std::vector<double> weight;          // per kappa
+  std::vector<DevBuf> C;               // per kappa: float2 [nband][ldc]
+  std::vector<long> ldc;
+  std::vector<char> resident;          // per kappa: this process holds the block
+  // projector state
+  std::unique_ptr<pawb200_ppot> pps;
+  int num_sites = 0;
+  int fftg[3] = {0, 0, 0};
+  std::vector<int> labels;
+  std::vector<double> coords;
+  std::unique_ptr<SiteTables> proj_sites;
+  std::vector<DevBuf> P;               // per kappa: double2 [nslot][ldp]
+  long ldp = 0;
+  bool has_projections = false;
+  // overlap_setup state (this wf's bands projected on the other structure's filtered partial waves)
+  std::vector<DevBuf> W;               // per kappa: double2 [nslot][ldw]
+  long ldw = 0;
+  int wp_num = 0;
+  std::vector<int> wp_nlm;             // channels per wave-projection site
+  // as wf_S: off-site data
+  std::vector<std::vector<cdouble>> omega;
+  std::vector<double> dcoords;
+  std::vector<int> omega_n1, omega_n2;
+  uint64_t overlap_partner = 0;
+  // real-space table cache (mode 2), keyed by grid + coords
+  std::unique_ptr<SiteTables> ae_sites;
+  // per-band call caches
+  HostMatrixCache pseudo_cache, aug_cache;
+
+  int nkappa() const { return nwk * nspin; }
+  int halves() const { return ncl ? 2 : 1; }
+  int nslot() const { return nband * halves(); }
+  int npw_half(int kap) const { return kp[kap].nplane / halves(); }
+};
+
+namespace {
+
+int g_shard_rank = 0, g_shard_world = 1;
+
+// ---- WAVECAR ingest -----------------------------------------------------------------------
+struct ByteSource {
+  const unsigned char* mem = nullptr;
+  FILE* fp = nullptr;
+  void read(void* dst, long off, size_t n) {
+    if (mem) {
+      memcpy(dst, mem + off, n);
+    } else {
+      if (fseek(fp, off, SEEK_SET) != 0 || fread(dst, 1, n, fp) != n)
+        throw std::runtime_error("short read from WAVECAR");
+    }
+  }
+};
+
+pawb200_pswf* ingest(ByteSource src, const double* kws) {
+  require_device();
+  auto wf = std::make_unique<pawb200_pswf>();
+  double h0[3];
+  src.read(h0, 0, 24);
+  WavecarHeader hd;
+  hd.nrecl = (long)std::round(h0[0]);
+  hd.nspin = (int)std::round(h0[1]);
+  if (hd.nrecl < 96 || hd.nspin < 1 || hd.nspin > 2) throw std::runtime_error("not a WAVECAR header");
+  std::vector<double> rec(hd.nrecl / 8);
+  src.read(rec.data(), hd.nrecl, 12 * 8);
+  hd.nwk = (int)std::round(rec[0]);
+  hd.nband = (int)std::round(rec[1]);
+  hd.encut = rec[2];
+  for (int i = 0; i < 9; i++) hd.lattice[i] = rec[3 + i];
+  wavecar_bounds(hd);
+  wf->nspin = hd.nspin; wf->nwk = hd.nwk; wf->nband = hd.nband; wf->encut = hd.encut;
+  memcpy(wf->lattice, hd.lattice, sizeof(hd.lattice));
+  memcpy(wf->reclattice, hd.reclattice, sizeof(hd.reclattice));
+  const int NK = hd.nwk * hd.nspin;
+  wf->kp.resize(NK); wf->weight.resize(NK); wf->C.resize(NK); wf->ldc.assign(NK, 0);
+  wf->resident.assign(NK, 0);
+  unsigned char* stage = nullptr;
+  size_t stage_bytes = 0;
+  ScopedStage tm(ST_H2D);
+  for (int kap = 0; kap < NK; kap++) {
+    const long base = 2 + (long)kap * (1 + hd.nband);
+    const size_t hdr_doubles = std::min<size_t>(hd.nrecl / 8, 4 + 3 * (size_t)hd.nband);
+    src.read(rec.data(), base * hd.nrecl, hdr_doubles * 8);
+    KPointInfo& kp = wf->kp[kap];
+    kp.nplane = (int)std::round(rec[0]);
+    kp.k[0] = rec[1]; kp.k[1] = rec[2]; kp.k[2] = rec[3];
+    kp.energy.resize(hd.nband); kp.occ.resize(hd.nband);
+    for (int b = 0; b < hd.nband; b++) { kp.energy[b] = rec[4 + 3 * b]; kp.occ[b] = rec[6 + 3 * b]; }
+    wf->weight[kap] = kws ? kws[kap % hd.nwk] : 1.0;
+    if (kap >= hd.nwk && kp.k[0] == wf->kp[kap - hd.nwk].k[0] && kp.k[1] == wf->kp[kap - hd.nwk].k[1] &&
+        kp.k[2] == wf->kp[kap - hd.nwk].k[2]) {
+      kp.G = wf->kp[kap - hd.nwk].G;   // second spin channel: same k, same list
+    } else {
+      kp.G = enumerate_g(hd, kp.k, wf->G_bounds);
+    }
+    const int ng = (int)(kp.G.size() / 3);
+    if (2 * ng == kp.nplane) {
+      wf->ncl = 1;
+    } else if (ng != kp.nplane) {
+      // reader.c:282-284 only prints; a mismatched basis cannot be mapped, so this is an error here
+      throw std::runtime_error("plane-wave count mismatch at k-point " + std::to_string(kap) + ": " +
+                               std::to_string(ng) + " enumerated vs " + std::to_string(kp.nplane) +
+                               " stored (gamma-only WAVECARs are unsupported, as in the reference)");
+    }
+    if ((long)kp.nplane * 8 > hd.nrecl) throw std::runtime_error("record shorter than nplane");
+    if (kap % g_shard_world != g_shard_rank) continue;   // sharded ingest: not this rank's block
+    wf->resident[kap] = 1;
+    const long ld = ((long)kp.nplane + 31) / 32 * 32;
+    wf->ldc[kap] = ld;
+    wf->C[kap].alloc((size_t)hd.nband * ld * sizeof(float2));
+    wf->C[kap].zero();
+    const unsigned char* from;
+    if (src.mem) {
+      from = src.mem + (base + 1) * hd.nrecl;
+    } else {
+      const size_t need = (size_t)hd.nband * hd.nrecl;
+      if (need > stage_bytes) {
+        if (stage) cudaFreeHost(stage);
+        CUDA_OK(cudaMallocHost((void**)&stage, need));
+        stage_bytes = need;
+      }
+      CUDA_OK(cudaStreamSynchronize(g_stream));
+      src.read(stage, (base + 1) * hd.nrecl, need);
+      from = stage;
+    }
+    CUDA_OK(cudaMemcpy2DAsync(wf->C[kap].p, ld * sizeof(float2), from, hd.nrecl,
+                              (size_t)kp.nplane * sizeof(float2), hd.nband, cudaMemcpyHostToDevice,
+                              g_stream));
+  }
+  CUDA_OK(cudaStreamSynchronize(g_stream));
+  if (stage) cudaFreeHost(stage);
+  return wf.release();
+}
+
+// ---- inverse scatter map -------------------------------------------------------------------
+DevBuf build_inverse_map(const pawb200_pswf* wf, int kap, const int* fftg, std::vector<int>* fwd = nullptr) {
+  const KPointInfo& kp = wf->kp[kap];
+  const int npw = wf->npw_half(kap);
+  const long ngrid = (long)fftg[0] * fftg[1] * fftg[2];
+  std::vector<int> inv(ngrid, -1);
+  if (fwd) fwd->resize(npw);
+  for (int w = 0; w < npw; w++) {
+    const int g1 = (kp.G[3 * w] + fftg[0]) % fftg[0];
+    const int g2 = (kp.G[3 * w + 1] + fftg[1]) % fftg[1];
+    const int g3 = (kp.G[3 * w + 2] + fftg[2]) % fftg[2];
+    if (g1 < 0 || g2 < 0 || g3 < 0) throw std::runtime_error("FFT grid smaller than the G range");
+    const long lin = ((long)g1 * fftg[1] + g2) * fftg[2] + g3;
+    inv[lin] = w;   // later plane waves overwrite earlier ones, like linalg.c:31
+    if (fwd) (*fwd)[w] = (int)lin;
+  }
+  return upload(inv);
+}
+
+void launch_scatter(const pawb200_pswf* wf, int kap, int slot0, int nslot, const DevBuf& inv,
+                    double2* x, const int* fftg) {
+  const long ngrid = (long)fftg[0] * fftg[1] * fftg[2];
+  const double scale = std::pow(determinant3(wf->lattice), -0.5);   // linalg.c:34
+  const int h = wf->halves();
+  if (slot0 % h) throw std::runtime_error("slot batches must start on a band boundary");
+  const int threads = 256;
+  long blocks = std::min<long>((ngrid + threads - 1) / threads, (long)g_num_sms * 16);
+  ScopedStage tm(ST_SCATTER);
+  scatter_pw_kernel<<<(unsigned)blocks, threads, 0, g_stream>>>(
+      wf->C[kap].as<float2>(), wf->ldc[kap], slot0 / h, h, wf->npw_half(kap), inv.as<int>(), x, ngrid,
+      nslot, scale);
+  count_launch();
+  check_launch();
+}
+
+void launch_fft(double2* x, const int* fftg, int batch, int direction) {
+  cufftHandle plan = get_plan(fftg, batch);
+  ScopedStage tm(ST_FFT);
+  CUFFT_OK(cufftExecZ2Z(plan, (cufftDoubleComplex*)x, (cufftDoubleComplex*)x, direction));
+}
+
+template <int MT>
+void launch_project_mt(const SiteTables& T, const double2* x, long ngrid, int nslot, double2* P,
+                       long ldp, int slot0) {
+  if (T.by_mt[MT].empty()) return;
+  static bool configured = false;
+  const size_t smem = sphere_project_smem(MT);
+  if (!configured) {
+    CUDA_OK(cudaFuncSetAttribute(sphere_project_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem));
+    configured = true;
+  }
+  dim3 grid((nslot + PROJ_NB - 1) / PROJ_NB, (unsigned)T.by_mt[MT].size());
+  sphere_project_kernel<MT><<<grid, 128, smem, g_stream>>>(
+      T.sites.as<SiteDev>(), T.by_mt_dev[MT].as<int>(), T.idx.as<int>(), T.tablek.as<double2>(), x, ngrid,
+      nslot, P, ldp, slot0);
+  count_launch();
+  check_launch();
+}
+
+void launch_project(const SiteTables& T, const double2* x, long ngrid, int nslot, double2* P, long ldp,
+                    int slot0) {
+  ScopedStage tm(ST_PROJECT);
+  launch_project_mt<1>(T, x, ngrid, nslot, P, ldp, slot0);
+  launch_project_mt<2>(T, x, ngrid, nslot, P, ldp, slot0);
+  launch_project_mt<3>(T, x, ngrid, nslot, P, ldp, slot0);
+}
+
+void make_phase_table(SiteTables& T, const pawb200_pswf* wf, int kap, const int* fftg) {
+  if (T.nsites == 0 || T.total_pts == 0) return;
+  T.tablek.ensure(std::max<size_t>(1, T.total_tab) * sizeof(double2));
+  double kc[3] = {wf->kp[kap].k[0], wf->kp[kap].k[1], wf->kp[kap].k[2]};
+  frac_to_cart(kc, wf->reclattice);                                           // projector.c:233-237
+  const double dv = determinant3(wf->lattice) / fftg[0] / fftg[1] / fftg[2];   // projector.c:229
+  int maxpts = 0;
+  for (auto& sd : T.host) maxpts = std::max(maxpts, sd.npts_pad);
+  dim3 grid((maxpts + 255) / 256, T.nsites);
+  ScopedStage tm(ST_TABLE);
+  phase_table_kernel<<<grid, 256, 0, g_stream>>>(T.sites.as<SiteDev>(), T.path.as<double>(), T.total_pts,
+                                                 T.table.as<double2>(), T.tablek.as<double2>(), kc[0],
+                                                 kc[1], kc[2], dv);
+  count_launch();
+  check_launch();
+}
+
+DevBuf g_grid;   // FFT box batch, reused across calls
+
+// All bands of all resident (k,spin) blocks of `wf` -> <table|psi~>, written to out[kap] [nslot][ld].
+void project_all_bands(pawb200_pswf* wf, SiteTables& T, const int* fftg, std::vector<DevBuf>& out,
+                       long& ld) {
+  const int NK = wf->nkappa();
+  const long ngrid = (long)fftg[0] * fftg[1] * fftg[2];
+  ld = ((long)std::max(T.nproj, 1) + 7) / 8 * 8;
+  out.clear();
+  out.resize(NK);
+  const int nslot = wf->nslot();
+  long batch = (long)(fft_budget_bytes() / (sizeof(double2) * ngrid));
+  batch = std::max<long>(batch, wf->halves());
+  if (batch >= 32) batch = batch / 32 * 32;
+  batch -= batch % wf->halves();
+  batch = std::min<long>(batch, nslot);
+  g_grid.ensure((size_t)batch * ngrid * sizeof(double2));
+  for (int kap = 0; kap < NK; kap++) {
+    if (!wf->resident[kap]) continue;
+    out[kap].alloc((size_t)nslot * ld * sizeof(double2));
+    out[kap].zero();
+    if (T.nsites == 0) continue;
+    DevBuf inv = build_inverse_map(wf, kap, fftg);
+    make_phase_table(T, wf, kap, fftg);
+    for (int s0 = 0; s0 < nslot; s0 += (int)batch) {
+      const int nb = (int)std::min<long>(batch, nslot - s0);
+      launch_scatter(wf, kap, s0, nb, inv, g_grid.as<double2>(), fftg);
+      launch_fft(g_grid.as<double2>(), fftg, nb, CUFFT_INVERSE);
+      launch_project(T, g_grid.as<double2>(), ngrid, nb, out[kap].as<double2>(), ld, s0);
+    }
+    CUDA_OK(cudaStreamSynchronize(g_stream));   // inv is freed at scope exit
+  }
+}
+
+// ---- GEMM driver ------------------------------------------------------------------------------
+DevBuf g_zg_ws;
+
+template <typename T>
+void run_zgemm(const T* A, long lda, const T* B, long ldb, int M, int N, long Kpad, double2* out,
+               long ldo, bool accumulate, int stage) {
+  static bool configured = false;
+  constexpr size_t smem = zgemm_smem_bytes<T>();
+  if (!configured) {
+    CUDA_OK(cudaFuncSetAttribute(zgemm_abh_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  if (M == 0 || N == 0) return;
+  ZgPlan plan;
+  plan.M = M; plan.N = N;
+  plan.tiles_m = (M + ZG_BM - 1) / ZG_BM;
+  plan.tiles_n = (N + ZG_BN - 1) / ZG_BN;
+  if (Kpad % ZgTraits<T>::KT) throw std::runtime_error("GEMM K dimension is not padded");
+  plan.kiters = Kpad / ZgTraits<T>::KT;
+  if (plan.kiters == 0) {
+    if (!accumulate) CUDA_OK(cudaMemset2DAsync(out, ldo * sizeof(double2), 0, N * sizeof(double2), M, g_stream));
+    return;
+  }
+  plan.total = (long)plan.tiles_m * plan.tiles_n * plan.kiters;
+  plan.G = (int)std::min<long>(2L * g_num_sms, plan.total);
+  g_zg_ws.ensure((size_t)plan.G * 2 * ZG_BM * ZG_BN * sizeof(double2));
+  ScopedStage tm(stage);
+  zgemm_abh_kernel<T><<<plan.G, ZG_THREADS, smem, g_stream>>>(A, lda, B, ldb, plan, out, ldo,
+                                                               accumulate ? 1 : 0, g_zg_ws.as<double2>());
+  count_launch();
+  check_launch();
+  zgemm_fixup_kernel<<<plan.tiles_m * plan.tiles_n, 256, 0, g_stream>>>(plan, g_zg_ws.as<double2>(), out,
+                                                                         ldo, accumulate ? 1 : 0);
+  count_launch();
+  check_launch();
+}
+
+int flipped(const pawb200_pswf* wf, int kap, int flip) {
+  if (wf->nspin == 2 && flip) return kap < wf->nwk ? kap + wf->nwk : kap - wf->nwk;
+  return kap;
+}
+
+void check_pair(const pawb200_pswf* S, const pawb200_pswf* R) {
+  if (!S || !R) throw std::runtime_error("NULL wavefunction pointer");
+  if (S->nwk != R->nwk || S->nspin != R->nspin)
+    throw std::runtime_error("wavefunctions have different k-point / spin counts (the reference reads out "
+                             "of bounds here, SURVEY 8b); refusing");
+  if (S->ncl || R->ncl) throw std::runtime_error("band-pair overlaps are not defined for noncollinear input "
+                                                 "(projector.py:74-75)");
+}
+
+// pseudo overlap block for one kappa into dev [nbS][nbR]
+void pseudo_block(pawb200_pswf* S, pawb200_pswf* R, int kap, int flip, double2* out, long ldo) {
+  const int kr = flipped(R, kap, flip);
+  if (!S->resident[kap] || !R->resident[kr]) throw std::runtime_error("(k,spin) block not resident on this rank");
+  // the reference takes num_waves from wf_ref->kpts[kpt_num] (pseudoprojector.c:84) for both vectors
+  if (S->kp[kap].nplane != R->kp[kr].nplane)
+    throw std::runtime_error("plane-wave bases differ between the two wavefunctions at kappa " + std::to_string(kap));
+  run_zgemm<float2>(S->C[kap].as<float2>(), S->ldc[kap], R->C[kr].as<float2>(), R->ldc[kr], S->nband,
+                    R->nband, S->ldc[kap], out, ldo, false, ST_GEMM_PS);
+}
+
+struct SiteLists {
+  std::vector<int> M_R, M_S, N_R, N_S, N_RS_R, N_RS_S;
+  size_t hash() const {
+    size_t h = 1469598103934665603ull;
+    for (auto* v : {&M_R, &M_S, &N_R, &N_S, &N_RS_R, &N_RS_S}) {
+      int n = (int)v->size();
+      h = hash_bytes(&n, sizeof(n), h);
+      if (n) h = hash_bytes(v->data(), n * sizeof(int), h);
+    }
+    return h;
+  }
+};
+
+SiteLists make_lists(int num_M, int num_N_R, int num_N_S, int num_N_RS, const int* M_R, const int* M_S,
+                     const int* N_R, const int* N_S, const int* N_RS_R, const int* N_RS_S) {
+  SiteLists L;
+  auto cp = [](std::vector<int>& d, const int* s, int n) { if (n > 0 && s) d.assign(s, s + n); };
+  cp(L.M_R, M_R, num_M); cp(L.M_S, M_S, num_M);
+  cp(L.N_R, N_R, num_N_R); cp(L.N_S, N_S, num_N_S);
+  cp(L.N_RS_R, N_RS_R, num_N_RS); cp(L.N_RS_S, N_RS_S, num_N_RS);
+  return L;
+}
+
+// Augmentation operands (see kernels.cuh block_apply_kernel) and the c128 GEMM, for one kappa.
+struct AugPlan {
+  std::vector<BlockOp> opsS, opsR_P, opsR_W, opsS_W;   // ops reading P_S / P_R / W_R / W_S
+  std::vector<cdouble> mats;                           // k-independent matrices (D blocks)
+  std::vector<std::pair<int, long>> rs_mats;           // (pair index, offset) of k-dependent blocks
+  long K = 0, Kpad = 0;
+};
+
+AugPlan plan_aug(const pawb200_pswf* S, const pawb200_pswf* R, const SiteLists& L) {
+  if (!S->has_projections || !R->has_projections)
+    throw std::runtime_error("setup_projections has not been run on both wavefunctions");
+  const auto& elsR = R->pps->list.el;
+  const auto& elsS = S->pps->list.el;
+  AugPlan A;
+  long col = 0;
+  auto siteR = [&](int s) -> const SiteDev& {
+    if (s < 0 || s >= R->num_sites) throw std::runtime_error("site index out of range (basis)");
+    return R->proj_sites->host[s];
+  };
+  auto siteS = [&](int s) -> const SiteDev& {
+    if (s < 0 || s >= S->num_sites) throw std::runtime_error("site index out of range (wf)");
+    return S->proj_sites->host[s];
+  };
+  // O_M  (projector.c:890-910)
+  for (size_t q = 0; q < L.M_R.size(); q++) {
+    const SiteDev &r = siteR(L.M_R[q]), &s = siteS(L.M_S[q]);
+    const Element& pp = elsR[R->labels[L.M_R[q]]];
+    const Element& ps = elsS[S->labels[L.M_S[q]]];
+    const long off = (long)A.mats.size();
+    for (int i = 0; i < r.nlm; i++)
+      for (int j = 0; j < s.nlm; j++) {
+        const Channel &ci = pp.chan[i], &cj = ps.chan[j];
+        double v = 0;
+        if (ci.l == cj.l && ci.m == cj.m) {
+          if (cj.n >= pp.num_projs) throw std::runtime_error("matched sites carry different PAW datasets");
+          v = pp.aeov[ci.n * pp.num_projs + cj.n] - pp.psov[ci.n * pp.num_projs + cj.n];
+        }
+        A.mats.push_back(cdouble(v, 0));
+      }
+    A.opsR_P.push_back({r.lm_off, (int)col, r.nlm, 0, -1});
+    A.opsS.push_back({s.lm_off, (int)col, r.nlm, s.nlm, off});
+    col += r.nlm;
+  }
+  // O_R  (:915-924): W_S (S bands on R's N_R sites) against P_R
+  if (!L.N_R.empty()) {
+    if (S->wp_num != (int)L.N_R.size()) throw std::runtime_error("overlap_setup_real was not run for these site lists");
+    int woff = 0;
+    for (size_t q = 0; q < L.N_R.size(); q++) {
+      const SiteDev& r = siteR(L.N_R[q]);
+      if (S->wp_nlm[q] != r.nlm) throw std::runtime_error("wave-projection channel mismatch (N_R)");
+      A.opsR_P.push_back({r.lm_off, (int)col, r.nlm, 0, -1});
+      A.opsS_W.push_back({woff, (int)col, r.nlm, 0, -1});
+      woff += r.nlm;
+      col += r.nlm;
+    }
+  }
+  // O_S  (:929-938): W_R (R bands on S's N_S sites) against P_S
+  if (!L.N_S.empty()) {
+    if (R->wp_num != (int)L.N_S.size()) throw std::runtime_error("overlap_setup_real was not run for these site lists");
+    int woff = 0;
+    for (size_t q = 0; q < L.N_S.size(); q++) {
+      const SiteDev& s = siteS(L.N_S[q]);
+      if (R->wp_nlm[q] != s.nlm) throw std::runtime_error("wave-projection channel mismatch (N_S)");
+      A.opsR_W.push_back({woff, (int)col, s.nlm, 0, -1});
+      A.opsS.push_back({s.lm_off, (int)col, s.nlm, 0, -1});
+      woff += s.nlm;
+      col += s.nlm;
+    }
+  }
+  // O_N  (:944-959)
+  if (!L.N_RS_R.empty()) {
+    if (S->omega.size() != L.N_RS_R.size()) throw std::runtime_error("off-site overlaps missing: run overlap_setup_real");
+    for (size_t q = 0; q < L.N_RS_R.size(); q++) {
+      const SiteDev &r = siteR(L.N_RS_R[q]), &s = siteS(L.N_RS_S[q]);
+      if (S->omega_n1[q] != r.nlm || S->omega_n2[q] != s.nlm) throw std::runtime_error("off-site block shape mismatch");
+      const long off = (long)A.mats.size();
+      A.mats.resize(A.mats.size() + (size_t)r.nlm * s.nlm);
+      A.rs_mats.push_back({(int)q, off});
+      A.opsR_P.push_back({r.lm_off, (int)col, r.nlm, 0, -1});
+      A.opsS.push_back({s.lm_off, (int)col, r.nlm, s.nlm, off});
+      col += r.nlm;
+    }
+  }
+  A.K = col;
+  A.Kpad = (col + 7) / 8 * 8;
+  return A;
+}
+
+void apply_ops(const std::vector<BlockOp>& ops, const DevBuf& mats, const double2* src, long lds, double2* dst,
+               long ldd, int nrows) {
+  if (ops.empty()) return;
+  DevBuf d = upload(ops);
+  dim3 grid(std::min(nrows, 4096), (unsigned)ops.size());
+  block_apply_kernel<<<grid, 128, 0, g_stream>>>(d.as<BlockOp>(), mats.as<double2>(), src, lds, dst, ldd, nrows);
+  count_launch();
+  check_launch();
+  CUDA_OK(cudaStreamSynchronize(g_stream));
+}
+
+void aug_block(pawb200_pswf* S, pawb200_pswf* R, AugPlan& A, int kap, int flip, double2* out, long ldo,
+               bool accumulate) {
+  if (A.K == 0) {
+    if (!accumulate)
+      CUDA_OK(cudaMemset2DAsync(out, ldo * sizeof(double2), 0, R->nband * sizeof(double2), S->nband, g_stream));
+    return;
+  }
+  const int kr = flipped(R, kap, flip);
+  if (!S->resident[kap] || !R->resident[kr]) throw std::runtime_error("(k,spin) block not resident on this rank");
+  // k-dependent off-site blocks: Omega * exp(2 pi i k_R . d)   (projector.c:953-955)
+  for (auto& pr : A.rs_mats) {
+    const int q = pr.first;
+    const double* d = S->dcoords.data() + 3 * q;
+    const double* k = R->kp[kr].k;
+    const double ang = 2 * kPi * (k[0] * d[0] + k[1] * d[1] + k[2] * d[2]);
+    const cdouble ph = std::exp(cdouble(0, 1) * ang);
+    for (size_t e = 0; e < S->omega[q].size(); e++) A.mats[pr.second + e] = S->omega[q][e] * ph;
+  }
+  DevBuf mats = upload(A.mats.empty() ? std::vector<cdouble>(1) : A.mats);
+  DevBuf opS((size_t)S->nband * A.Kpad * sizeof(double2)), opR((size_t)R->nband * A.Kpad * sizeof(double2));
+  {
+    ScopedStage tm(ST_GEMM_AUG);
+    opS.zero();
+    opR.zero();
+    apply_ops(A.opsS, mats, S->P[kap].as<double2>(), S->ldp, opS.as<double2>(), A.Kpad, S->nband);
+    apply_ops(A.opsS_W, mats, S->W.empty() ? nullptr : S->W[kap].as<double2>(), S->ldw, opS.as<double2>(), A.Kpad, S->nband);
+    apply_ops(A.opsR_P, mats, R->P[kr].as<double2>(), R->ldp, opR.as<double2>(), A.Kpad, R->nband);
+    apply_ops(A.opsR_W, mats, R->W.empty() ? nullptr : R->W[kr].as<double2>(), R->ldw, opR.as<double2>(), A.Kpad, R->nband);
+  }
+  run_zgemm<double2>(opS.as<double2>(), A.Kpad, opR.as<double2>(), A.Kpad, S->nband, R->nband, A.Kpad, out, ldo,
+                     accumulate, ST_GEMM_AUG);
+  CUDA_OK(cudaStreamSynchronize(g_stream));
+}
+
+// Full block(s) to host: out[kap - lo][bS][bR]
+void overlap_matrix(pawb200_pswf* S, pawb200_pswf* R, const SiteLists* L, int flip, int lo, int hi,
+                    bool pseudo, bool aug, cdouble* out) {
+  check_pair(S, R);
+  const int nS = S->nband, nR = R->nband;
+  DevBuf blk((size_t)nS * nR * sizeof(double2));
+  AugPlan A;
+  if (aug) A = plan_aug(S, R, *L);
+  for (int kap = lo; kap < hi; kap++) {
+    cdouble* dst = out + (size_t)(kap - lo) * nS * nR;
+    const int kr = flipped(R, kap, flip);
+    if (!S->resident[kap] || !R->resident[kr]) {
+      std::fill(dst, dst + (size_t)nS * nR, cdouble(0, 0));   // another rank's block
+      continue;
+    }
+    if (pseudo) pseudo_block(S, R, kap, flip, blk.as<double2>(), nR);
+    if (aug) aug_block(S, R, A, kap, flip, blk.as<double2>(), nR, pseudo);
+    ScopedStage tm(ST_D2H);
+    CUDA_OK(cudaMemcpyAsync(dst, blk.p, (size_t)nS * nR * sizeof(double2), cudaMemcpyDeviceToHost, g_stream));
+    CUDA_OK(cudaStreamSynchronize(g_stream));
+  }
+}
+
+// ---- real-space states -----------------------------------------------------------------------
+SiteTables& ae_tables(pawb200_pswf* wf, const int* fftg, const int* labels, const double* coords) {
+  if (!wf->has_projections) throw std::runtime_error("setup_projections has not been run");
+  const size_t h = hash_bytes(coords, sizeof(double) * 3 * wf->num_sites, hash_bytes(labels, sizeof(int) * wf->num_sites));
+  if (!wf->ae_sites || wf->ae_sites->fftg[0] != fftg[0] || wf->ae_sites->fftg[1] != fftg[1] ||
+      wf->ae_sites->fftg[2] != fftg[2] || wf->ae_sites->coord_hash != h) {
+    std::vector<int> all(wf->num_sites);
+    for (int i = 0; i < wf->num_sites; i++) all[i] = i;
+    wf->ae_sites = build_site_tables(wf->pps->list.el, all.data(), wf->num_sites, labels, coords, wf->lattice,
+                                     fftg, 2, false);
+    wf->ae_sites->coord_hash = h;
+  }
+  return *wf->ae_sites;
+}
+
+// boxes for slots [slot0, slot0+nslot) of kappa, AE-augmented, left in g_grid
+void realspace_boxes(pawb200_pswf* wf, int kap, int slot0, int nslot, const int* fftg, SiteTables& T,
+                     const DevBuf& inv) {
+  const long ngrid = (long)fftg[0] * fftg[1] * fftg[2];
+  g_grid.ensure((size_t)nslot * ngrid * sizeof(double2));
+  double2* x = g_grid.as<double2>();
+  launch_scatter(wf, kap, slot0, nslot, inv, x, fftg);
+  launch_fft(x, fftg, nslot, CUFFT_INVERSE);
+  const double* k = wf->kp[kap].k;
+  ScopedStage tm(ST_AUGMENT);
+  const long blocks = std::min<long>((ngrid + 255) / 256, (long)g_num_sms * 16);
+  bloch_phase_kernel<<<(unsigned)blocks, 256, 0, g_stream>>>(x, fftg[0], fftg[1], fftg[2], k[0], k[1], k[2], 1.0, nslot);
+  count_launch();
+  check_launch();
+  if (T.nsites && T.total_pts) {
+    int maxpts = 0, maxlm = 0;
+    for (auto& sd : T.host) { maxpts = std::max(maxpts, sd.npts); maxlm = std::max(maxlm, sd.nlm); }
+    // P rows of these slots: sites are in structure order so lm offsets coincide with proj_sites
+    constexpr int NBMAX = 32;
+    for (int b0 = 0; b0 < nslot; b0 += NBMAX) {
+      const int nb = std::min(NBMAX, nslot - b0);
+      dim3 grid(std::max(1, (maxpts + 255) / 256), T.nsites);
+      augment_add_kernel<<<grid, 256, sizeof(double2) * nb * maxlm, g_stream>>>(
+          T.sites.as<SiteDev>(), T.idx.as<int>(), T.wrap.as<int>(), T.total_pts, T.table.as<double2>(),
+          wf->P[kap].as<double2>() + (long)(slot0 + b0) * wf->ldp, wf->ldp, nb, x + (long)b0 * ngrid, ngrid,
+          k[0], k[1], k[2]);
+      count_launch();
+      check_launch();
+    }
+  }
+}
+
+void check_kpoint(const pawb200_pswf* wf, int band, int kap) {
+  if (!wf) throw std::runtime_error("NULL wavefunction pointer");
+  if (band < 0 || band >= wf->nband) throw std::runtime_error("band index out of range");
+  if (kap < 0 || kap >= wf->nkappa()) throw std::runtime_error("k-point/spin index out of range");
+  if (!wf->resident[kap]) throw std::runtime_error("(k,spin) block not resident on this rank");
+}
+
+void state_to_host(pawb200_c128* out, int band, int kap, pawb200_pswf* wf, const int* fftg, const int* labels,
+                   const double* coords) {
+  require_device();
+  check_kpoint(wf, band, kap);
+  SiteTables& T = ae_tables(wf, fftg, labels, coords);
+  DevBuf inv = build_inverse_map(wf, kap, fftg);
+  const int h = wf->halves();
+  realspace_boxes(wf, kap, band * h, h, fftg, T, inv);
+  const long ngrid = (long)fftg[0] * fftg[1] * fftg[2];
+  ScopedStage tm(ST_D2H);
+  CUDA_OK(cudaMemcpyAsync(out, g_grid.p, (size_t)h * ngrid * sizeof(double2), cudaMemcpyDeviceToHost, g_stream));
+  CUDA_OK(cudaStreamSynchronize(g_stream));
+}
+
+void density_to_host(double* Pout, pawb200_pswf* wf, const int* fftg, const int* labels, const double* coords,
+                     int only_band, int only_kap) {
+  require_device();
+  if (!wf) throw std::runtime_error("NULL wavefunction pointer");
+  SiteTables& T = ae_tables(wf, fftg, labels, coords);
+  const long ngrid = (long)fftg[0] * fftg[1] * fftg[2];
+  const int h = wf->halves();
+  DevBuf rho(ngrid * sizeof(double));
+  rho.zero();
+  long batch = std::max<long>(1, (long)(fft_budget_bytes() / (sizeof(double2) * ngrid)) / h);
+  batch = std::min<long>(batch, 64);
+  const double spin_mult = wf->ncl ? 1.0 : 2 / wf->nspin;   // density.c:164, 187
+  for (int kap = 0; kap < wf->nkappa(); kap++) {
+    if (only_kap >= 0 && kap != only_kap) continue;
+    if (!wf->resident[kap]) continue;
+    std::vector<int> bands;
+    std::vector<double> wts;
+    if (only_band >= 0) {
+      bands.push_back(only_band);
+      wts.push_back(1.0);                                    // ae_state_density, density.c:35-37
+    } else {
+      for (int b = 0; b < wf->nband; b++)
+        if (wf->kp[kap].occ[b] > 0) {                        // density.c:168
+          bands.push_back(b);
+          wts.push_back(wf->weight[kap] * wf->kp[kap].occ[b] * spin_mult);
+        }
+    }
+    if (bands.empty()) continue;
+    DevBuf inv = build_inverse_map(wf, kap, fftg);
+    // occupied bands are contiguous in practice; process maximal runs in batches
+    size_t i = 0;
+    while (i < bands.size()) {
+      size_t j = i + 1;
+      while (j < bands.size() && bands[j] == bands[j - 1] + 1 && (long)(j - i) < batch) j++;
+      const int nb = (int)(j - i);
+      realspace_boxes(wf, kap, bands[i] * h, nb * h, fftg, T, inv);
+      std::vector<double> w(nb * h);
+      for (int q = 0; q < nb; q++)
+        for (int hh = 0; hh < h; hh++) w[q * h + hh] = wts[i + q];
+      DevBuf dw = upload(w);
+      const long blocks = std::min<long>((ngrid + 255) / 256, (long)g_num_sms * 16);
+      ScopedStage tm(ST_AUGMENT);
+      density_accum_kernel<<<(unsigned)blocks, 256, 0, g_stream>>>(g_grid.as<double2>(), ngrid, nb * h,
+                                                                   dw.as<double>(), rho.as<double>());
+      count_launch();
+      check_launch();
+      CUDA_OK(cudaStreamSynchronize(g_stream));
+      i = j;
+    }
+  }
+  std::vector<double> hrho(ngrid);
+  CUDA_OK(cudaMemcpy(hrho.data(), rho.p, ngrid * sizeof(double), cudaMemcpyDeviceToHost));
+  for (long g = 0; g < ngrid; g++) Pout[g] += hrho[g];     // the reference accumulates into P
+}
+
+}  // namespace
+
+// =======================================================================================
+// C ABI
+// =======================================================================================
+extern "C" {
+
+const char* pawb200_last_error(void) { return g_has_error ? g_error.c_str() : nullptr; }
+void pawb200_clear_error(void) { g_has_error = false; }
+const char* pawb200_version(void) { return "pawpyseed_b200 0.1 (sm_100a)"; }
+
+int pawb200_device_check(void) {
+  API_BEGIN
+  require_device();
+  return 0;
+  API_END(-1)
+}
+
+void pawb200_set_read_shard(int rank, int world) {
+  if (world < 1) world = 1;
+  g_shard_rank = ((rank % world) + world) % world;
+  g_shard_world = world;
+}
+
+pawb200_pswf_t* pawb200_read_wavefunctions(const char* filename, const double* kws) {
+  API_BEGIN
+  ByteSource s;
+  s.fp = fopen(filename, "rb");
+  if (!s.fp) throw std::runtime_error(std::string("cannot open ") + filename);
+  pawb200_pswf* wf = nullptr;
+  try {
+    wf = ingest(s, kws);
+  } catch (...) {
+    fclose(s.fp);
+    throw;
+  }
+  fclose(s.fp);
+  return wf;
+  API_END(nullptr)
+}
+
+pawb200_pswf_t* pawb200_read_wavefunctions_from_str(const char* start, const double* kws) {
+  API_BEGIN
+  if (!start) throw std::runtime_error("NULL WAVECAR buffer");
+  ByteSource s;
+  s.mem = (const unsigned char*)start;
+  return ingest(s, kws);
+  API_END(nullptr)
+}
+
+void pawb200_free_pswf(pawb200_pswf_t* wf) {
+  if (!wf) return;
+  cudaStreamSynchronize(g_stream);
+  delete wf;
+}
+
+int pawb200_get_nband(pawb200_pswf_t* wf) { return wf ? wf->nband : 0; }
+int pawb200_get_nwk(pawb200_pswf_t* wf) { return wf ? wf->nwk : 0; }
+int pawb200_get_nspin(pawb200_pswf_t* wf) { return wf ? wf->nspin : 0; }
+int pawb200_is_ncl(pawb200_pswf_t* wf) { return wf ? wf->ncl : 0; }
+double pawb200_get_encut(pawb200_pswf_t* wf) { return wf ? wf->encut : 0; }
+
+double pawb200_get_energy(pawb200_pswf_t* wf, int band, int kpt, int spin) {
+  API_BEGIN
+  const int kap = kpt + spin * wf->nwk;
+  if (!wf || band < 0 || band >= wf->nband || kap < 0 || kap >= wf->nkappa()) throw std::runtime_error("index out of range");
+  return wf->kp[kap].energy[band];
+  API_END(NAN)
+}
+double pawb200_get_occ(pawb200_pswf_t* wf, int band, int kpt, int spin) {
+  API_BEGIN
+  const int kap = kpt + spin * wf->nwk;
+  if (!wf || band < 0 || band >= wf->nband || kap < 0 || kap >= wf->nkappa()) throw std::runtime_error("index out of range");
+  return wf->kp[kap].occ[band];
+  API_END(NAN)
+}
+double* pawb200_get_occs(pawb200_pswf_t* wf) {
+  if (!wf) return nullptr;
+  const int NK = wf->nkappa();
+  double* o = (double*)malloc(sizeof(double) * NK * wf->nband);
+  for (int k = 0; k < NK; k++)
+    for (int b = 0; b < wf->nband; b++) o[b * NK + k] = wf->kp[k].occ[b];
+  return o;
+}
+void pawb200_set_num_sites(pawb200_pswf_t* wf, int nsites) { if (wf) wf->num_sites = nsites; }
+void pawb200_free_ptr(void* p) { free(p); }
+
+pawb200_ppot_t* pawb200_get_projector_list(int num_els, const int* labels, const int* ls, const double* wave_grids,
+                                           const double* projectors, const double* aewaves,
+                                           const double* pswaves, const double* rmaxs, double grid_encut) {
+  API_BEGIN
+  auto p = std::make_unique<pawb200_ppot>();
+  p->list.el = build_elements(num_els, labels, ls, wave_grids, projectors, aewaves, pswaves, rmaxs, grid_encut);
+  return p.release();
+  API_END(nullptr)
+}
+void pawb200_free_ppot_list(pawb200_ppot_t* pps, int) { delete pps; }
+
+void pawb200_setup_projections(pawb200_pswf_t* wf, pawb200_ppot_t* pps, int num_elems, int num_sites,
+                               const int* fftg, const int* labels, const double* coords) {
+  API_BEGIN
+  require_device();
+  if (!wf || !pps) throw std::runtime_error("NULL argument");
+  if ((int)pps->list.el.size() != num_elems) throw std::runtime_error("num_elems does not match the projector list");
+  for (int s = 0; s < num_sites; s++)
+    if (labels[s] < 0 || labels[s] >= num_elems) throw std::runtime_error("site label out of range");
+  wf->pps.reset(pps);
+  wf->num_sites = num_sites;
+  for (int d = 0; d < 3; d++) wf->fftg[d] = fftg[d];
+  wf->labels.assign(labels, labels + num_sites);
+  wf->coords.assign(coords, coords + 3 * num_sites);
+  wf->gen++;
+  wf->ae_sites.reset();
+  wf->W.clear();
+  wf->wp_num = 0;
+  std::vector<int> all(num_sites);
+  for (int i = 0; i < num_sites; i++) all[i] = i;
+  wf->proj_sites = build_site_tables(pps->list.el, all.data(), num_sites, labels, coords, wf->lattice, fftg, 0, true);
+  project_all_bands(wf, *wf->proj_sites, fftg, wf->P, wf->ldp);
+  wf->has_projections = true;
+  API_END_VOID
+}
+
+void pawb200_projection_matrix(pawb200_c128* out, pawb200_pswf_t* wf_S, pawb200_pswf_t* wf_R, int num_M,
+                               int num_N_R, int num_N_S, int num_N_RS, const int* M_R, const int* M_S,
+                               const int* N_R, const int* N_S, const int* N_RS_R, const int* N_RS_S,
+                               int flip_spin, int kappa_lo, int kappa_hi, int pseudo_only) {
+  API_BEGIN
+  require_device();
+  check_pair(wf_S, wf_R);
+  if (kappa_lo < 0 || kappa_hi > wf_S->nkappa() || kappa_lo > kappa_hi) throw std::runtime_error("bad kappa range");
+  SiteLists L = make_lists(num_M, num_N_R, num_N_S, num_N_RS, M_R, M_S, N_R, N_S, N_RS_R, N_RS_S);
+  overlap_matrix(wf_S, wf_R, &L, flip_spin, kappa_lo, kappa_hi, true, !pseudo_only, (cdouble*)out);
+  API_END_VOID
+}
+
+void pawb200_pseudoprojection(pawb200_c128* projections, pawb200_pswf_t* wf_ref, pawb200_pswf_t* wf_proj,
+                              int BAND_NUM, int flip_spin) {
+  API_BEGIN
+  require_device();
+  check_pair(wf_proj, wf_ref);
+  if (BAND_NUM < 0 || BAND_NUM >= wf_proj->nband) throw std::runtime_error("band index out of range");
+  HostMatrixCache& c = wf_proj->pseudo_cache;
+  const int NK = wf_ref->nkappa(), nS = wf_proj->nband, nR = wf_ref->nband;
+  if (!c.valid || c.other_id != wf_ref->id || c.flip != (flip_spin ? 1 : 0)) {
+    c.data.assign((size_t)NK * nS * nR, cdouble(0, 0));
+    overlap_matrix(wf_proj, wf_ref, nullptr, flip_spin, 0, NK, true, false, c.data.data());
+    c.other_id = wf_ref->id;
+    c.flip = flip_spin ? 1 : 0;
+    c.valid = true;
+  }
+  cdouble* out = (cdouble*)projections;
+  for (int k = 0; k < NK; k++)
+    for (int b = 0; b < nR; b++) out[(size_t)b * NK + k] = c.data[((size_t)k * nS + BAND_NUM) * nR + b];
+  API_END_VOID
+}
+
+void pawb200_overlap_setup_real(pawb200_pswf_t* wf_R, pawb200_pswf_t* wf_S, const int* labels_R,
+                                const int* labels_S, const double* coords_R, const double* coords_S,
+                                const int* N_R, const int* N_S, const int* N_RS_R, const int* N_RS_S,
+                                int num_N_R, int num_N_S, int num_N_RS) {
+  API_BEGIN
+  require_device();
+  check_pair(wf_S, wf_R);
+  if (!wf_R->has_projections || !wf_S->has_projections) throw std::runtime_error("setup_projections has not been run");
+  wf_R->gen++;
+  wf_S->gen++;
+  wf_R->aug_cache.valid = wf_S->aug_cache.valid = false;
+  wf_R->W.clear(); wf_S->W.clear();
+  wf_R->wp_num = num_N_S; wf_S->wp_num = num_N_R;
+  wf_R->wp_nlm.clear(); wf_S->wp_nlm.clear();
+  const auto& elsR = wf_R->pps->list.el;
+  const auto& elsS = wf_S->pps->list.el;
+  // part 1 (projector.c:625-646): filtered partial waves of R's N_R sites on S's grid, all S bands
+  if (num_N_R > 0) {
+    auto T = build_site_tables(elsR, N_R, num_N_R, labels_R, coords_R, wf_S->lattice, wf_S->fftg, 1, false);
+    for (auto& sd : T->host) wf_S->wp_nlm.push_back(sd.nlm);
+    project_all_bands(wf_S, *T, wf_S->fftg, wf_S->W, wf_S->ldw);
+  }
+  // part 2 (:649-671)
+  if (num_N_S > 0) {
+    auto T = build_site_tables(elsS, N_S, num_N_S, labels_S, coords_S, wf_R->lattice, wf_R->fftg, 1, false);
+    for (auto& sd : T->host) wf_R->wp_nlm.push_back(sd.nlm);
+    project_all_bands(wf_R, *T, wf_R->fftg, wf_R->W, wf_R->ldw);
+  }
+  // part 3 (:682-719): off-site partial-wave overlaps, host side (O(pairs * channels^2) radial integrals)
+  wf_S->omega.assign(num_N_RS, {});
+  wf_S->dcoords.assign(3 * (size_t)num_N_RS, 0.0);
+  wf_S->omega_n1.assign(num_N_RS, 0);
+  wf_S->omega_n2.assign(num_N_RS, 0);
+#pragma omp parallel for schedule(dynamic)
+  for (int i = 0; i < num_N_RS; i++) {
+    const int s1 = N_RS_R[i], s2 = N_RS_S[i];
+    const Element& p1 = elsR[labels_R[s1]];
+    const Element& p2 = elsS[labels_S[s2]];
+    double R = 0;
+    double* d = wf_S->dcoords.data() + 3 * i;
+    min_image_path(coords_S + 3 * s2, coords_R + 3 * s1, wf_R->lattice, d, &R);
+    auto& om = wf_S->omega[i];
+    om.resize((size_t)p1.total_projs * p2.total_projs);
+    for (int a = 0; a < p1.total_projs; a++)
+      for (int b = 0; b < p2.total_projs; b++) {
+        const Channel &ca = p1.chan[a], &cb = p2.chan[b];
+        const RadialFunc &fa = p1.funcs[ca.n], &fb = p2.funcs[cb.n];
+        om[(size_t)a * p2.total_projs + b] = std::conj(offsite_overlap_recip(
+            d, p1.kwave_grid.data(), fa.kwave.data(), fa.kwave_s, p1.wave_gridsize, p2.kwave_grid.data(),
+            fb.kwave.data(), fb.kwave_s, p2.wave_gridsize, ca.l, ca.m, cb.l, cb.m));
+      }
+    wf_S->omega_n1[i] = p1.total_projs;
+    wf_S->omega_n2[i] = p2.total_projs;
+  }
+  wf_S->overlap_partner = wf_R->id;
+  API_END_VOID
+}
+
+void pawb200_compensation_terms(pawb200_c128* overlap, int BAND_NUM, pawb200_pswf_t* wf_S, pawb200_pswf_t* wf_R,
+                                int num_M, int num_N_R, int num_N_S, int num_N_RS, const int* M_R, const int* M_S,
+                                const int* N_R, const int* N_S, const int* N_RS_R, const int* N_RS_S,
+                                const int*, const double*, const int*, const double*, const int*, int spin_flip) {
+  API_BEGIN
+  require_device();
+  check_pair(wf_S, wf_R);
+  if (BAND_NUM < 0 || BAND_NUM >= wf_S->nband) throw std::runtime_error("band index out of range");
+  SiteLists L = make_lists(num_M, num_N_R, num_N_S, num_N_RS, M_R, M_S, N_R, N_S, N_RS_R, N_RS_S);
+  HostMatrixCache& c = wf_S->aug_cache;
+  const int NK = wf_R->nkappa(), nS = wf_S->nband, nR = wf_R->nband;
+  const size_t lh = L.hash();
+  if (!c.valid || c.other_id != wf_R->id || c.other_gen != wf_R->gen || c.self_gen != wf_S->gen ||
+      c.flip != (spin_flip ? 1 : 0) || c.list_hash != lh) {
+    c.data.assign((size_t)NK * nS * nR, cdouble(0, 0));
+    overlap_matrix(wf_S, wf_R, &L, spin_flip, 0, NK, false, true, c.data.data());
+    c.other_id = wf_R->id; c.other_gen = wf_R->gen; c.self_gen = wf_S->gen;
+    c.flip = spin_flip ? 1 : 0; c.list_hash = lh; c.valid = true;
+  }
+  cdouble* out = (cdouble*)overlap;
+  for (int k = 0; k < NK; k++)
+    for (int b = 0; b < nR; b++) out[(size_t)b * NK + k] += c.data[((size_t)k * nS + BAND_NUM) * nR + b];
+  API_END_VOID
+}
+
+// ---- real space ---------------------------------------------------------------------------------
+void pawb200_realspace_state(pawb200_c128* x, int BAND_NUM, int KPOINT_NUM, pawb200_pswf_t* wf, const int* fftg,
+                             const int* labels, const double* coords) {
+  API_BEGIN
+  if (wf && wf->ncl) throw std::runtime_error("noncollinear wavefunction: use pawb200_ncl_realspace_state");
+  state_to_host(x, BAND_NUM, KPOINT_NUM, wf, fftg, labels, coords);
+  API_END_VOID
+}
+void pawb200_ncl_realspace_state(pawb200_c128* x, int BAND_NUM, int KPOINT_NUM, pawb200_pswf_t* wf,
+                                 const int* fftg, const int* labels, const double* coords) {
+  API_BEGIN
+  if (wf && !wf->ncl) throw std::runtime_error("collinear wavefunction: use pawb200_realspace_state");
+  state_to_host(x, BAND_NUM, KPOINT_NUM, wf, fftg, labels, coords);
+  API_END_VOID
+}
+void pawb200_remove_phase(pawb200_c128* x, int KPOINT_NUM, pawb200_pswf_t* wf, const int* fftg) {
+  API_BEGIN
+  require_device();
+  if (!wf || KPOINT_NUM < 0 || KPOINT_NUM >= wf->nkappa()) throw std::runtime_error("k-point index out of range");
+  const long ngrid = (long)fftg[0] * fftg[1] * fftg[2];
+  g_grid.ensure(ngrid * sizeof(double2));
+  CUDA_OK(cudaMemcpyAsync(g_grid.p, x, ngrid * sizeof(double2), cudaMemcpyHostToDevice, g_stream));
+  const double* k = wf->kp[KPOINT_NUM].k;
+  const long blocks = std::min<long>((ngrid + 255) / 256, (long)g_num_sms * 16);
+  bloch_phase_kernel<<<(unsigned)blocks, 256, 0, g_stream>>>(g_grid.as<double2>(), fftg[0], fftg[1], fftg[2], k[0],
+                                                             k[1], k[2], -1.0, 1);
+  count_launch();
+  check_launch();
+  CUDA_OK(cudaMemcpyAsync(x, g_grid.p, ngrid * sizeof(double2), cudaMemcpyDeviceToHost, g_stream));
+  CUDA_OK(cudaStreamSynchronize(g_stream));
+  API_END_VOID
+}
+void pawb200_ae_state_density(double* P, int BAND_NUM, int KPOINT_NUM, pawb200_pswf_t* wf, const int* fftg,
+                              const int* labels, const double* coords) {
+  API_BEGIN
+  check_kpoint(wf, BAND_NUM, KPOINT_NUM);
+  density_to_host(P, wf, fftg, labels, coords, BAND_NUM, KPOINT_NUM);
+  API_END_VOID
+}
+void pawb200_ae_chg_density(double* P, pawb200_pswf_t* wf, const int* fftg, const int* labels, const double* coords) {
+  API_BEGIN
+  density_to_host(P, wf, fftg, labels, coords, -1, -1);
+  API_END_VOID
+}
+void pawb200_ncl_ae_chg_density(double* P, pawb200_pswf_t* wf, const int* fftg, const int* labels,
+                                const double* coords) {
+  API_BEGIN
+  density_to_host(P, wf, fftg, labels, coords, -1, -1);
+  API_END_VOID
+}
+
+void pawb200_write_volumetric(const char* filename, const double* x, const int* fftg, double scale) {
+  API_BEGIN
+  // density.c:461-477: x fastest, z slowest, "%E   " five per line.  Host I/O by design.
+  FILE* fp = fopen(filename, "w");
+  if (!fp) throw std::runtime_error(std::string("cannot open ") + filename);
+  std::vector<char> buf(1 << 20);
+  setvbuf(fp, buf.data(), _IOFBF, buf.size());
+  long t = 1;
+  for (int k = 0; k < fftg[2]; k++)
+    for (int j = 0; j < fftg[1]; j++)
+      for (int i = 0; i < fftg[0]; i++) {
+        fprintf(fp, "%E   ", x[((long)i * fftg[1] + j) * fftg[2] + k] * scale);
+        if (t % 5 == 0) fputc('\n', fp);
+        t++;
+      }
+  fclose(fp);
+  API_END_VOID
+}
+
+// ---- single-band FFT entry points ---------------------------------------------------------------
+void pawb200_fft3d(pawb200_c128* x, const int*, const double* lattice, const double*, const int* Gs,
+                   const pawb200_c64* Cs, int num_waves, const int* fftg) {
+  API_BEGIN
+  require_device();
+  const long ngrid = (long)fftg[0] * fftg[1] * fftg[2];
+  std::vector<int> inv(ngrid, -1);
+  for (int w = 0; w < num_waves; w++) {
+    const long g1 = (Gs[3 * w] + fftg[0]) % fftg[0], g2 = (Gs[3 * w + 1] + fftg[1]) % fftg[1],
+               g3 = (Gs[3 * w + 2] + fftg[2]) % fftg[2];
+    if (g1 < 0 || g2 < 0 || g3 < 0) throw std::runtime_error("FFT grid smaller than the G range");
+    inv[(g1 * fftg[1] + g2) * fftg[2] + g3] = w;
+  }
+  DevBuf dinv = upload(inv);
+  DevBuf dC((size_t)std::max(num_waves, 1) * sizeof(float2));
+  CUDA_OK(cudaMemcpyAsync(dC.p, Cs, (size_t)num_waves * sizeof(float2), cudaMemcpyHostToDevice, g_stream));
+  g_grid.ensure(ngrid * sizeof(double2));
+  const double scale = std::pow(determinant3(lattice), -0.5);
+  const long blocks = std::min<long>((ngrid + 255) / 256, (long)g_num_sms * 16);
+  scatter_pw_kernel<<<(unsigned)blocks, 256, 0, g_stream>>>(dC.as<float2>(), 0, 0, 1, num_waves, dinv.as<int>(),
+                                                            g_grid.as<double2>(), ngrid, 1, scale);
+  count_launch();
+  check_launch();
+  launch_fft(g_grid.as<double2>(), fftg, 1, CUFFT_INVERSE);
+  CUDA_OK(cudaMemcpyAsync(x, g_grid.p, ngrid * sizeof(double2), cudaMemcpyDeviceToHost, g_stream));
+  CUDA_OK(cudaStreamSynchronize(g_stream));
+  API_END_VOID
+}
+
+void pawb200_fwd_fft3d(pawb200_c128* x, const int*, const double* lattice, const double*, const int* Gs,
+                       pawb200_c64* Cs, int num_waves, const int* fftg) {
+  API_BEGIN
+  require_device();
+  const long ngrid = (long)fftg[0] * fftg[1] * fftg[2];
+  std::vector<int> gi(num_waves);
+  for (int w = 0; w < num_waves; w++) {
+    const long g1 = (Gs[3 * w] + fftg[0]) % fftg[0], g2 = (Gs[3 * w + 1] + fftg[1]) % fftg[1],
+               g3 = (Gs[3 * w + 2] + fftg[2]) % fftg[2];
+    gi[w] = (int)((g1 * fftg[1] + g2) * fftg[2] + g3);
+  }
+  DevBuf dgi = upload(gi);
+  DevBuf dC((size_t)std::max(num_waves, 1) * sizeof(float2));
+  g_grid.ensure(ngrid * sizeof(double2));
+  CUDA_OK(cudaMemcpyAsync(g_grid.p, x, ngrid * sizeof(double2), cudaMemcpyHostToDevice, g_stream));
+  launch_fft(g_grid.as<double2>(), fftg, 1, CUFFT_FORWARD);
+  const double scale = std::pow(determinant3(lattice), 0.5) / fftg[0] / fftg[1] / fftg[2];   // linalg.c:64-65
+  gather_pw_kernel<<<(num_waves + 255) / 256, 256, 0, g_stream>>>(g_grid.as<double2>(), dgi.as<int>(),
+                                                                  dC.as<float2>(), num_waves, scale);
+  count_launch();
+  check_launch();
+  // like the in-place DFTI transform, x holds the (scaled) spectrum afterwards
+  CUDA_OK(cudaMemcpyAsync(Cs, dC.p, (size_t)num_waves * sizeof(float2), cudaMemcpyDeviceToHost, g_stream));
+  CUDA_OK(cudaStreamSynchronize(g_stream));
+  API_END_VOID
+}
+
+// ---- utilities -----------------------------------------------------------------------------------
+double pawb200_legendre(int l, int m, double x) { return assoc_legendre(l, m, x); }
+void pawb200_Ylm(int l, int m, double theta, double phi, double* o) {
+  const cdouble v = sph_harm(l, m, theta, phi);
+  o[0] = v.real(); o[1] = v.imag();
+}
+void pawb200_Ylm2(int l, int m, double ct, double phi, double* o) {
+  const cdouble v = sph_harm_cos(l, m, ct, phi);
+  o[0] = v.real(); o[1] = v.imag();
+}
+void pawb200_frac_to_cartesian(double* c, const double* lattice) { frac_to_cart(c, lattice); }
+void pawb200_cartesian_to_frac(double* c, const double* rec) { cart_to_frac(c, rec); }
+double* pawb200_spline_coeff(const double* x, const double* y, int N) {
+  Spline s = make_spline(x, y, N);
+  double* o = (double*)malloc(sizeof(double) * 3 * N);
+  for (int r = 0; r < 3; r++) std::copy(s.c[r].begin(), s.c[r].end(), o + (size_t)r * N);
+  return o;
+}
+static Spline wrap_spline(const double* s3n, int n) {
+  Spline s;
+  for (int r = 0; r < 3; r++) s.c[r].assign(s3n + (size_t)r * n, s3n + (size_t)(r + 1) * n);
+  return s;
+}
+double pawb200_proj_interpolate(double r, double rmax, int size, const double* x, const double* f, const double* s) {
+  return eval_linear_grid(r, rmax, size, x, f, wrap_spline(s, size));
+}
+double pawb200_wave_interpolate(double r, int size, const double* x, const double* f, const double* s) {
+  return eval_log_grid(r, size, x, f, wrap_spline(s, size));
+}
+double pawb200_spline_integral(const double* x, const double* a, const double* s, int size) {
+  return spline_integrate(x, a, wrap_spline(s, size), size);
+}
+void pawb200_spherical_bessel_transform(double encut, int l, int N, const double* r, const double* f, double* k_out,
+                                        double* fk_out) {
+  API_BEGIN
+  BesselTransform t(encut, 0, l, N, r);   // pawpyc.pyx:143-145
+  std::vector<double> g = t.forward(f, l);
+  std::copy(t.kgrid().begin(), t.kgrid().end(), k_out);
+  std::copy(g.begin(), g.end(), fk_out);
+  API_END_VOID
+}
+void pawb200_reciprocal_offsite_wave_overlap(const double* dcoord, const double* k1, const double* f1,
+                                             const double* s1, int size1, const double* k2, const double* f2,
+                                             const double* s2, int size2, int l1, int m1, int l2, int m2,
+                                             double* o) {
+  API_BEGIN
+  const cdouble v = offsite_overlap_recip(dcoord, k1, f1, wrap_spline(s1, size1), size1, k2, f2,
+                                          wrap_spline(s2, size2), size2, l1, m1, l2, m2);
+  o[0] = v.real(); o[1] = v.imag();
+  API_END_VOID
+}
+
+// ---- extensions ------------------------------------------------------------------------------------
+void pawb200_set_kappa_range(pawb200_pswf_t* wf, int lo, int hi) {
+  if (!wf) return;
+  for (int k = 0; k < wf->nkappa(); k++)
+    if (k < lo || k >= hi) wf->resident[k] = 0;   // blocks outside the range are dropped
+}
+int pawb200_num_projections(pawb200_pswf_t* wf, int which) {
+  if (!wf) return 0;
+  if (which == 3) { int n = 0; for (int v : wf->wp_nlm) n += v; return n; }
+  return wf->proj_sites ? wf->proj_sites->nproj : 0;
+}
+int pawb200_get_projections(pawb200_pswf_t* wf, int band, int kappa, int which, pawb200_c128* out) {
+  API_BEGIN
+  check_kpoint(wf, band, kappa);
+  const int n = pawb200_num_projections(wf, which);
+  const std::vector<DevBuf>& src = which == 3 ? wf->W : wf->P;
+  const long ld = which == 3 ? wf->ldw : wf->ldp;
+  if (src.empty() || !src[kappa].p) throw std::runtime_error("projections not available");
+  int slot = band;
+  if (wf->ncl) {
+    if (which == 0) throw std::runtime_error("noncollinear: ask for up (1) or down (2) projections");
+    slot = 2 * band + (which == 2 ? 1 : 0);
+  }
+  CUDA_OK(cudaMemcpy(out, src[kappa].as<double2>() + (long)slot * ld, (size_t)n * sizeof(double2), cudaMemcpyDeviceToHost));
+  return n;
+  API_END(-1)
+}
+int pawb200_get_channel_index(pawb200_pswf_t* wf, int* out) {
+  if (!wf || !wf->proj_sites) return 0;
+  int n = 0;
+  for (int s = 0; s < wf->num_sites; s++) {
+    const Element& el = wf->pps->list.el[wf->labels[s]];
+    for (auto& c : el.chan) {
+      if (out) { out[4 * n] = s; out[4 * n + 1] = c.n; out[4 * n + 2] = c.l; out[4 * n + 3] = c.m; }
+      n++;
+    }
+  }
+  return n;
+}
+int pawb200_get_site_indices(pawb200_pswf_t* wf, int site, int* out, int capacity) {
+  if (!wf || !wf->proj_sites || site < 0 || site >= wf->num_sites) return -1;
+  const auto& v = wf->proj_sites->host_idx[site];
+  if (out) std::copy(v.begin(), v.begin() + std::min<size_t>(capacity, v.size()), out);
+  return (int)v.size();
+}
+void pawb200_get_timers(pawb200_timers* t) {
+  drain_timers();
+  t->h2d_ms = g_stage_ms[ST_H2D]; t->scatter_ms = g_stage_ms[ST_SCATTER]; t->fft_ms = g_stage_ms[ST_FFT];
+  t->project_ms = g_stage_ms[ST_PROJECT]; t->table_ms = g_stage_ms[ST_TABLE];
+  t->gemm_pseudo_ms = g_stage_ms[ST_GEMM_PS]; t->gemm_aug_ms = g_stage_ms[ST_GEMM_AUG];
+  t->augment_ms = g_stage_ms[ST_AUGMENT]; t->d2h_ms = g_stage_ms[ST_D2H];
+  t->launches = g_launches.load();
+}
+void pawb200_reset_timers(void) {
+  drain_timers();
+  for (auto& v : g_stage_ms) v = 0;
+  g_launches = 0;
+}
+
+}  // extern "C"

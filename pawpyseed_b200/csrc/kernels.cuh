@@ -1,0 +1,453 @@
+// sm_100a kernels of the PAW band-projection path (everything except the complex GEMM,
+// which lives in zgemm.cuh).  Layouts and roofline notes are in DESIGN.md; each kernel names
+// the reference loop it replaces (file:line relative to pawpyseed/core/).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pawb200 {
+
+// ---------------------------------------------------------------------------------------
+// small device helpers
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+// D(8x8) += A(8x4,row) * B(4x8,col), FP64 tensor core (SASS: DMMA.8x8x4)
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
+  return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+
+// ---------------------------------------------------------------------------------------
+// (a2) plane-wave scatter into the FFT box, fused with the zero fill  [linalg.c:22-33]
+//   x[slot][g] = inv[g] >= 0 ? scale * widen(C[slot_base(slot) + inv[g]]) : 0
+// One thread per grid point, all `nslot` boxes of the batch written from one read of inv[].
+// Writes are fully coalesced 16-B stores; algorithmic bytes = 16*N_grid + 8*npw per slot.
+//   slot -> coefficient row: band = slot / halves, half = slot % halves (noncollinear: 2)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+scatter_pw_kernel(const float2* __restrict__ C, long ldc, int band0, int halves, int half_len,
+                  const int* __restrict__ inv, double2* __restrict__ x, long ngrid, int nslot,
+                  double scale) {
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (long g = (long)blockIdx.x * blockDim.x + threadIdx.x; g < ngrid; g += stride) {
+    const int j = __ldg(inv + g);
+    if (j < 0) {
+#pragma unroll 4
+      for (int s = 0; s < nslot; s++) x[(long)s * ngrid + g] = make_double2(0.0, 0.0);
+    } else {
+#pragma unroll 4
+      for (int s = 0; s < nslot; s++) {
+        const int band = band0 + s / halves, half = s % halves;
+        const float2 c = __ldg(C + (long)band * ldc + (long)half * half_len + j);
+        x[(long)s * ngrid + g] = make_double2(scale * (double)c.x, scale * (double)c.y);
+      }
+    }
+  }
+}
+
+// (a3) gather back after a forward FFT  [linalg.c:72-77]; narrow to complex64
+__global__ void gather_pw_kernel(const double2* __restrict__ x, const int* __restrict__ gidx,
+                                 float2* __restrict__ Cout, int npw, double scale) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w < npw) {
+    const double2 v = x[gidx[w]];
+    Cout[w] = make_float2((float)(v.x * scale), (float)(v.y * scale));
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// (a4) projector / partial-wave tables on sphere points  [utils.c:547-588, 672-686]
+// One thread per (site point); evaluates the radial cubic spline once per radial channel and
+// the complex Y_lm for each m.  Geometry (index list, membership) was decided on the host.
+// ---------------------------------------------------------------------------------------
+struct ElemDev {            // per element, device pointers
+  const double* grid;       // linear radial grid (proj_grid or smooth_grid), n points
+  const double* f;          // [nfunc][n] function values
+  const double* spl;        // [nfunc][3][n] spline rows
+  const int* chan_n;        // per channel: radial index
+  const int* chan_l;
+  const int* chan_m;
+  int n, nfunc, nchan;
+  double rmax;
+};
+
+__device__ __forceinline__ double dpow_half(double v) { return sqrt(v); }
+
+__device__ double d_legendre(int l, int m, double x);
+__device__ inline double d_ifac(int n) {
+  double t = 1;
+  for (int q = 2; q <= n; q++) t *= q;
+  return t;
+}
+__device__ inline double d_legendre(int l, int m, double x) {
+  // closed sum of utils.c:377-386 for m >= 0; negative m through the symmetry relation
+  int am = m < 0 ? -m : m;
+  double total = 0;
+  for (int n = l; n >= 0 && 2 * n - l - am >= 0; n--) {
+    double term = pow(x, (double)(2 * n - l - am)) * d_ifac(2 * n) / d_ifac(2 * n - l - am) /
+                  d_ifac(n) / d_ifac(l - n);
+    total += ((l - n) & 1) ? -term : term;
+  }
+  double v = total * ((am & 1) ? -1.0 : 1.0) * pow(1 - x * x, am / 2.0) / (double)(1 << l);
+  if (m < 0) v *= ((am & 1) ? -1.0 : 1.0) * d_ifac(l - am) / d_ifac(l + am);
+  return v;
+}
+__device__ inline double2 d_ylm(int l, int m, double theta, double phi) {
+  const double PI = 3.14159265358979323846;
+  const double norm = sqrt((2 * l + 1) / (4 * PI) * d_ifac(l - m) / d_ifac(l + m));
+  const double p = norm * d_legendre(l, m, cos(theta));
+  double s, c;
+  sincos(m * phi, &s, &c);
+  return make_double2(p * c, p * s);
+}
+__device__ inline void d_angles(const double* v, double r, double* theta, double* phi) {
+  const double PI = 3.14159265358979323846;
+  if (r == 0) {
+    *theta = 0;
+    *phi = 0;
+    return;
+  }
+  *theta = acos(v[2] / r);
+  if (r - fabs(v[2]) == 0)
+    *phi = 0;
+  else
+    *phi = acos(v[0] / sqrt(v[0] * v[0] + v[1] * v[1]));
+  if (v[1] < 0) *phi = 2 * PI - *phi;
+}
+__device__ inline double d_eval_linear(double r, double rmax, int n, const double* x,
+                                       const double* f, const double* spl) {
+  if (r > x[n - 1]) return 0;
+  if (r < x[0]) return f[0];
+  int i = (int)(r / rmax * n);
+  if (i > n - 2) i = n - 2;
+  const double t = r - x[i];
+  return f[i] + t * (spl[i] + t * (spl[n + i] + t * spl[2 * n + i]));
+}
+__device__ inline double d_eval_log(double r, int n, const double* x, const double* f,
+                                    const double* spl) {
+  if (r > x[n - 1]) return 0;
+  if (r < x[0]) return f[0];
+  int i = (int)(log(r / x[0]) / log(x[1] / x[0]));
+  if (i > n - 2) i = n - 2;
+  const double t = r - x[i];
+  return f[i] + t * (spl[i] + t * (spl[n + i] + t * spl[2 * n + i]));
+}
+
+struct SiteDev {            // per site in a table set
+  int elem;                 // element label
+  int npts, npts_pad;       // real / padded point count (pad = multiple of 32)
+  long pt_off;              // offset into idx/path arrays (padded points)
+  long tab_off;             // offset (double2 elements) of table block [nlm][npts_pad]
+  int nlm, lm_off;          // channels of this site, offset into the concatenated channel axis
+  double coord[3];          // fractional position of the atom
+};
+
+// mode 0: linear-grid radial function (projector or filtered phi-phit), value = R(r) Y_lm,
+//         r from the minimum-image path of the wrapped grid point (utils.c:566-588)
+// mode 1: log-grid partial wave difference, value = R(r)/r Y_lm from the direct offset
+//         (wave_value2, utils.c:522-545)
+__global__ void __launch_bounds__(128)
+site_table_kernel(const SiteDev* __restrict__ sites, const ElemDev* __restrict__ elems,
+                  const int* __restrict__ idx, const double* __restrict__ path, long path_ld,
+                  double2* __restrict__ table, const double* __restrict__ lattice, int n0, int n1,
+                  int n2, int mode) {
+  const SiteDev sd = sites[blockIdx.y];
+  const ElemDev ed = elems[sd.elem];
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < sd.npts_pad; p += gridDim.x * blockDim.x) {
+    double2* out = table + sd.tab_off + p;
+    if (p >= sd.npts) {
+      for (int c = 0; c < sd.nlm; c++) out[(long)c * sd.npts_pad] = make_double2(0, 0);
+      continue;
+    }
+    double v[3], r;
+    if (mode == 0) {
+      const int g = idx[sd.pt_off + p];
+      const int i = g / (n1 * n2), rem = g % (n1 * n2);
+      const double fr[3] = {(double)i / n0, (double)(rem / n2) / n1, (double)(rem % n2) / n2};
+      r = INFINITY;
+      for (int a = -1; a <= 1; a++)
+        for (int b = -1; b <= 1; b++)
+          for (int c = -1; c <= 1; c++) {
+            const double t0 = fr[0] + a - sd.coord[0], t1 = fr[1] + b - sd.coord[1],
+                         t2 = fr[2] + c - sd.coord[2];
+            const double x = t0 * lattice[0] + t1 * lattice[3] + t2 * lattice[6];
+            const double y = t0 * lattice[1] + t1 * lattice[4] + t2 * lattice[7];
+            const double z = t0 * lattice[2] + t1 * lattice[5] + t2 * lattice[8];
+            const double d = sqrt(x * x + y * y + z * z);
+            if (d < r) {
+              r = d;
+              v[0] = x; v[1] = y; v[2] = z;
+            }
+          }
+    } else {
+      v[0] = path[sd.pt_off + p];
+      v[1] = path[path_ld + sd.pt_off + p];
+      v[2] = path[2 * path_ld + sd.pt_off + p];
+      r = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    }
+    double theta, phi;
+    d_angles(v, r, &theta, &phi);
+    int last_n = -1;
+    double rad = 0;
+    for (int c = 0; c < sd.nlm; c++) {
+      const int fn = ed.chan_n[c];
+      if (fn != last_n) {
+        const double* f = ed.f + (long)fn * ed.n;
+        const double* sp = ed.spl + (long)fn * 3 * ed.n;
+        if (mode == 0) {
+          rad = d_eval_linear(r, ed.rmax, ed.n, ed.grid, f, sp);
+        } else {
+          rad = d_eval_log(r, ed.n, ed.grid, f, sp);
+          rad = (r < ed.grid[0]) ? rad / ed.grid[0] : rad / r;
+        }
+        last_n = fn;
+      }
+      const double2 y = d_ylm(ed.chan_l[c], ed.chan_m[c], theta, phi);
+      out[(long)c * sd.npts_pad] = make_double2(rad * y.x, rad * y.y);
+    }
+  }
+}
+
+// Per-k projector table: Tk = conj(T) * dv * exp(i k_cart . path)   [projector.c:259-263, 269]
+// (the phase does not depend on the band, so it is folded into the table once per k-point)
+__global__ void __launch_bounds__(256)
+phase_table_kernel(const SiteDev* __restrict__ sites, const double* __restrict__ path, long path_ld,
+                   const double2* __restrict__ table, double2* __restrict__ tablek, double kx,
+                   double ky, double kz, double dv) {
+  const SiteDev sd = sites[blockIdx.y];
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < sd.npts_pad; p += gridDim.x * blockDim.x) {
+    const long q = sd.pt_off + p;
+    const double kr = kx * path[q] + ky * path[path_ld + q] + kz * path[2 * path_ld + q];
+    double s, c;
+    sincos(kr, &s, &c);
+    const double2 ph = make_double2(dv * c, dv * s);
+    for (int ch = 0; ch < sd.nlm; ch++) {
+      const long o = sd.tab_off + (long)ch * sd.npts_pad + p;
+      const double2 t = table[o];
+      tablek[o] = cmul(make_double2(t.x, -t.y), ph);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// (a5) <p_i|psi~> : sphere gather + contraction on FP64 tensor cores  [projector.c:245-272]
+//   P[slot][lm_off + lm] = sum_pt Tk[lm][pt] * x[slot][idx[pt]]
+// CTA = one site x 32 grid slots (bands); 4 warps, each owns 8 slots (one n-tile) and all
+// m-tiles.  Sphere samples are gathered with 16-B cp.async into a KT-point stage ring
+// (the gather is the HBM-bound stream: 16 B per point per band, read once); the table tile is
+// staged alongside (re-read from L2 by the other band blocks of the same site).
+// ---------------------------------------------------------------------------------------
+constexpr int PROJ_KT = 32;       // points per stage
+constexpr int PROJ_NB = 32;       // grid slots per CTA
+constexpr int PROJ_STAGES = 4;
+constexpr int PROJ_LDB = PROJ_NB + 2;   // double2 row stride of the sample tile (bank spread)
+constexpr int PROJ_LDA = PROJ_KT + 4;   // double2 row stride of the table tile
+
+template <int MT>   // m-tiles of 8 channels
+__global__ void __launch_bounds__(128)
+sphere_project_kernel(const SiteDev* __restrict__ sites, const int* __restrict__ site_list,
+                      const int* __restrict__ idx, const double2* __restrict__ tablek,
+                      const double2* __restrict__ x, long ngrid, int nslot, double2* __restrict__ P,
+                      long ldp, int slot0) {
+  const SiteDev sd = sites[site_list[blockIdx.y]];   // sites with exactly MT m-tiles
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double2* sB = reinterpret_cast<double2*>(smem_raw);                       // [ST][KT][LDB]
+  double2* sA = sB + PROJ_STAGES * PROJ_KT * PROJ_LDB;                      // [ST][8*MT][LDA]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int sbase = blockIdx.x * PROJ_NB;          // first slot of this CTA (within the batch)
+  const int nk = sd.npts_pad / PROJ_KT;
+
+  // zero the channel-padding rows of every stage once (never overwritten)
+  for (int e = tid; e < PROJ_STAGES * 8 * MT * PROJ_LDA; e += 128) {
+    const int row = (e / PROJ_LDA) % (8 * MT);
+    if (row >= sd.nlm) sA[e] = make_double2(0, 0);
+  }
+
+  auto issue = [&](int kt, int st) {
+    if (kt < nk) {
+      const int g = __ldg(idx + sd.pt_off + kt * PROJ_KT + lane);
+      double2* dstB = sB + (st * PROJ_KT + lane) * PROJ_LDB;
+#pragma unroll
+      for (int q = 0; q < PROJ_NB / 4; q++) {
+        const int sl = warp + 4 * q;
+        int s = sbase + sl;
+        if (s >= nslot) s = nslot - 1;   // tail CTA: duplicate the last slot, discarded on store
+        cp_async16(dstB + sl, x + (long)s * ngrid + g);
+      }
+      // table tile: nlm rows x 32 points; 128 threads cover 4 rows per pass
+      for (int row = warp; row < sd.nlm; row += 4)
+        cp_async16(sA + (st * 8 * MT + row) * PROJ_LDA + lane,
+                   tablek + sd.tab_off + (long)row * sd.npts_pad + kt * PROJ_KT + lane);
+    }
+    cp_async_commit();
+  };
+
+  double rr[MT][2], ii[MT][2], ri[MT][2];
+#pragma unroll
+  for (int m = 0; m < MT; m++) rr[m][0] = rr[m][1] = ii[m][0] = ii[m][1] = ri[m][0] = ri[m][1] = 0;
+
+#pragma unroll
+  for (int s = 0; s < PROJ_STAGES - 1; s++) issue(s, s);
+
+  for (int kt = 0; kt < nk; kt++) {
+    cp_async_wait<PROJ_STAGES - 2>();
+    __syncthreads();
+    issue(kt + PROJ_STAGES - 1, (kt + PROJ_STAGES - 1) % PROJ_STAGES);
+    const int st = kt % PROJ_STAGES;
+    const double2* tB = sB + st * PROJ_KT * PROJ_LDB;
+    const double2* tA = sA + st * 8 * MT * PROJ_LDA;
+#pragma unroll
+    for (int kk = 0; kk < PROJ_KT / 4; kk++) {
+      const double2 b = tB[(4 * kk + (lane & 3)) * PROJ_LDB + 8 * warp + (lane >> 2)];
+#pragma unroll
+      for (int m = 0; m < MT; m++) {
+        const double2 a = tA[(8 * m + (lane >> 2)) * PROJ_LDA + 4 * kk + (lane & 3)];
+        dmma884(rr[m][0], rr[m][1], a.x, b.x);
+        dmma884(ii[m][0], ii[m][1], a.y, b.y);
+        dmma884(ri[m][0], ri[m][1], a.x, b.y);
+        dmma884(ri[m][0], ri[m][1], a.y, b.x);
+      }
+    }
+  }
+  cp_async_wait<0>();
+
+  // D fragment: row (channel) = lane>>2, cols (slots) = 2*(lane&3)+{0,1}
+#pragma unroll
+  for (int m = 0; m < MT; m++) {
+    const int ch = 8 * m + (lane >> 2);
+    if (ch < sd.nlm) {
+#pragma unroll
+      for (int c = 0; c < 2; c++) {
+        const int s = sbase + 8 * warp + 2 * (lane & 3) + c;
+        if (s < nslot)
+          P[(long)(slot0 + s) * ldp + sd.lm_off + ch] = make_double2(rr[m][c] - ii[m][c], ri[m][c]);
+      }
+    }
+  }
+}
+
+inline size_t sphere_project_smem(int MT) {
+  return sizeof(double2) * PROJ_STAGES * (PROJ_KT * PROJ_LDB + 8 * MT * PROJ_LDA);
+}
+
+// ---------------------------------------------------------------------------------------
+// augmentation operands for the one-centre GEMM  [projector.c:890-959 in matrix form]
+// ---------------------------------------------------------------------------------------
+// Generic "gather + small block matmul":  dst[row][dst_off + i] = sum_j Mat[i][j] * src[row][src_off + j]
+// (Mat == nullptr: plain copy of ni entries).  One block entry per (site pair); rows = bands.
+struct BlockOp {
+  int src_off, dst_off, ni, nj;
+  long mat_off;             // offset into the matrix pool (double2), -1 for identity copy
+};
+__global__ void __launch_bounds__(128)
+block_apply_kernel(const BlockOp* __restrict__ ops, const double2* __restrict__ mats,
+                   const double2* __restrict__ src, long lds, double2* __restrict__ dst, long ldd,
+                   int nrows) {
+  const BlockOp op = ops[blockIdx.y];
+  for (int row = blockIdx.x; row < nrows; row += gridDim.x) {
+    const double2* s = src + (long)row * lds + op.src_off;
+    double2* d = dst + (long)row * ldd + op.dst_off;
+    for (int i = threadIdx.x; i < op.ni; i += blockDim.x) {
+      if (op.mat_off < 0) {
+        d[i] = s[i];
+      } else {
+        const double2* M = mats + op.mat_off + (long)i * op.nj;
+        double2 acc = make_double2(0, 0);
+        for (int j = 0; j < op.nj; j++) {
+          const double2 t = cmul(M[j], s[j]);
+          acc.x += t.x;
+          acc.y += t.y;
+        }
+        d[i] = acc;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// (a12) real-space AE state  [density.c:241-253, 297-304]
+// ---------------------------------------------------------------------------------------
+// x[g] *= exp(sign * 2 pi i k.r_frac), one thread per grid point
+__global__ void __launch_bounds__(256)
+bloch_phase_kernel(double2* __restrict__ x, int n0, int n1, int n2, double kx, double ky,
+                   double kz, double sign, int nbox) {
+  const double PI = 3.14159265359;   // density.c:13
+  const long ngrid = (long)n0 * n1 * n2;
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (long g = (long)blockIdx.x * blockDim.x + threadIdx.x; g < ngrid; g += stride) {
+    const int i = (int)(g / ((long)n1 * n2));
+    const int rem = (int)(g % ((long)n1 * n2));
+    const double kr = kx * ((double)i / n0) + ky * ((double)(rem / n2) / n1) +
+                      kz * ((double)(rem % n2) / n2);
+    double s, c;
+    sincos(sign * 2 * PI * kr, &s, &c);
+    for (int b = 0; b < nbox; b++) {
+      const double2 v = x[(long)b * ngrid + g];
+      x[(long)b * ngrid + g] = make_double2(v.x * c - v.y * s, v.x * s + v.y * c);
+    }
+  }
+}
+
+// x[idx[pt]] += e^{2 pi i k.(R + wrap)} * sum_lm A[lm][pt] * P[lm]   (one warp-wide pass per site)
+// Spheres of neighbouring atoms may overlap, so the accumulation uses FP64 atomics (the
+// reference races here under OpenMP, density.c:256-304).
+__global__ void __launch_bounds__(256)
+augment_add_kernel(const SiteDev* __restrict__ sites, const int* __restrict__ idx,
+                   const int* __restrict__ wrap, long wrap_ld, const double2* __restrict__ table,
+                   const double2* __restrict__ P, long ldp, int nbox, double2* __restrict__ x,
+                   long ngrid, double kx, double ky, double kz) {
+  const double PI = 3.14159265359;   // density.c:13
+  const SiteDev sd = sites[blockIdx.y];
+  extern __shared__ double2 sP[];    // [nbox][nlm]
+  for (int e = threadIdx.x; e < nbox * sd.nlm; e += blockDim.x)
+    sP[e] = P[(long)(e / sd.nlm) * ldp + sd.lm_off + (e % sd.nlm)];
+  __syncthreads();
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < sd.npts; p += gridDim.x * blockDim.x) {
+    const long q = sd.pt_off + p;
+    const double ph = (sd.coord[0] + wrap[q]) * kx + (sd.coord[1] + wrap[wrap_ld + q]) * ky +
+                      (sd.coord[2] + wrap[2 * wrap_ld + q]) * kz;
+    double s, c;
+    sincos(2 * PI * ph, &s, &c);
+    const int g = idx[q];
+    for (int b = 0; b < nbox; b++) {
+      double2 acc = make_double2(0, 0);
+      for (int ch = 0; ch < sd.nlm; ch++) {
+        const double2 t = cmul(table[sd.tab_off + (long)ch * sd.npts_pad + p], sP[b * sd.nlm + ch]);
+        acc.x += t.x;
+        acc.y += t.y;
+      }
+      double* dst = reinterpret_cast<double*>(x + (long)b * ngrid + g);
+      atomicAdd(dst, acc.x * c - acc.y * s);
+      atomicAdd(dst + 1, acc.x * s + acc.y * c);
+    }
+  }
+}
+
+// (a13) density accumulation  [density.c:170-173, 193-196]:  rho[g] += sum_box w[box] |x_box[g]|^2
+__global__ void __launch_bounds__(256)
+density_accum_kernel(const double2* __restrict__ x, long ngrid, int nbox,
+                     const double* __restrict__ w, double* __restrict__ rho) {
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (long g = (long)blockIdx.x * blockDim.x + threadIdx.x; g < ngrid; g += stride) {
+    double a = 0;
+    for (int b = 0; b < nbox; b++) {
+      const double2 v = x[(long)b * ngrid + g];
+      a += (v.x * v.x + v.y * v.y) * w[b];
+    }
+    rho[g] += a;
+  }
+}
+
+}  // namespace pawb200

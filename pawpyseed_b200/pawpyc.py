@@ -1,0 +1,462 @@
+"""Host-side mirror of pawpyseed's Cython shim (pawpyseed/core/pawpyc.pyx).
+
+Same class names, method names, argument meaning and error behaviour as the reference
+cdef classes - ``PWFPointer`` (:197), ``PseudoWavefunction`` (:270), ``CWavefunction`` (:328),
+``CNCLWavefunction`` (:558), ``CProjector`` (:634), ``Timer`` (:37) - but every C call goes
+to the GPU engine through the C ABI of include/pawpyseed_b200.h.  pymatgen / monty are
+optional: a ``Vasprun``-like object only needs ``actual_kpoints``,
+``actual_kpoints_weights`` and ``eigenvalue_band_properties``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import gzip
+import bz2
+import sys
+import time
+
+import numpy as np
+
+from . import _lib
+from ._lib import PAWpyError, check, dp, f64, i32, ip
+
+
+class Timer:
+    """pawpyc.pyx:37-49."""
+    ALL_SETUP_TIME = 0
+    ALL_OVERLAP_TIME = 0
+    ALL_AUGMENTATION_TIME = 0
+
+    @staticmethod
+    def setup_time(t):
+        Timer.ALL_SETUP_TIME += t
+
+    @staticmethod
+    def overlap_time(t):
+        Timer.ALL_OVERLAP_TIME += t
+
+    @staticmethod
+    def augmentation_time(t):
+        Timer.ALL_AUGMENTATION_TIME += t
+
+
+def el(site):
+    """pawpyc.pyx:55-60."""
+    return site.specie.symbol
+
+
+# ---- C utility wrappers (pawpyc.pyx:77-191) ------------------------------------------------
+def legendre(l, m, x):
+    return _lib.lib().pawb200_legendre(int(l), int(m), float(x))
+
+
+def Ylm(l, m, theta, phi):
+    o = np.zeros(2)
+    _lib.lib().pawb200_Ylm(int(l), int(m), float(theta), float(phi), dp(o))
+    return complex(o[0], o[1])
+
+
+def Ylm2(l, m, costheta, phi):
+    o = np.zeros(2)
+    _lib.lib().pawb200_Ylm2(int(l), int(m), float(costheta), float(phi), dp(o))
+    return complex(o[0], o[1])
+
+
+def frac_to_cartesian(coord, lattice):
+    lat = f64(np.asarray(lattice).flatten())
+    _lib.lib().pawb200_frac_to_cartesian(dp(coord), dp(lat))
+
+
+def cartesian_to_frac(coord, reclattice):
+    rec = f64(np.asarray(reclattice).flatten())
+    _lib.lib().pawb200_cartesian_to_frac(dp(coord), dp(rec))
+
+
+def _spline(x, y):
+    L = _lib.lib()
+    n = len(x)
+    p = L.pawb200_spline_coeff(dp(x), dp(y), n)
+    out = np.ctypeslib.as_array(C.cast(p, _lib.c_dbl_p), shape=(3 * n,)).copy()
+    L.pawb200_free_ptr(p)
+    return out
+
+
+def interpolate(res, tst, x, y, rmax, size, tstsize):
+    L = _lib.lib()
+    x, y = f64(x), f64(y)
+    coef = _spline(x[:size], y[:size])
+    for i in range(tstsize):
+        res[i] = L.pawb200_proj_interpolate(float(tst[i]), float(rmax), int(size), dp(x), dp(y), dp(coef))
+
+
+def spherical_bessel_transform(encut, l, r, f):
+    r, f = f64(r), f64(f)
+    k = np.zeros(len(r))
+    fk = np.zeros(len(r))
+    _lib.lib().pawb200_spherical_bessel_transform(float(encut), int(l), len(r), dp(r), dp(f), dp(k), dp(fk))
+    check()
+    return k, fk
+
+
+def reciprocal_offsite_wave_overlap(dcoord, r1, f1, r2, f2, l1, m1, l2, m2):
+    encut = 1e5
+    k1, fk1 = spherical_bessel_transform(encut, l1, r1, f1)
+    k2, fk2 = spherical_bessel_transform(encut, l2, r2, f2)
+    s1, s2 = _spline(k1, fk1), _spline(k2, fk2)
+    d = f64(dcoord)
+    o = np.zeros(2)
+    _lib.lib().pawb200_reciprocal_offsite_wave_overlap(dp(d), dp(k1), dp(fk1), dp(s1), len(k1), dp(k2),
+                                                       dp(fk2), dp(s2), len(k2), int(l1), int(m1),
+                                                       int(l2), int(m2), dp(o))
+    check()
+    return complex(o[0], o[1])
+
+
+# ---- base classes ------------------------------------------------------------------------------
+class PWFPointer:
+    """pawpyc.pyx:197-267.  Holds the opaque engine handle (GPU-resident coefficients)."""
+
+    def __init__(self, filename=None, vr=None):
+        self.ptr = None
+        self._buf = None
+        if filename is None or vr is None:
+            return
+        self.weights = np.array(vr.actual_kpoints_weights, dtype=np.float64)
+        self.kpts = np.array(vr.actual_kpoints, dtype=np.float64)
+        self.band_props = np.array(vr.eigenvalue_band_properties)
+        self._read(filename)
+
+    @classmethod
+    def from_arrays(cls, source, kpts, weights, band_props=(0.0, 0.0, 0.0, False)):
+        """Same as the constructor without a Vasprun: `source` is a WAVECAR path (.gz/.bz2
+        accepted, pawpyc.pyx:217-222) or an in-memory WAVECAR image (bytes / uint8 array)."""
+        self = cls()
+        self.weights = np.array(weights, dtype=np.float64)
+        self.kpts = np.array(kpts, dtype=np.float64).reshape(-1, 3)
+        self.band_props = np.array(band_props)
+        self._read(source)
+        return self
+
+    def _read(self, source):
+        L = _lib.lib()
+        kws = f64(self.weights)
+        if isinstance(source, (bytes, bytearray, memoryview, np.ndarray)):
+            buf = np.frombuffer(source, dtype=np.uint8) if not isinstance(source, np.ndarray) else source
+            self._buf = np.ascontiguousarray(buf, dtype=np.uint8)
+            self.ptr = L.pawb200_read_wavefunctions_from_str(self._buf.ctypes.data_as(C.c_void_p), dp(kws))
+            self._buf = None   # the engine copied what it needs to HBM
+        else:
+            filename = str(source)
+            if ".gz" in filename or ".bz2" in filename:
+                opener = gzip.open if ".gz" in filename else bz2.open
+                with opener(filename, "rb") as f:
+                    contents = np.frombuffer(f.read(), dtype=np.uint8)
+                self.ptr = L.pawb200_read_wavefunctions_from_str(contents.ctypes.data_as(C.c_void_p), dp(kws))
+            else:
+                self.ptr = L.pawb200_read_wavefunctions(filename.encode("utf-8"), dp(kws))
+        check()
+        if not self.ptr:
+            raise PAWpyError("read_wavefunctions returned NULL")
+        sys.stdout.flush()
+
+
+class PseudoWavefunction:
+    """pawpyc.pyx:270-325."""
+
+    def __init__(self, pwf: PWFPointer):
+        if pwf.ptr is None:
+            raise Exception("NULL PWFPointer ptr!")
+        L = _lib.lib()
+        self.wf_ptr = pwf.ptr
+        pwf.ptr = None   # ownership moves, like the C pointer in the reference
+        self.kpts = pwf.kpts.copy(order="C")
+        self.kws = pwf.weights.copy(order="C")
+        self.ncl = L.pawb200_is_ncl(self.wf_ptr) > 0
+        self.nband = L.pawb200_get_nband(self.wf_ptr)
+        self.nwk = L.pawb200_get_nwk(self.wf_ptr)
+        self.nspin = L.pawb200_get_nspin(self.wf_ptr)
+        self.encut = L.pawb200_get_encut(self.wf_ptr)
+
+    def __del__(self):
+        try:
+            if getattr(self, "wf_ptr", None):
+                _lib.lib().pawb200_free_pswf(self.wf_ptr)
+                self.wf_ptr = None
+        except Exception:
+            pass
+
+    def pseudoprojection(self, band_num, basis, flip_spin=False):
+        """<psibt_n1k|psit_n2k> for all n1, k and a given n2 (pawpyc.pyx:311-325)."""
+        res = np.zeros(basis.nband * basis.nwk * basis.nspin, dtype=np.complex128)
+        _lib.lib().pawb200_pseudoprojection(res.ctypes.data_as(_lib.c_dbl_p), basis.wf_ptr, self.wf_ptr,
+                                            int(band_num), int(bool(flip_spin)))
+        check()
+        return res
+
+
+class CWavefunction(PseudoWavefunction):
+    """pawpyc.pyx:328-555."""
+
+    def __init__(self, pwf):
+        self.projector_owner = 0
+        super().__init__(pwf)
+
+    def _c_projector_setup(self, num_elems, num_sites, grid_encut, nums, coords, dim, pps):
+        """pawpyc.pyx:352-412: flatten the PAW data per element (sorted labels) and run
+        get_projector_list + setup_projections."""
+        L = _lib.lib()
+        start = time.monotonic()
+        clabels, ls, wgrids, projectors, aewaves, pswaves, rmaxs = [], [], [], [], [], [], []
+        for num in sorted(pps.keys()):
+            pp = pps[num]
+            clabels += [num, len(pp.ls), pp.ndata, len(pp.grid)]
+            rmaxs.append(pp.rmax)
+            ls += list(pp.ls)
+            wgrids.append(np.asarray(pp.grid, dtype=np.float64))
+            for i in range(len(pp.ls)):
+                projectors.append(np.asarray(pp.realprojs[i], dtype=np.float64))
+                aewaves.append(np.asarray(pp.aewaves[i], dtype=np.float64))
+                pswaves.append(np.asarray(pp.pswaves[i], dtype=np.float64))
+        clabels_v, ls_v = i32(clabels), i32(ls)
+        wgrids_v, projectors_v = f64(np.concatenate(wgrids)), f64(np.concatenate(projectors))
+        aewaves_v, pswaves_v = f64(np.concatenate(aewaves)), f64(np.concatenate(pswaves))
+        rmaxs_v = f64(rmaxs)
+        projector_list = L.pawb200_get_projector_list(
+            int(num_elems), ip(clabels_v), ip(ls_v), dp(wgrids_v), dp(projectors_v), dp(aewaves_v),
+            dp(pswaves_v), dp(rmaxs_v), float(grid_encut))
+        check()
+        end = time.monotonic()
+        Timer.setup_time(end - start)
+        self.number_projector_elements = num_elems
+        self.nums = np.array(nums, dtype=np.int32, copy=True)
+        self.coords = np.array(coords, dtype=np.float64, copy=True).reshape(-1)
+        self.update_dimv(dim)
+        L.pawb200_setup_projections(self.wf_ptr, projector_list, int(num_elems), int(num_sites),
+                                    ip(self.dimv), ip(self.nums), dp(self.coords))
+        check()
+        self.projector_owner = 1
+
+    def update_dimv(self, dim):
+        dim = np.array(dim, dtype=np.int32, order="C")
+        self.dimv = dim
+        self.fdimv = (dim * 2).astype(np.int32)
+        self.gridsize = int(np.cumprod(dim)[-1])
+        self.fgridsize = int(np.cumprod(dim * 2)[-1])
+
+    def _check_bks(self, b, k, s):
+        if b < 0 or b >= self.nband:
+            raise ValueError("Invalid band choice")
+        if k < 0 or k >= self.nwk:
+            raise ValueError("Invalid k-point choice")
+        if s < 0 or s >= self.nspin:
+            raise ValueError("Invalid spin choice")
+
+    def _get_realspace_state(self, b, k, s, remove_phase=False):
+        self._check_bks(b, k, s)
+        L = _lib.lib()
+        res = np.zeros(self.gridsize, dtype=np.complex128, order="C")
+        L.pawb200_realspace_state(res.ctypes.data_as(_lib.c_dbl_p), b, k + s * self.nwk, self.wf_ptr,
+                                  ip(self.dimv), ip(self.nums), dp(self.coords))
+        check()
+        if remove_phase:
+            L.pawb200_remove_phase(res.ctypes.data_as(_lib.c_dbl_p), k + s * self.nwk, self.wf_ptr, ip(self.dimv))
+            check()
+        res.shape = tuple(self.dimv)
+        return res
+
+    def _get_realspace_state_density(self, b, k, s):
+        self._check_bks(b, k, s)
+        res = np.zeros(self.fgridsize, dtype=np.float64, order="C")
+        _lib.lib().pawb200_ae_state_density(dp(res), b, k + s * self.nwk, self.wf_ptr, ip(self.fdimv),
+                                            ip(self.nums), dp(self.coords))
+        check()
+        res.shape = tuple(self.fdimv)
+        return res
+
+    def _get_realspace_density(self, bands=None):
+        """pawpyc.pyx:455-494."""
+        L = _lib.lib()
+        res = np.zeros(self.fgridsize, dtype=np.float64, order="C")
+        if bands is None:
+            L.pawb200_ae_chg_density(dp(res), self.wf_ptr, ip(self.fdimv), ip(self.nums), dp(self.coords))
+            check()
+        else:
+            blist = [bands] if isinstance(bands, (int, np.integer)) else list(bands)
+            for b in blist:
+                if b < 0 or b >= self.nband:
+                    raise ValueError("Invalid band choice")
+                for k in range(self.nwk * self.nspin):
+                    work = np.zeros(self.fgridsize, dtype=np.float64, order="C")
+                    L.pawb200_ae_state_density(dp(work), int(b), k, self.wf_ptr, ip(self.fdimv),
+                                               ip(self.nums), dp(self.coords))
+                    check()
+                    res += work * self.kws[k % self.nwk] / self.nspin
+        res.shape = tuple(self.fdimv)
+        return res
+
+    def _write_realspace_state(self, filename1, filename2, scale, b, k, s, remove_phase=False):
+        self._check_bks(b, k, s)
+        L = _lib.lib()
+        res = self._get_realspace_state(b, k, s, remove_phase)
+        flat = res.reshape(self.gridsize)
+        for fn, part in ((filename1, np.real(flat)), (filename2, np.imag(flat))):
+            arr = np.ascontiguousarray(part)
+            L.pawb200_write_volumetric(fn.encode("utf-8"), dp(arr), ip(self.dimv), float(scale))
+            check()
+        return res
+
+    def _write_realspace_density(self, filename, scale, bands=None):
+        res = self._get_realspace_density(bands)
+        flat = np.ascontiguousarray(res.reshape(self.fgridsize))
+        _lib.lib().pawb200_write_volumetric(filename.encode("utf-8"), dp(flat), ip(self.fdimv), float(scale))
+        check()
+        return res
+
+    def _get_occs(self):
+        """pawpyc.pyx:532-538 (through get_occ instead of reaching into the struct)."""
+        L = _lib.lib()
+        nk = self.nwk * self.nspin
+        p = L.pawb200_get_occs(self.wf_ptr)
+        res = np.ctypeslib.as_array(C.cast(p, _lib.c_dbl_p), shape=(self.nband * nk,)).copy()
+        L.pawb200_free_ptr(p)
+        return res
+
+    def _get_energy_list(self, bands):
+        L = _lib.lib()
+        for b in bands:
+            if b < 0 or b >= self.nband:
+                raise ValueError("Invalid band choice")
+        energy_list = {}
+        for b in bands:
+            energy_list[b] = []
+            for s in range(self.nspin):
+                for k in range(self.nwk):
+                    energy_list[b].append([L.pawb200_get_energy(self.wf_ptr, b, k, s),
+                                           L.pawb200_get_occ(self.wf_ptr, b, k, s)])
+        return energy_list
+
+    # ---- extensions: direct access to device-resident projections ------------------------------
+    def _get_projections(self, b, kappa, which=0):
+        L = _lib.lib()
+        n = L.pawb200_num_projections(self.wf_ptr, which)
+        out = np.zeros(n, dtype=np.complex128)
+        L.pawb200_get_projections(self.wf_ptr, int(b), int(kappa), int(which), out.ctypes.data_as(_lib.c_dbl_p))
+        check()
+        return out
+
+    def _get_channel_index(self):
+        L = _lib.lib()
+        n = L.pawb200_get_channel_index(self.wf_ptr, None)
+        out = np.zeros((n, 4), dtype=np.int32)
+        L.pawb200_get_channel_index(self.wf_ptr, ip(out.reshape(-1)))
+        return out
+
+    def _get_site_indices(self, site):
+        L = _lib.lib()
+        n = L.pawb200_get_site_indices(self.wf_ptr, int(site), None, 0)
+        if n < 0:
+            raise PAWpyError("site tables not available")
+        out = np.zeros(max(n, 1), dtype=np.int32)
+        L.pawb200_get_site_indices(self.wf_ptr, int(site), ip(out), n)
+        return out[:n]
+
+
+class CNCLWavefunction(CWavefunction):
+    """pawpyc.pyx:558-631."""
+
+    def _get_realspace_state(self, b, k, s, remove_phase=False):
+        self._check_bks(b, k, s)
+        L = _lib.lib()
+        res = np.zeros(self.gridsize * 2, dtype=np.complex128, order="C")
+        L.pawb200_ncl_realspace_state(res.ctypes.data_as(_lib.c_dbl_p), b, k + s * self.nwk, self.wf_ptr,
+                                      ip(self.dimv), ip(self.nums), dp(self.coords))
+        check()
+        res0, res1 = res[:self.gridsize], res[self.gridsize:]
+        if remove_phase:
+            for part in (res0, res1):
+                L.pawb200_remove_phase(part.ctypes.data_as(_lib.c_dbl_p), k + s * self.nwk, self.wf_ptr,
+                                       ip(self.dimv))
+                check()
+        return res0.reshape(tuple(self.dimv)), res1.reshape(tuple(self.dimv))
+
+    def _get_realspace_density(self):
+        res = np.zeros(self.gridsize, dtype=np.float64, order="C")
+        _lib.lib().pawb200_ncl_ae_chg_density(dp(res), self.wf_ptr, ip(self.dimv), ip(self.nums), dp(self.coords))
+        check()
+        res.shape = tuple(self.dimv)
+        return res
+
+    def _write_realspace_state(self, filename1, filename2, filename3, filename4, scale, b, k, s,
+                               remove_phase=False):
+        self._check_bks(b, k, s)
+        L = _lib.lib()
+        res0, res1 = self._get_realspace_state(b, k, s, remove_phase=remove_phase)
+        for fr, fi, res in ((filename1, filename2, res0), (filename3, filename4, res1)):
+            flat = res.reshape(self.gridsize)
+            for fn, part in ((fr, np.real(flat)), (fi, np.imag(flat))):
+                arr = np.ascontiguousarray(part)
+                L.pawb200_write_volumetric(fn.encode("utf-8"), dp(arr), ip(self.dimv), float(scale))
+                check()
+        return res0, res1
+
+    def _write_realspace_density(self, filename, scale):
+        res = self._get_realspace_density()
+        flat = np.ascontiguousarray(res.reshape(self.gridsize))
+        _lib.lib().pawb200_write_volumetric(filename.encode("utf-8"), dp(flat), ip(self.dimv), float(scale))
+        check()
+        return res
+
+
+class CProjector:
+    """pawpyc.pyx:634-736 (aug_real / pseudo paths)."""
+
+    def __init__(self, wf, basis):
+        self.wf = wf
+        self.basis = basis
+
+    def _setup_overlap(self, site_cat, recip):
+        if recip:
+            raise PAWpyError("method 'aug_recip' is not part of the B200 hot path (SURVEY 8f3); use 'aug_real'")
+        names = ("M_R", "M_S", "N_R", "N_S", "N_RS_R", "N_RS_S")
+        for n, lst in zip(names, site_cat):
+            setattr(self, n, np.array(lst, dtype=np.int32, order="C"))
+            setattr(self, "num_" + n, len(lst))
+        _lib.lib().pawb200_overlap_setup_real(
+            self.basis.wf_ptr, self.wf.wf_ptr, ip(self.basis.nums), ip(self.wf.nums),
+            dp(self.basis.coords), dp(self.wf.coords), ip(self.N_R), ip(self.N_S), ip(self.N_RS_R),
+            ip(self.N_RS_S), self.num_N_R, self.num_N_S, self.num_N_RS_R)
+        check()
+
+    def _add_augmentation_terms(self, res, band_num, flip_spin):
+        if res.dtype != np.complex128 or not res.flags["C_CONTIGUOUS"]:
+            raise ValueError("res must be a contiguous complex128 array")
+        _lib.lib().pawb200_compensation_terms(
+            res.ctypes.data_as(_lib.c_dbl_p), int(band_num), self.wf.wf_ptr, self.basis.wf_ptr,
+            self.num_M_R, self.num_N_R, self.num_N_S, self.num_N_RS_R, ip(self.M_R), ip(self.M_S),
+            ip(self.N_R), ip(self.N_S), ip(self.N_RS_R), ip(self.N_RS_S), ip(self.wf.nums),
+            dp(self.wf.coords), ip(self.basis.nums), dp(self.basis.coords), ip(self.wf.dimv),
+            int(bool(flip_spin)))
+        check()
+
+    def _projection_recip(self, res, band_num, flip_spin):
+        raise PAWpyError("method 'aug_recip' is not part of the B200 hot path (SURVEY 8f3)")
+
+    def _realspace_projection(self, band_num, dim):
+        raise PAWpyError("method 'realspace' is not part of the B200 hot path (SURVEY 8f4)")
+
+    # ---- extension: all band pairs in one call ---------------------------------------------------
+    def _projection_matrix(self, flip_spin=False, kappa_range=None, pseudo_only=False):
+        """out[kappa, b_wf, b_basis]; row b_wf of block kappa equals
+        single_band_projection(b_wf)[b_basis*NK + kappa]."""
+        NK = self.basis.nwk * self.basis.nspin
+        lo, hi = (0, NK) if kappa_range is None else kappa_range
+        out = np.zeros((hi - lo, self.wf.nband, self.basis.nband), dtype=np.complex128)
+        have = hasattr(self, "M_R")
+        z = np.zeros(0, np.int32)
+        lists = [getattr(self, n) if have else z for n in ("M_R", "M_S", "N_R", "N_S", "N_RS_R", "N_RS_S")]
+        _lib.lib().pawb200_projection_matrix(
+            out.ctypes.data_as(_lib.c_dbl_p), self.wf.wf_ptr, self.basis.wf_ptr, len(lists[0]),
+            len(lists[2]), len(lists[3]), len(lists[4]), *[ip(a) for a in lists],
+            int(bool(flip_spin)), int(lo), int(hi), int(bool(pseudo_only) or not have))
+        check()
+        return out
