@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -102,6 +103,55 @@ void require_device() {
   if (state < 0) throw std::runtime_error(why);
 }
 
+// Stream-ordered caching allocator: all work runs on one stream, so a block returned to the pool
+// can be handed out again without a device synchronisation (later kernels are ordered after the
+// earlier users).  Avoids cudaMalloc/cudaFree (and their implicit syncs) on the per-step path.
+struct DevPool {
+  std::map<size_t, std::vector<void*>> free_;
+  size_t cached_bytes = 0;
+  static size_t bucket(size_t n) {
+    if (n <= (1u << 20)) {
+      size_t b = 256;
+      while (b < n) b <<= 1;
+      return b;
+    }
+    const size_t g = (size_t)2 << 20;
+    return (n + g - 1) / g * g;
+  }
+  void* get(size_t& n) {
+    n = bucket(n);
+    auto it = free_.find(n);
+    if (it != free_.end() && !it->second.empty()) {
+      void* p = it->second.back();
+      it->second.pop_back();
+      cached_bytes -= n;
+      return p;
+    }
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, n);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      trim();
+      e = cudaMalloc(&p, n);
+      if (e != cudaSuccess)
+        throw std::runtime_error(std::string("CUDA: out of device memory allocating ") + std::to_string(n >> 20) + " MiB");
+    }
+    return p;
+  }
+  void put(void* p, size_t n) {
+    free_[n].push_back(p);
+    cached_bytes += n;
+  }
+  void trim() {
+    cudaDeviceSynchronize();
+    for (auto& kv : free_)
+      for (void* p : kv.second) cudaFree(p);
+    free_.clear();
+    cached_bytes = 0;
+  }
+};
+DevPool g_pool;
+
 struct DevBuf {
   void* p = nullptr;
   size_t bytes = 0;
@@ -118,23 +168,59 @@ struct DevBuf {
   void alloc(size_t n) {
     release();
     if (n == 0) return;
-    CUDA_OK(cudaMalloc(&p, n));
+    p = g_pool.get(n);
     bytes = n;
   }
   void ensure(size_t n) { if (n > bytes) alloc(n); }
-  void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+  void release() { if (p) g_pool.put(p, bytes); p = nullptr; bytes = 0; }
   void zero() { if (p) CUDA_OK(cudaMemsetAsync(p, 0, bytes, g_stream)); }
+  void zero(size_t n) { if (p) CUDA_OK(cudaMemsetAsync(p, 0, std::min(n, bytes), g_stream)); }
   template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+// Pinned staging arena for host->device uploads of setup data: bump allocation, recycled at the
+// synchronisation points the API already has (or when full).
+struct PinnedArena {
+  unsigned char* base = nullptr;
+  size_t cap = 0, used = 0;
+  void* take(size_t n) {
+    n = (n + 255) / 256 * 256;
+    if (n > cap) {   // grow: everything in flight must land first
+      CUDA_OK(cudaStreamSynchronize(g_stream));
+      if (base) cudaFreeHost(base);
+      cap = std::max<size_t>(n * 2, (size_t)64 << 20);
+      CUDA_OK(cudaMallocHost((void**)&base, cap));
+      used = 0;
+    }
+    if (used + n > cap) {
+      CUDA_OK(cudaStreamSynchronize(g_stream));
+      used = 0;
+    }
+    void* p = base + used;
+    used += n;
+    return p;
+  }
+  void reset_after_sync() { used = 0; }
+};
+PinnedArena g_arena;
+
+void stream_sync() {
+  CUDA_OK(cudaStreamSynchronize(g_stream));
+  g_arena.reset_after_sync();
+}
+
 template <typename T>
-DevBuf upload(const std::vector<T>& v) {
-  DevBuf b(v.size() * sizeof(T));
-  if (!v.empty())
-    CUDA_OK(cudaMemcpyAsync(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, g_stream));
-  CUDA_OK(cudaStreamSynchronize(g_stream));   // v may be a temporary
+DevBuf upload(const T* v, size_t n) {
+  DevBuf b(std::max<size_t>(n, 1) * sizeof(T));
+  if (n) {
+    void* st = g_arena.take(n * sizeof(T));
+    memcpy(st, v, n * sizeof(T));
+    CUDA_OK(cudaMemcpyAsync(b.p, st, n * sizeof(T), cudaMemcpyHostToDevice, g_stream));
+  }
   return b;
 }
+template <typename T>
+DevBuf upload(const std::vector<T>& v) { return upload(v.data(), v.size()); }
 
 // ---- stage timers (CUDA events on the launch stream) ---------------------------------------
 enum Stage { ST_H2D, ST_SCATTER, ST_FFT, ST_PROJECT, ST_TABLE, ST_GEMM_PS, ST_GEMM_AUG, ST_AUGMENT,
@@ -181,6 +267,23 @@ void drain_timers() {
   }
   g_pending.clear();
 }
+
+// ---- host wall-clock sections (PAWB200_PROFILE=1 prints them from pawb200_get_timers) ---------
+struct HostProf {
+  std::map<std::string, double> ms;
+  std::map<std::string, long> calls;
+};
+HostProf g_hostprof;
+struct HostSection {
+  const char* name;
+  std::chrono::steady_clock::time_point t0;
+  explicit HostSection(const char* n) : name(n), t0(std::chrono::steady_clock::now()) {}
+  ~HostSection() {
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    g_hostprof.ms[name] += ms;
+    g_hostprof.calls[name] += 1;
+  }
+};
 
 inline void count_launch(int n = 1) { g_launches += n; }
 inline void check_launch() { CUDA_OK(cudaGetLastError()); }
@@ -298,6 +401,7 @@ std::unique_ptr<SiteTables> build_site_tables(const std::vector<Element>& els, c
                                               int nlist, const int* labels, const double* coords,
                                               const double* lattice, const int* fftg, int mode,
                                               bool keep_host_idx) {
+  HostSection hs_("build_site_tables");
   auto T = std::make_unique<SiteTables>();
   T->nsites = nlist;
   T->mode = mode;
@@ -305,6 +409,7 @@ std::unique_ptr<SiteTables> build_site_tables(const std::vector<Element>& els, c
   T->host.resize(nlist);
   T->site_id.assign(site_list, site_list + nlist);
   std::vector<SphereGeom> geom(nlist);
+  auto* hs_geom = new HostSection("  sphere_geometry");
 #pragma omp parallel for schedule(dynamic)
   for (int s = 0; s < nlist; s++) {
     const int p = site_list[s];
@@ -318,6 +423,7 @@ std::unique_ptr<SiteTables> build_site_tables(const std::vector<Element>& els, c
     }
     geom[s] = sphere_geometry(coords + 3 * p, lattice, fftg, rmax, radius);
   }
+  delete hs_geom;
   long pt = 0, tab = 0;
   int lm = 0;
   for (int s = 0; s < nlist; s++) {
@@ -340,15 +446,22 @@ std::unique_ptr<SiteTables> build_site_tables(const std::vector<Element>& els, c
   T->total_pts = pt;
   T->total_tab = tab;
   T->nproj = lm;
-  std::vector<int32_t> idx(pt, 0), wrap(3 * pt, 0);
-  std::vector<double> path(3 * pt, 0.0);
+  // pack index / path (/ wrap) arrays straight into pinned staging memory, in parallel over sites
+  const size_t npt = (size_t)std::max<long>(pt, 1);
+  // one arena block for all three arrays (a later take() may recycle the arena)
+  unsigned char* blk = (unsigned char*)g_arena.take(npt * (3 * sizeof(double) + 4 * sizeof(int32_t)));
+  double* path = (double*)blk;
+  int32_t* idx = (int32_t*)(blk + 3 * npt * sizeof(double));
+  int32_t* wrap = mode == 2 ? idx + npt : nullptr;
+#pragma omp parallel for schedule(dynamic)
   for (int s = 0; s < nlist; s++) {
     const SiteDev& sd = T->host[s];
-    for (int q = 0; q < sd.npts; q++) {
-      idx[sd.pt_off + q] = geom[s].index[q];
+    for (int q = 0; q < sd.npts_pad; q++) {
+      const bool real = q < sd.npts;
+      idx[sd.pt_off + q] = real ? geom[s].index[q] : 0;
       for (int d = 0; d < 3; d++) {
-        path[d * pt + sd.pt_off + q] = geom[s].path[3 * q + d];
-        wrap[d * pt + sd.pt_off + q] = geom[s].wrap[3 * q + d];
+        path[d * pt + sd.pt_off + q] = real ? geom[s].path[3 * q + d] : 0.0;
+        if (wrap) wrap[d * pt + sd.pt_off + q] = real ? geom[s].wrap[3 * q + d] : 0;
       }
     }
   }
@@ -357,9 +470,14 @@ std::unique_ptr<SiteTables> build_site_tables(const std::vector<Element>& els, c
     for (int s = 0; s < nlist; s++) T->host_idx[s] = std::move(geom[s].index);
   }
   T->sites = upload(T->host);
-  T->idx = upload(idx);
-  T->path = upload(path);
-  if (mode == 2) T->wrap = upload(wrap);
+  T->idx.alloc(npt * sizeof(int32_t));
+  CUDA_OK(cudaMemcpyAsync(T->idx.p, idx, npt * sizeof(int32_t), cudaMemcpyHostToDevice, g_stream));
+  T->path.alloc(3 * npt * sizeof(double));
+  CUDA_OK(cudaMemcpyAsync(T->path.p, path, 3 * npt * sizeof(double), cudaMemcpyHostToDevice, g_stream));
+  if (wrap) {
+    T->wrap.alloc(3 * npt * sizeof(int32_t));
+    CUDA_OK(cudaMemcpyAsync(T->wrap.p, wrap, 3 * npt * sizeof(int32_t), cudaMemcpyHostToDevice, g_stream));
+  }
   T->table.alloc(std::max<size_t>(1, tab) * sizeof(double2));
   T->by_mt.assign(4, {});
   for (int s = 0; s < nlist; s++) T->by_mt[(T->host[s].nlm + 7) / 8].push_back(s);
@@ -379,8 +497,7 @@ std::unique_ptr<SiteTables> build_site_tables(const std::vector<Element>& els, c
         T->sites.as<SiteDev>(), ed.dev.as<ElemDev>(), T->idx.as<int>(), T->path.as<double>(), pt,
         T->table.as<double2>(), dlat.as<double>(), fftg[0], fftg[1], fftg[2], mode == 2 ? 1 : 0);
     count_launch();
-    check_launch();
-    CUDA_OK(cudaStreamSynchronize(g_stream));   // ed / dlat go out of scope
+    check_launch();   // ed / dlat return to the stream-ordered pool
   }
   return T;
 }
@@ -466,6 +583,7 @@ struct ByteSource {
 };
 
 pawb200_pswf* ingest(ByteSource src, const double* kws) {
+  HostSection hs_("ingest");
   require_device();
   auto wf = std::make_unique<pawb200_pswf>();
   double h0[3];
@@ -547,6 +665,7 @@ pawb200_pswf* ingest(ByteSource src, const double* kws) {
 
 // ---- inverse scatter map -------------------------------------------------------------------
 DevBuf build_inverse_map(const pawb200_pswf* wf, int kap, const int* fftg, std::vector<int>* fwd = nullptr) {
+  HostSection hs_("build_inverse_map");
   const KPointInfo& kp = wf->kp[kap];
   const int npw = wf->npw_half(kap);
   const long ngrid = (long)fftg[0] * fftg[1] * fftg[2];
@@ -635,6 +754,7 @@ DevBuf g_grid;   // FFT box batch, reused across calls
 // All bands of all resident (k,spin) blocks of `wf` -> <table|psi~>, written to out[kap] [nslot][ld].
 void project_all_bands(pawb200_pswf* wf, SiteTables& T, const int* fftg, std::vector<DevBuf>& out,
                        long& ld) {
+  HostSection hs_("project_all_bands");
   const int NK = wf->nkappa();
   const long ngrid = (long)fftg[0] * fftg[1] * fftg[2];
   ld = ((long)std::max(T.nproj, 1) + 7) / 8 * 8;
@@ -660,7 +780,6 @@ void project_all_bands(pawb200_pswf* wf, SiteTables& T, const int* fftg, std::ve
       launch_fft(g_grid.as<double2>(), fftg, nb, CUFFT_INVERSE);
       launch_project(T, g_grid.as<double2>(), ngrid, nb, out[kap].as<double2>(), ld, s0);
     }
-    CUDA_OK(cudaStreamSynchronize(g_stream));   // inv is freed at scope exit
   }
 }
 
@@ -758,6 +877,7 @@ struct AugPlan {
 };
 
 AugPlan plan_aug(const pawb200_pswf* S, const pawb200_pswf* R, const SiteLists& L) {
+  HostSection hs_("plan_aug");
   if (!S->has_projections || !R->has_projections)
     throw std::runtime_error("setup_projections has not been run on both wavefunctions");
   const auto& elsR = R->pps->list.el;
@@ -845,11 +965,11 @@ void apply_ops(const std::vector<BlockOp>& ops, const DevBuf& mats, const double
   block_apply_kernel<<<grid, 128, 0, g_stream>>>(d.as<BlockOp>(), mats.as<double2>(), src, lds, dst, ldd, nrows);
   count_launch();
   check_launch();
-  CUDA_OK(cudaStreamSynchronize(g_stream));
 }
 
 void aug_block(pawb200_pswf* S, pawb200_pswf* R, AugPlan& A, int kap, int flip, double2* out, long ldo,
                bool accumulate) {
+  HostSection hs_("aug_block");
   if (A.K == 0) {
     if (!accumulate)
       CUDA_OK(cudaMemset2DAsync(out, ldo * sizeof(double2), 0, R->nband * sizeof(double2), S->nband, g_stream));
@@ -879,12 +999,12 @@ void aug_block(pawb200_pswf* S, pawb200_pswf* R, AugPlan& A, int kap, int flip, 
   }
   run_zgemm<double2>(opS.as<double2>(), A.Kpad, opR.as<double2>(), A.Kpad, S->nband, R->nband, A.Kpad, out, ldo,
                      accumulate, ST_GEMM_AUG);
-  CUDA_OK(cudaStreamSynchronize(g_stream));
 }
 
 // Full block(s) to host: out[kap - lo][bS][bR]
 void overlap_matrix(pawb200_pswf* S, pawb200_pswf* R, const SiteLists* L, int flip, int lo, int hi,
                     bool pseudo, bool aug, cdouble* out) {
+  HostSection hs_("overlap_matrix");
   check_pair(S, R);
   const int nS = S->nband, nR = R->nband;
   DevBuf blk((size_t)nS * nR * sizeof(double2));
@@ -901,8 +1021,8 @@ void overlap_matrix(pawb200_pswf* S, pawb200_pswf* R, const SiteLists* L, int fl
     if (aug) aug_block(S, R, A, kap, flip, blk.as<double2>(), nR, pseudo);
     ScopedStage tm(ST_D2H);
     CUDA_OK(cudaMemcpyAsync(dst, blk.p, (size_t)nS * nR * sizeof(double2), cudaMemcpyDeviceToHost, g_stream));
-    CUDA_OK(cudaStreamSynchronize(g_stream));
   }
+  stream_sync();
 }
 
 // ---- real-space states -----------------------------------------------------------------------
@@ -1119,6 +1239,7 @@ pawb200_ppot_t* pawb200_get_projector_list(int num_els, const int* labels, const
                                            const double* projectors, const double* aewaves,
                                            const double* pswaves, const double* rmaxs, double grid_encut) {
   API_BEGIN
+  HostSection hs_("get_projector_list");
   auto p = std::make_unique<pawb200_ppot>();
   p->list.el = build_elements(num_els, labels, ls, wave_grids, projectors, aewaves, pswaves, rmaxs, grid_encut);
   return p.release();
@@ -1129,6 +1250,7 @@ void pawb200_free_ppot_list(pawb200_ppot_t* pps, int) { delete pps; }
 void pawb200_setup_projections(pawb200_pswf_t* wf, pawb200_ppot_t* pps, int num_elems, int num_sites,
                                const int* fftg, const int* labels, const double* coords) {
   API_BEGIN
+  HostSection hs_("setup_projections");
   require_device();
   if (!wf || !pps) throw std::runtime_error("NULL argument");
   if ((int)pps->list.el.size() != num_elems) throw std::runtime_error("num_elems does not match the projector list");
@@ -1190,6 +1312,7 @@ void pawb200_overlap_setup_real(pawb200_pswf_t* wf_R, pawb200_pswf_t* wf_S, cons
                                 const int* N_R, const int* N_S, const int* N_RS_R, const int* N_RS_S,
                                 int num_N_R, int num_N_S, int num_N_RS) {
   API_BEGIN
+  HostSection hs_("overlap_setup_real");
   require_device();
   check_pair(wf_S, wf_R);
   if (!wf_R->has_projections || !wf_S->has_projections) throw std::runtime_error("setup_projections has not been run");
@@ -1493,6 +1616,11 @@ int pawb200_get_site_indices(pawb200_pswf_t* wf, int site, int* out, int capacit
 }
 void pawb200_get_timers(pawb200_timers* t) {
   drain_timers();
+  if (getenv("PAWB200_PROFILE")) {
+    for (auto& kv : g_hostprof.ms)
+      fprintf(stderr, "[pawb200 host] %-22s %9.2f ms  (%ld calls)\n", kv.first.c_str(), kv.second,
+              g_hostprof.calls[kv.first]);
+  }
   t->h2d_ms = g_stage_ms[ST_H2D]; t->scatter_ms = g_stage_ms[ST_SCATTER]; t->fft_ms = g_stage_ms[ST_FFT];
   t->project_ms = g_stage_ms[ST_PROJECT]; t->table_ms = g_stage_ms[ST_TABLE];
   t->gemm_pseudo_ms = g_stage_ms[ST_GEMM_PS]; t->gemm_aug_ms = g_stage_ms[ST_GEMM_AUG];
@@ -1501,6 +1629,8 @@ void pawb200_get_timers(pawb200_timers* t) {
 }
 void pawb200_reset_timers(void) {
   drain_timers();
+  g_hostprof.ms.clear();
+  g_hostprof.calls.clear();
   for (auto& v : g_stage_ms) v = 0;
   g_launches = 0;
 }

@@ -230,6 +230,7 @@ void BesselTransform::dft_backward(std::vector<cdouble>& x) const {
   // both simple and more accurate than a mixed-radix FFT; cost is microseconds per element.
   const int N = n2_;
   std::vector<cdouble> out(N);
+#pragma omp parallel for schedule(static)
   for (int n = 0; n < N; n++) {
     long double sr = 0, si = 0;
     long idx = 0;
