@@ -1,0 +1,231 @@
+"""GPU parity tests: the sm_100a path, called through the C ABI (via the pawpyc mirror), against
+ (1) the committed golden vectors from the unmodified reference C, and
+ (2) the numpy oracle on seeded synthetic inputs.
+Bars: FP64 quantities 1e-10 relative (north_star); index arrays bit-exact; the pseudo overlap
+against the reference's single-precision value 5e-6 absolute (it is an FP32 accumulate there)."""
+import os
+
+import numpy as np
+import pytest
+
+import cases
+from oracle import paw_numpy as pn
+from pawpyseed_b200 import _lib, pawpyc, synth
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+G = cases.GOLDEN
+
+
+def rel(a, b):
+    return np.abs(np.asarray(a) - np.asarray(b)).max() / max(np.abs(b).max(), 1e-300)
+
+
+def gpu_wf(image, kpts, kws, pps, labels, coords, dim, grid_encut, ncl=False):
+    cls = pawpyc.CNCLWavefunction if ncl else pawpyc.CWavefunction
+    wf = cls(pawpyc.PWFPointer.from_arrays(image, kpts, kws))
+    wf._c_projector_setup(len(pps), len(labels), grid_encut, labels, coords, dim, pps)
+    return wf
+
+
+def oracle_wf(c):
+    w = pn.Wavefunction.from_image(c["image"], c["kws"])
+    w.setup_projections(c["pps"], c["labels"], c["coords"], c["dim"], c["grid_encut"])
+    return w
+
+
+def from_case(c):
+    return gpu_wf(c["image"], c["kpts"], c["kws"], c["pps"], c["labels"], c["coords"], c["dim"],
+                  c["grid_encut"], c["ncl"])
+
+
+# ---------------------------------------------------------------------------------------------
+# golden: the reference's own Ga4 fixtures (BASELINE config 1)
+# ---------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def ga4():
+    g = np.load(os.path.join(G, "ga4.npz"), allow_pickle=True)
+    pps = synth.synthetic_pps(["Ga"])
+    lab = np.zeros(4, np.int32)
+    R = gpu_wf(g["image_R"], g["kpts"], g["kws"], pps, lab, cases.GA4_COORDS, g["dim"], float(g["grid_encut"]))
+    S = gpu_wf(g["image_S"], g["kpts"], g["kws"], pps, lab, cases.GA4_COORDS, g["dim"], float(g["grid_encut"]))
+    return g, R, S
+
+
+def test_ga4_indices_bit_exact(ga4):
+    g, R, _ = ga4
+    assert np.array_equal(R._get_channel_index(), g["chan_index"])
+    assert np.array_equal(R._get_site_indices(0), g["site_index_0"])
+    assert [len(R._get_site_indices(s)) for s in range(4)] == list(g["site_npts"])
+
+
+def test_ga4_projections(ga4):
+    g, R, S = ga4
+    for wf, key in ((R, "proj_R"), (S, "proj_S")):
+        got = np.array([[wf._get_projections(b, k) for b in range(8)] for k in range(4)])
+        assert rel(got, g[key]) < TOL
+
+
+@pytest.mark.parametrize("ci", [0, 1, 2])
+def test_ga4_single_band_projection(ga4, ci):
+    g, R, S = ga4
+    pr = pawpyc.CProjector(S, R)
+    pr._setup_overlap([list(x) for x in g["cats"][ci]], False)
+    for flip in (0, 1):
+        for bi, b in enumerate(g["bands"]):
+            res = S.pseudoprojection(int(b), R, bool(flip))
+            assert np.abs(res - g["pseudo_f%d" % flip][bi]).max() < 5e-6      # FP32 term of the reference
+            ps = res.copy()
+            pr._add_augmentation_terms(res, int(b), bool(flip))                 # accumulates (+=)
+            assert rel(res - ps, g["aug_c%d_f%d" % (ci, flip)][bi]) < TOL
+
+
+def test_ga4_realspace_and_density(ga4):
+    g, R, _ = ga4
+    assert rel(R._get_realspace_state(1, 1, 1), g["state_b1_k1"]) < TOL
+    assert rel(R._get_realspace_state(1, 1, 1, remove_phase=True), g["state_b1_k1_nophase"]) < TOL
+    assert rel(R._get_realspace_density(), g["density"]) < TOL
+
+
+def test_ncl_fixture():
+    g = np.load(os.path.join(G, "ncl.npz"), allow_pickle=True)
+    N = gpu_wf(g["image"], g["kpts"], g["kws"], synth.synthetic_pps(["Ga"]), np.zeros(4, np.int32),
+               cases.GA4_COORDS, g["dim"], float(g["grid_encut"]), ncl=True)
+    assert N.ncl
+    up = np.array([[N._get_projections(b, k, 1) for b in range(4)] for k in range(2)])
+    dn = np.array([[N._get_projections(b, k, 2) for b in range(4)] for k in range(2)])
+    assert rel(up, g["up"]) < TOL and rel(dn, g["down"]) < TOL
+    s0, s1 = N._get_realspace_state(2, 1, 0)
+    assert rel(np.stack([s0, s1]), g["state_b2_k1"]) < TOL
+    assert rel(N._get_realspace_density(), g["density"]) < TOL
+
+
+# ---------------------------------------------------------------------------------------------
+# oracle: seeded synthetic cells
+# ---------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def gan():
+    cR, cS = cases.small_case(seed=7), cases.small_case(seed=11, perturb=0.03)
+    return cR, cS, from_case(cR), from_case(cS), oracle_wf(cR), oracle_wf(cS)
+
+
+def test_synthetic_golden_two_element(gan):
+    g = np.load(os.path.join(G, "synth_gan.npz"), allow_pickle=True)
+    cR, cS = cases.small_case(seed=7, nband=6), cases.small_case(seed=11, nband=6, perturb=0.03)
+    R, S = from_case(cR), from_case(cS)
+    assert np.array_equal(R._get_channel_index(), g["chan_index"])
+    got = np.array([[R._get_projections(b, k) for b in range(6)] for k in range(4)])
+    assert rel(got, g["proj_R"]) < TOL
+    pr = pawpyc.CProjector(S, R)
+    pr._setup_overlap([list(x) for x in g["cats"][0]], False)
+    for flip in (0, 1):
+        for bi, b in enumerate(g["bands"]):
+            res = np.zeros(6 * 4, complex)
+            pr._add_augmentation_terms(res, int(b), bool(flip))
+            assert rel(res, g["aug_c0_f%d" % flip][bi]) < TOL
+
+
+@pytest.mark.parametrize("cat", [
+    [[0, 1, 2, 3], [0, 1, 2, 3], [], [], [], []],                       # all matched (O_M only)
+    [[], [], [0, 1, 2, 3], [0, 1, 2, 3], [0, 1, 2, 3], [0, 1, 2, 3]],    # all off-site (O_R, O_S, O_N)
+    [[0, 1], [0, 1], [2, 3], [2, 3], [2, 3, 2], [2, 3, 3]],              # mixed, with a Ga-N pair
+    [[0], [0], [1, 2, 3], [], [], []],                                   # N_R only (vacancy-like)
+    [[], [], [], [], [], []],                                            # nothing: pure pseudo overlap
+])
+def test_overlap_matrix_vs_oracle(gan, cat):
+    cR, cS, R, S, oR, oS = gan
+    pr = pawpyc.CProjector(S, R)
+    pr._setup_overlap(cat, False)
+    opr = pn.Projector(oS, oR, cat)
+    nb, NK = cR["nband"], 4
+    for flip in (False, True):
+        want = np.array([opr.single_band_projection(b, flip) for b in range(nb)]).reshape(nb, nb, NK)
+        got = pr._projection_matrix(flip)                                 # [kappa][b_wf][b_basis]
+        assert rel(got, want.transpose(2, 0, 1)) < TOL
+        # per-band reference API (pseudoprojection + compensation_terms) agrees with the batched call
+        for b in (0, nb - 1):
+            res = S.pseudoprojection(b, R, flip)
+            pr._add_augmentation_terms(res, b, flip)
+            assert rel(res, want[b].reshape(-1)) < TOL
+
+
+def test_hermiticity_and_self_projection(gan):
+    cR, _, R, _, oR, _ = gan
+    pr = pawpyc.CProjector(R, R)
+    pr._setup_overlap([[0, 1, 2, 3], [0, 1, 2, 3], [], [], [], []], False)
+    M = pr._projection_matrix()
+    for k in range(4):
+        assert np.abs(M[k] - M[k].conj().T).max() < 1e-12                # <i|O|j> = conj(<j|O|i>)
+
+
+def test_ragged_band_counts_and_single_site():
+    for nband in (1, 5, 33):
+        c = cases.small_case(seed=3, nband=nband, elements=("N",), labels=(0,), coords=[[0.1, 0.2, 0.3]],
+                             nspin=1, kpts=((0.0, 0.0, 0.0),))
+        wf, o = from_case(c), oracle_wf(c)
+        got = np.array([wf._get_projections(b, 0) for b in range(nband)])
+        assert rel(got, np.array(o.P[0])) < TOL
+        pr = pawpyc.CProjector(wf, wf)
+        pr._setup_overlap([[0], [0], [], [], [], []], False)
+        want = np.array([pn.Projector(o, o, [[0], [0], [], [], [], []]).single_band_projection(b)
+                         for b in range(nband)])
+        assert rel(pr._projection_matrix()[0], want) < TOL
+
+
+def test_realspace_state_custom_grid_and_density(gan):
+    cR, _, R, _, oR, _ = gan
+    x = R._get_realspace_state(3, 1, 1)
+    assert rel(x, oR.realspace_state(3, 1 + 2)) < TOL
+    d = R._get_realspace_density()
+    want = oR.chg_density(cR["dim"] * 2)
+    assert rel(d, want) < TOL
+    sd = R._get_realspace_state_density(2, 0, 1)
+    xs = oR.realspace_state(2, 2, cR["dim"] * 2)
+    assert rel(sd, np.abs(xs) ** 2) < TOL
+
+
+def test_fft_check_known_answer():
+    """The reference's own KAT (tests.c:28-80): FFT of a band equals the direct plane-wave sum to 1e-5,
+    and fwd_fft3d(fft3d(C)) returns C to 1e-5."""
+    g = np.load(os.path.join(G, "ga4.npz"), allow_pickle=True)
+    o = pn.Wavefunction.from_image(g["image_R"], g["kws"])
+    Gs, Cs = np.ascontiguousarray(o.Gs[0], dtype=np.int32), np.ascontiguousarray(o.Cs[0][0])
+    dim = np.ascontiguousarray(g["dim"], dtype=np.int32)
+    lat = np.ascontiguousarray(o.lattice.reshape(-1))
+    L = _lib.lib()
+    x = np.zeros(int(np.prod(dim)), np.complex128)
+    k = np.zeros(3)
+    L.pawb200_fft3d(x.ctypes.data_as(_lib.c_dbl_p), None, _lib.dp(lat), _lib.dp(k), _lib.ip(Gs.reshape(-1)),
+                    Cs.ctypes.data, len(Cs), _lib.ip(dim))
+    _lib.check()
+    I, J, K = np.meshgrid(*[np.arange(n) / n for n in dim], indexing="ij")
+    direct = np.zeros(tuple(dim), complex)
+    for w in range(len(Cs)):
+        direct += Cs[w] * np.exp(2j * np.pi * (I * Gs[w, 0] + J * Gs[w, 1] + K * Gs[w, 2]))
+    direct *= pn.determinant(o.lattice) ** -0.5
+    assert np.abs(x.reshape(tuple(dim)) - direct).max() < 1e-5
+    assert rel(x.reshape(tuple(dim)), pn.fft3d(Gs, Cs, o.lattice, dim)) < 1e-13
+    back = np.zeros(len(Cs), np.complex64)
+    L.pawb200_fwd_fft3d(x.ctypes.data_as(_lib.c_dbl_p), None, _lib.dp(lat), _lib.dp(k), _lib.ip(Gs.reshape(-1)),
+                        back.ctypes.data, len(Cs), _lib.ip(dim))
+    _lib.check()
+    assert np.abs(back - Cs).max() < 1e-5
+
+
+def test_error_behaviour():
+    c = cases.small_case(nband=4)
+    wf = from_case(c)
+    with pytest.raises(ValueError):
+        wf._get_realspace_state(99, 0, 0)                # pawpyc.pyx:426-427
+    with pytest.raises(ValueError):
+        wf._get_realspace_state(0, 9, 0)
+    res = np.zeros(4 * 4, complex)
+    pr = pawpyc.CProjector(wf, wf)
+    pr._setup_overlap([[0, 1, 2, 3], [0, 1, 2, 3], [], [], [], []], False)
+    with pytest.raises(_lib.PAWpyError):
+        pr._add_augmentation_terms(res, 99, False)       # the C ABI reports instead of reading out of bounds
+    with pytest.raises(_lib.PAWpyError):                 # mismatched spin counts: refused
+        c1 = cases.small_case(nband=4, nspin=1)
+        pawpyc.CProjector(from_case(c1), wf)._projection_matrix()
+    with pytest.raises(_lib.PAWpyError):
+        pawpyc.PWFPointer.from_arrays(np.zeros(4096, np.uint8), c["kpts"], c["kws"])   # not a WAVECAR

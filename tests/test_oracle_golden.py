@@ -1,0 +1,101 @@
+"""The oracle (oracle/paw_numpy.py) against the committed golden vectors, which were produced by the
+unmodified reference C (tests/golden/make_golden.py).  CPU only."""
+import os
+
+import numpy as np
+import pytest
+
+import cases
+from oracle import paw_numpy as pn
+from pawpyseed_b200 import synth
+
+G = cases.GOLDEN
+TOL = 1e-10     # the FP64 bar of BASELINE.json north_star
+
+
+def rel(a, b):
+    return np.abs(np.asarray(a) - np.asarray(b)).max() / max(np.abs(b).max(), 1e-300)
+
+
+@pytest.fixture(scope="module")
+def ga4():
+    g = np.load(os.path.join(G, "ga4.npz"), allow_pickle=True)
+    pps = synth.synthetic_pps(["Ga"])
+    R = pn.Wavefunction.from_image(g["image_R"], g["kws"])
+    S = pn.Wavefunction.from_image(g["image_S"], g["kws"])
+    lab = np.zeros(4, np.int32)
+    for w in (R, S):
+        w.setup_projections(pps, lab, cases.GA4_COORDS, g["dim"], float(g["grid_encut"]))
+    return g, R, S
+
+
+def test_reader_g_enumeration_matches_reference(ga4):
+    g, R, _ = ga4
+    assert np.array_equal(R.Gs[0], g["gvecs_k0"])          # bit-exact plane-wave order
+    assert R.nband == 8 and R.nwk == 2 and R.nspin == 2
+
+
+def test_indices_bit_exact(ga4):
+    g, R, _ = ga4
+    assert np.array_equal(R.chan_index, g["chan_index"])   # (site, n, l, m) order
+    assert np.array_equal(R.sites[0]["indices"], g["site_index_0"])
+    assert np.array_equal([len(s["indices"]) for s in R.sites], g["site_npts"])
+
+
+def test_projections(ga4):
+    g, R, S = ga4
+    assert rel(np.array(R.P), g["proj_R"]) < TOL
+    assert rel(np.array(S.P), g["proj_S"]) < TOL
+
+
+@pytest.mark.parametrize("ci", [0, 1, 2])
+@pytest.mark.parametrize("flip", [0, 1])
+def test_compensation_terms(ga4, ci, flip):
+    g, R, S = ga4
+    pr = pn.Projector(S, R, [list(x) for x in g["cats"][ci]])
+    got = np.array([pr.compensation_terms(int(b), bool(flip)) for b in g["bands"]])
+    assert rel(got, g["aug_c%d_f%d" % (ci, flip)]) < TOL
+
+
+def test_pseudoprojection_fp64_vs_reference_fp32(ga4):
+    g, R, S = ga4
+    got = np.array([S.pseudoprojection(int(b), R, False) for b in g["bands"]])
+    # the reference accumulates and stores this term in single precision (pseudoprojector.c:86)
+    assert np.abs(got - g["pseudo_f0"]).max() < 5e-6
+    got = np.array([S.pseudoprojection(int(b), R, True) for b in g["bands"]])
+    assert np.abs(got - g["pseudo_f1"]).max() < 5e-6
+
+
+def test_realspace_state_and_density(ga4):
+    g, R, _ = ga4
+    x = R.realspace_state(1, 1 + 1 * 2)
+    assert rel(x, g["state_b1_k1"]) < TOL
+    assert rel(R.remove_phase(x, 3), g["state_b1_k1_nophase"]) < TOL
+    assert rel(R.chg_density(g["dim"] * 2), g["density"]) < TOL
+
+
+def test_synthetic_two_element_offsite():
+    g = np.load(os.path.join(G, "synth_gan.npz"), allow_pickle=True)
+    cR, cS = cases.small_case(seed=7, nband=6), cases.small_case(seed=11, nband=6, perturb=0.03)
+    R = pn.Wavefunction.from_image(cR["image"], cR["kws"])
+    S = pn.Wavefunction.from_image(cS["image"], cS["kws"])
+    R.setup_projections(cR["pps"], cR["labels"], cR["coords"], cR["dim"], cR["grid_encut"])
+    S.setup_projections(cS["pps"], cS["labels"], cS["coords"], cS["dim"], cS["grid_encut"])
+    assert np.array_equal(R.chan_index, g["chan_index"])
+    assert rel(np.array(R.P), g["proj_R"]) < TOL
+    pr = pn.Projector(S, R, [list(x) for x in g["cats"][0]])
+    for flip in (0, 1):
+        got = np.array([pr.compensation_terms(int(b), bool(flip)) for b in g["bands"]])
+        assert rel(got, g["aug_c0_f%d" % flip]) < TOL
+
+
+def test_noncollinear_fixture():
+    g = np.load(os.path.join(G, "ncl.npz"), allow_pickle=True)
+    N = pn.Wavefunction.from_image(g["image"], g["kws"])
+    assert N.ncl
+    N.setup_projections(synth.synthetic_pps(["Ga"]), np.zeros(4, np.int32), cases.GA4_COORDS, g["dim"],
+                        float(g["grid_encut"]))
+    P = np.array(N.P)                     # [k][band][2][nproj]
+    assert rel(P[:, :, 0], g["up"]) < TOL
+    assert rel(P[:, :, 1], g["down"]) < TOL
+    assert rel(N.realspace_state(2, 1), g["state_b2_k1"]) < TOL
