@@ -167,7 +167,10 @@ int pawb200_get_site_indices(pawb200_pswf_t *wf, int site, int *out, int capacit
 typedef struct {
   double h2d_ms, scatter_ms, fft_ms, project_ms, table_ms, gemm_pseudo_ms, gemm_aug_ms,
          augment_ms, d2h_ms;
-  long long launches;
+  long long launches;        /* kernels of this library launched since the last reset */
+  long long boxes_scattered; /* FFT boxes filled by scatter_pw_kernel */
+  long long boxes_fft;       /* FFT boxes transformed */
+  long long slots_projected; /* (band, table-set) sphere projections */
 } pawb200_timers;
 void pawb200_get_timers(pawb200_timers *t);
 void pawb200_reset_timers(void);

@@ -26,7 +26,8 @@ c_dbl_p = C.POINTER(C.c_double)
 class Timers(C.Structure):
     _fields_ = [(n, C.c_double) for n in (
         "h2d_ms", "scatter_ms", "fft_ms", "project_ms", "table_ms", "gemm_pseudo_ms",
-        "gemm_aug_ms", "augment_ms", "d2h_ms")] + [("launches", C.c_longlong)]
+        "gemm_aug_ms", "augment_ms", "d2h_ms")] + [(n, C.c_longlong) for n in (
+        "launches", "boxes_scattered", "boxes_fft", "slots_projected")]
 
 
 _lib = None

@@ -71,6 +71,7 @@ void set_error(const std::string& m) {
 
 cudaStream_t g_stream = 0;   // legacy default stream: ordered with torch's default stream
 std::atomic<long long> g_launches{0};
+long long g_boxes_scattered = 0, g_boxes_fft = 0, g_slots_projected = 0;
 int g_num_sms = 0;
 
 void require_device() {
@@ -244,16 +245,17 @@ cudaEvent_t get_event() {
 struct ScopedStage {
   EventPair ep;
   bool on;
-  explicit ScopedStage(int stage) : on(g_timing) {
+  cudaStream_t st;
+  explicit ScopedStage(int stage, cudaStream_t stream = nullptr) : on(g_timing), st(stream ? stream : g_stream) {
     if (!on) return;
     ep.a = get_event();
     ep.b = get_event();
     ep.stage = stage;
-    cudaEventRecord(ep.a, g_stream);
+    cudaEventRecord(ep.a, st);
   }
   ~ScopedStage() {
     if (!on) return;
-    cudaEventRecord(ep.b, g_stream);
+    cudaEventRecord(ep.b, st);
     g_pending.push_back(ep);
   }
 };
@@ -553,6 +555,10 @@ struct pawb200_pswf {
   std::vector<double> dcoords;
   std::vector<int> omega_n1, omega_n2;
   uint64_t overlap_partner = 0;
+  // FFT boxes psi~(r) of every slot kept in HBM after setup_projections (if they fit the budget), so
+  // overlap_setup_real does not scatter + transform the bands a second time
+  std::vector<DevBuf> boxes;
+  int boxes_fftg[3] = {0, 0, 0};
   // real-space table cache (mode 2), keyed by grid + coords
   std::unique_ptr<SiteTables> ae_sites;
   // per-band call caches
@@ -582,6 +588,77 @@ struct ByteSource {
   }
 };
 
+// Staging ring for raw WAVECAR records: copies run on their own stream so the H2D of one wavefunction
+// overlaps the kernels of the previous one; events order copy -> permute -> next copy per slot.
+struct IngestRing {
+  struct Slot {
+    void* p = nullptr;
+    size_t bytes = 0;
+    cudaEvent_t filled = nullptr, consumed = nullptr;
+  };
+  cudaStream_t copy = nullptr;
+  Slot slots[2];
+  unsigned next = 0;
+};
+IngestRing& ingest_ring() {
+  static IngestRing r;
+  if (!r.copy) {
+    CUDA_OK(cudaStreamCreateWithFlags(&r.copy, cudaStreamNonBlocking));
+    for (auto& s : r.slots) {
+      CUDA_OK(cudaEventCreateWithFlags(&s.filled, cudaEventDisableTiming));
+      CUDA_OK(cudaEventCreateWithFlags(&s.consumed, cudaEventDisableTiming));
+    }
+  }
+  return r;
+}
+
+// Storage order of the plane waves = FFT-box index order (wrap(g1), wrap(g2), wrap(g3)) with
+// wrap(g) = g for g >= 0 and negatives after all non-negatives (independent of the grid size).
+// The file order is already sorted by (wrap(g3), wrap(g2), wrap(g1)) (reader.c:230-246 loop nest),
+// so two stable counting sorts (by g2, then g1) produce the target order in O(n).
+void box_order(KPointInfo& kp) {
+  const int ng = (int)(kp.G.size() / 3);
+  std::vector<int32_t> cur(ng), nxt(ng);
+  for (int w = 0; w < ng; w++) cur[w] = w;
+  bool sorted3 = true;   // verify the assumption; fall back to a comparison sort otherwise
+  auto key = [](int g, int lo, int hi) { return g >= 0 ? g : (hi + 1) + (g - lo); };
+  int lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+  for (int w = 0; w < ng; w++)
+    for (int d = 0; d < 3; d++) {
+      lo[d] = std::min(lo[d], (int)kp.G[3 * w + d]);
+      hi[d] = std::max(hi[d], (int)kp.G[3 * w + d]);
+    }
+  for (int w = 1; w < ng && sorted3; w++) {
+    long a = 0, b = 0;
+    for (int d = 2; d >= 0; d--) {
+      a = a * 4096 + key(kp.G[3 * (w - 1) + d], lo[d], hi[d]);
+      b = b * 4096 + key(kp.G[3 * w + d], lo[d], hi[d]);
+    }
+    if (a > b) sorted3 = false;
+  }
+  if (sorted3 && hi[0] - lo[0] < 4000 && hi[1] - lo[1] < 4000 && hi[2] - lo[2] < 4000) {
+    for (int d = 1; d >= 0; d--) {
+      const int nk = hi[d] - lo[d] + 2;
+      std::vector<int> cnt(nk + 1, 0);
+      for (int w = 0; w < ng; w++) cnt[key(kp.G[3 * cur[w] + d], lo[d], hi[d]) + 1]++;
+      for (int q = 0; q < nk; q++) cnt[q + 1] += cnt[q];
+      for (int w = 0; w < ng; w++) nxt[cnt[key(kp.G[3 * cur[w] + d], lo[d], hi[d])]++] = cur[w];
+      cur.swap(nxt);
+    }
+  } else {
+    std::stable_sort(cur.begin(), cur.end(), [&](int a, int b) {
+      for (int d = 0; d < 3; d++) {
+        const int ka = key(kp.G[3 * a + d], lo[d], hi[d]), kb = key(kp.G[3 * b + d], lo[d], hi[d]);
+        if (ka != kb) return ka < kb;
+      }
+      return false;
+    });
+  }
+  kp.perm = cur;
+  kp.pos.resize(ng);
+  for (int j = 0; j < ng; j++) kp.pos[kp.perm[j]] = j;
+}
+
 pawb200_pswf* ingest(ByteSource src, const double* kws) {
   HostSection hs_("ingest");
   require_device();
@@ -607,7 +684,7 @@ pawb200_pswf* ingest(ByteSource src, const double* kws) {
   wf->resident.assign(NK, 0);
   unsigned char* stage = nullptr;
   size_t stage_bytes = 0;
-  ScopedStage tm(ST_H2D);
+  IngestRing& ring = ingest_ring();
   for (int kap = 0; kap < NK; kap++) {
     const long base = 2 + (long)kap * (1 + hd.nband);
     const size_t hdr_doubles = std::min<size_t>(hd.nrecl / 8, 4 + 3 * (size_t)hd.nband);
@@ -618,11 +695,15 @@ pawb200_pswf* ingest(ByteSource src, const double* kws) {
     kp.energy.resize(hd.nband); kp.occ.resize(hd.nband);
     for (int b = 0; b < hd.nband; b++) { kp.energy[b] = rec[4 + 3 * b]; kp.occ[b] = rec[6 + 3 * b]; }
     wf->weight[kap] = kws ? kws[kap % hd.nwk] : 1.0;
-    if (kap >= hd.nwk && kp.k[0] == wf->kp[kap - hd.nwk].k[0] && kp.k[1] == wf->kp[kap - hd.nwk].k[1] &&
-        kp.k[2] == wf->kp[kap - hd.nwk].k[2]) {
-      kp.G = wf->kp[kap - hd.nwk].G;   // second spin channel: same k, same list
+    const bool same_k = kap >= hd.nwk && kp.k[0] == wf->kp[kap - hd.nwk].k[0] &&
+                        kp.k[1] == wf->kp[kap - hd.nwk].k[1] && kp.k[2] == wf->kp[kap - hd.nwk].k[2];
+    if (same_k) {   // second spin channel: same k, same list
+      kp.G = wf->kp[kap - hd.nwk].G;
+      kp.perm = wf->kp[kap - hd.nwk].perm;
+      kp.pos = wf->kp[kap - hd.nwk].pos;
     } else {
       kp.G = enumerate_g(hd, kp.k, wf->G_bounds);
+      box_order(kp);
     }
     const int ng = (int)(kp.G.size() / 3);
     if (2 * ng == kp.nplane) {
@@ -639,7 +720,7 @@ pawb200_pswf* ingest(ByteSource src, const double* kws) {
     const long ld = ((long)kp.nplane + 31) / 32 * 32;
     wf->ldc[kap] = ld;
     wf->C[kap].alloc((size_t)hd.nband * ld * sizeof(float2));
-    wf->C[kap].zero();
+    wf->C[kap].zero((size_t)hd.nband * ld * sizeof(float2));
     const unsigned char* from;
     if (src.mem) {
       from = src.mem + (base + 1) * hd.nrecl;
@@ -650,15 +731,41 @@ pawb200_pswf* ingest(ByteSource src, const double* kws) {
         CUDA_OK(cudaMallocHost((void**)&stage, need));
         stage_bytes = need;
       }
-      CUDA_OK(cudaStreamSynchronize(g_stream));
+      CUDA_OK(cudaStreamSynchronize(ring.copy));   // previous block has left the staging buffer
       src.read(stage, (base + 1) * hd.nrecl, need);
       from = stage;
     }
-    CUDA_OK(cudaMemcpy2DAsync(wf->C[kap].p, ld * sizeof(float2), from, hd.nrecl,
-                              (size_t)kp.nplane * sizeof(float2), hd.nband, cudaMemcpyHostToDevice,
-                              g_stream));
+    // raw records -> HBM on the copy stream (overlaps compute queued on the main stream), then the
+    // column permutation into box order on the main stream
+    IngestRing::Slot& sl = ring.slots[ring.next++ % 2];
+    const size_t raw_bytes = (size_t)hd.nband * ld * sizeof(float2);
+    if (raw_bytes > sl.bytes) {
+      CUDA_OK(cudaEventSynchronize(sl.consumed));
+      if (sl.p) cudaFree(sl.p);
+      CUDA_OK(cudaMalloc(&sl.p, raw_bytes));
+      sl.bytes = raw_bytes;
+    }
+    CUDA_OK(cudaStreamWaitEvent(ring.copy, sl.consumed, 0));
+    {
+      ScopedStage tm(ST_H2D, ring.copy);
+      CUDA_OK(cudaMemcpy2DAsync(sl.p, ld * sizeof(float2), from, hd.nrecl, (size_t)kp.nplane * sizeof(float2),
+                                hd.nband, cudaMemcpyHostToDevice, ring.copy));
+    }
+    CUDA_OK(cudaEventRecord(sl.filled, ring.copy));
+    CUDA_OK(cudaStreamWaitEvent(g_stream, sl.filled, 0));
+    {
+      const int half_len = kp.nplane / (wf->ncl ? 2 : 1);
+      DevBuf dperm = upload(kp.perm);
+      dim3 grid((half_len + 255) / 256, std::min(hd.nband, 64));
+      permute_coeff_kernel<<<grid, 256, 0, g_stream>>>((const float2*)sl.p, wf->C[kap].as<float2>(), ld, hd.nband,
+                                                      wf->ncl ? 2 : 1, half_len, dperm.as<int>());
+      count_launch();
+      check_launch();
+    }
+    CUDA_OK(cudaEventRecord(sl.consumed, g_stream));
   }
-  CUDA_OK(cudaStreamSynchronize(g_stream));
+  // the caller may release its buffer after we return: wait for the copies only, not for compute
+  CUDA_OK(cudaStreamSynchronize(ring.copy));
   if (stage) cudaFreeHost(stage);
   return wf.release();
 }
@@ -677,7 +784,7 @@ DevBuf build_inverse_map(const pawb200_pswf* wf, int kap, const int* fftg, std::
     const int g3 = (kp.G[3 * w + 2] + fftg[2]) % fftg[2];
     if (g1 < 0 || g2 < 0 || g3 < 0) throw std::runtime_error("FFT grid smaller than the G range");
     const long lin = ((long)g1 * fftg[1] + g2) * fftg[2] + g3;
-    inv[lin] = w;   // later plane waves overwrite earlier ones, like linalg.c:31
+    inv[lin] = kp.pos[w];   // later plane waves overwrite earlier ones, like linalg.c:31
     if (fwd) (*fwd)[w] = (int)lin;
   }
   return upload(inv);
@@ -692,6 +799,7 @@ void launch_scatter(const pawb200_pswf* wf, int kap, int slot0, int nslot, const
   const int threads = 256;
   long blocks = std::min<long>((ngrid + threads - 1) / threads, (long)g_num_sms * 16);
   ScopedStage tm(ST_SCATTER);
+  g_boxes_scattered += nslot;
   scatter_pw_kernel<<<(unsigned)blocks, threads, 0, g_stream>>>(
       wf->C[kap].as<float2>(), wf->ldc[kap], slot0 / h, h, wf->npw_half(kap), inv.as<int>(), x, ngrid,
       nslot, scale);
@@ -702,6 +810,7 @@ void launch_scatter(const pawb200_pswf* wf, int kap, int slot0, int nslot, const
 void launch_fft(double2* x, const int* fftg, int batch, int direction) {
   cufftHandle plan = get_plan(fftg, batch);
   ScopedStage tm(ST_FFT);
+  g_boxes_fft += batch;
   CUFFT_OK(cufftExecZ2Z(plan, (cufftDoubleComplex*)x, (cufftDoubleComplex*)x, direction));
 }
 
@@ -727,6 +836,7 @@ void launch_project_mt(const SiteTables& T, const double2* x, long ngrid, int ns
 void launch_project(const SiteTables& T, const double2* x, long ngrid, int nslot, double2* P, long ldp,
                     int slot0) {
   ScopedStage tm(ST_PROJECT);
+  g_slots_projected += nslot;
   launch_project_mt<1>(T, x, ngrid, nslot, P, ldp, slot0);
   launch_project_mt<2>(T, x, ngrid, nslot, P, ldp, slot0);
   launch_project_mt<3>(T, x, ngrid, nslot, P, ldp, slot0);
@@ -751,9 +861,16 @@ void make_phase_table(SiteTables& T, const pawb200_pswf* wf, int kap, const int*
 
 DevBuf g_grid;   // FFT box batch, reused across calls
 
+size_t keep_boxes_budget() {
+  const char* e = getenv("PAWB200_KEEP_BOXES_BYTES");
+  if (e) return (size_t)atoll(e);
+  return (size_t)32 << 30;
+}
+
 // All bands of all resident (k,spin) blocks of `wf` -> <table|psi~>, written to out[kap] [nslot][ld].
+// main_pass: this is setup_projections (boxes may be kept); otherwise kept boxes are reused when present.
 void project_all_bands(pawb200_pswf* wf, SiteTables& T, const int* fftg, std::vector<DevBuf>& out,
-                       long& ld) {
+                       long& ld, bool main_pass) {
   HostSection hs_("project_all_bands");
   const int NK = wf->nkappa();
   const long ngrid = (long)fftg[0] * fftg[1] * fftg[2];
@@ -766,19 +883,48 @@ void project_all_bands(pawb200_pswf* wf, SiteTables& T, const int* fftg, std::ve
   if (batch >= 32) batch = batch / 32 * 32;
   batch -= batch % wf->halves();
   batch = std::min<long>(batch, nslot);
-  g_grid.ensure((size_t)batch * ngrid * sizeof(double2));
+  int nres = 0;
+  for (int kap = 0; kap < NK; kap++) nres += wf->resident[kap] ? 1 : 0;
+  const size_t box_bytes = (size_t)nslot * ngrid * sizeof(double2);
+  const bool same_grid = wf->boxes_fftg[0] == fftg[0] && wf->boxes_fftg[1] == fftg[1] && wf->boxes_fftg[2] == fftg[2];
+  bool keep = false;
+  if (main_pass) {
+    wf->boxes.clear();
+    keep = box_bytes * (size_t)std::max(nres, 1) <= keep_boxes_budget();
+    if (keep) {
+      wf->boxes.resize(NK);
+      for (int d = 0; d < 3; d++) wf->boxes_fftg[d] = fftg[d];
+    }
+  }
   for (int kap = 0; kap < NK; kap++) {
     if (!wf->resident[kap]) continue;
     out[kap].alloc((size_t)nslot * ld * sizeof(double2));
     out[kap].zero();
     if (T.nsites == 0) continue;
-    DevBuf inv = build_inverse_map(wf, kap, fftg);
     make_phase_table(T, wf, kap, fftg);
+    const bool reuse = !main_pass && same_grid && (int)wf->boxes.size() == NK && wf->boxes[kap].p;
+    if (reuse) {
+      for (int s0 = 0; s0 < nslot; s0 += 2048) {
+        const int nb = std::min(2048, nslot - s0);
+        launch_project(T, wf->boxes[kap].as<double2>() + (long)s0 * ngrid, ngrid, nb, out[kap].as<double2>(), ld, s0);
+      }
+      continue;
+    }
+    DevBuf inv = build_inverse_map(wf, kap, fftg);
+    double2* base;
+    if (keep) {
+      wf->boxes[kap].alloc(box_bytes);
+      base = wf->boxes[kap].as<double2>();
+    } else {
+      g_grid.ensure((size_t)batch * ngrid * sizeof(double2));
+      base = g_grid.as<double2>();
+    }
     for (int s0 = 0; s0 < nslot; s0 += (int)batch) {
       const int nb = (int)std::min<long>(batch, nslot - s0);
-      launch_scatter(wf, kap, s0, nb, inv, g_grid.as<double2>(), fftg);
-      launch_fft(g_grid.as<double2>(), fftg, nb, CUFFT_INVERSE);
-      launch_project(T, g_grid.as<double2>(), ngrid, nb, out[kap].as<double2>(), ld, s0);
+      double2* x = keep ? base + (long)s0 * ngrid : base;
+      launch_scatter(wf, kap, s0, nb, inv, x, fftg);
+      launch_fft(x, fftg, nb, CUFFT_INVERSE);
+      launch_project(T, x, ngrid, nb, out[kap].as<double2>(), ld, s0);
     }
   }
 }
@@ -1268,7 +1414,7 @@ void pawb200_setup_projections(pawb200_pswf_t* wf, pawb200_ppot_t* pps, int num_
   std::vector<int> all(num_sites);
   for (int i = 0; i < num_sites; i++) all[i] = i;
   wf->proj_sites = build_site_tables(pps->list.el, all.data(), num_sites, labels, coords, wf->lattice, fftg, 0, true);
-  project_all_bands(wf, *wf->proj_sites, fftg, wf->P, wf->ldp);
+  project_all_bands(wf, *wf->proj_sites, fftg, wf->P, wf->ldp, true);
   wf->has_projections = true;
   API_END_VOID
 }
@@ -1328,13 +1474,13 @@ void pawb200_overlap_setup_real(pawb200_pswf_t* wf_R, pawb200_pswf_t* wf_S, cons
   if (num_N_R > 0) {
     auto T = build_site_tables(elsR, N_R, num_N_R, labels_R, coords_R, wf_S->lattice, wf_S->fftg, 1, false);
     for (auto& sd : T->host) wf_S->wp_nlm.push_back(sd.nlm);
-    project_all_bands(wf_S, *T, wf_S->fftg, wf_S->W, wf_S->ldw);
+    project_all_bands(wf_S, *T, wf_S->fftg, wf_S->W, wf_S->ldw, false);
   }
   // part 2 (:649-671)
   if (num_N_S > 0) {
     auto T = build_site_tables(elsS, N_S, num_N_S, labels_S, coords_S, wf_R->lattice, wf_R->fftg, 1, false);
     for (auto& sd : T->host) wf_R->wp_nlm.push_back(sd.nlm);
-    project_all_bands(wf_R, *T, wf_R->fftg, wf_R->W, wf_R->ldw);
+    project_all_bands(wf_R, *T, wf_R->fftg, wf_R->W, wf_R->ldw, false);
   }
   // part 3 (:682-719): off-site partial-wave overlaps, host side (O(pairs * channels^2) radial integrals)
   wf_S->omega.assign(num_N_RS, {});
@@ -1626,6 +1772,7 @@ void pawb200_get_timers(pawb200_timers* t) {
   t->gemm_pseudo_ms = g_stage_ms[ST_GEMM_PS]; t->gemm_aug_ms = g_stage_ms[ST_GEMM_AUG];
   t->augment_ms = g_stage_ms[ST_AUGMENT]; t->d2h_ms = g_stage_ms[ST_D2H];
   t->launches = g_launches.load();
+  t->boxes_scattered = g_boxes_scattered; t->boxes_fft = g_boxes_fft; t->slots_projected = g_slots_projected;
 }
 void pawb200_reset_timers(void) {
   drain_timers();
@@ -1633,6 +1780,7 @@ void pawb200_reset_timers(void) {
   g_hostprof.calls.clear();
   for (auto& v : g_stage_ms) v = 0;
   g_launches = 0;
+  g_boxes_scattered = g_boxes_fft = g_slots_projected = 0;
 }
 
 }  // extern "C"

@@ -114,7 +114,9 @@ struct WavecarHeader {
 struct KPointInfo {
   int nplane = 0;               // coefficients per band as stored (2*ng for noncollinear)
   double k[3];
-  std::vector<int32_t> G;       // 3 per plane wave (duplicated for ncl like reader.c:274-281)
+  std::vector<int32_t> G;       // 3 per plane wave (one spinor half), file order
+  std::vector<int32_t> perm;    // storage position j holds file coefficient perm[j] (box-index order)
+  std::vector<int32_t> pos;     // inverse of perm
   std::vector<double> energy, occ;
 };
 // Enumerate G vectors for one k-point in file order (reader.c:230-271); updates G_bounds.

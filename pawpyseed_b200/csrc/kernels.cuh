@@ -57,6 +57,20 @@ scatter_pw_kernel(const float2* __restrict__ C, long ldc, int band0, int halves,
   }
 }
 
+// One-time reorder of the coefficient columns into FFT-box index order (z runs contiguous), so the
+// scatter reads them coalesced.  Both wavefunctions of a pair get the same permutation (same G list),
+// so the band-band GEMM over the plane-wave axis is unaffected.
+__global__ void __launch_bounds__(256)
+permute_coeff_kernel(const float2* __restrict__ raw, float2* __restrict__ C, long ld, int nband,
+                     int halves, int half_len, const int* __restrict__ perm) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= half_len) return;
+  const int src = perm[j];
+  for (int b = blockIdx.y; b < nband; b += gridDim.y)
+    for (int h = 0; h < halves; h++)
+      C[(long)b * ld + (long)h * half_len + j] = raw[(long)b * ld + (long)h * half_len + src];
+}
+
 // (a3) gather back after a forward FFT  [linalg.c:72-77]; narrow to complex64
 __global__ void gather_pw_kernel(const double2* __restrict__ x, const int* __restrict__ gidx,
                                  float2* __restrict__ Cout, int npw, double scale) {
