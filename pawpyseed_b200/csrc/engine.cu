@@ -22,6 +22,7 @@
 #include "host_paw.h"
 #include "kernels.cuh"
 #include "zgemm.cuh"
+#include "fft3d.cuh"
 
 using namespace pawb200;
 
@@ -559,6 +560,7 @@ struct pawb200_pswf {
   // overlap_setup_real does not scatter + transform the bands a second time
   std::vector<DevBuf> boxes;
   int boxes_fftg[3] = {0, 0, 0};
+  bool boxes_interleaved = false;   // layout of `boxes`: [group][grid][16] (pruned FFT) or [slot][grid] (cuFFT)
   // real-space table cache (mode 2), keyed by grid + coords
   std::unique_ptr<SiteTables> ae_sites;
   // per-band call caches
@@ -861,6 +863,187 @@ void make_phase_table(SiteTables& T, const pawb200_pswf* wf, int kap, const int*
 
 DevBuf g_grid;   // FFT box batch, reused across calls
 
+// ---- pruned band-interleaved FFT (fft3d.cuh) -----------------------------------------------------------
+struct PrunedPlan {
+  bool ok = false;
+  FftGeom g;
+  DevBuf col_start, col_cnt, col_ypos, zpos, plane_col0, plane_ncol, plane_xpos, tw[3];
+};
+
+bool factor_pair(int n, int& r1, int& r2) {
+  static const int ok[] = {2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 14, 15, 16};
+  int best = 1 << 30;
+  bool found = false;
+  for (int a : ok)
+    for (int b : ok)
+      if (a * b == n && std::max(a, b) < best) {
+        best = std::max(a, b);
+        r1 = a;
+        r2 = b;
+        found = true;
+      }
+  return found;
+}
+
+void init_small_twiddles() {
+  static bool done = false;
+  if (done) return;
+  double2 h[FFT_MAXR + 1][FFT_MAXR];
+  memset(h, 0, sizeof(h));
+  for (int R = 1; R <= FFT_MAXR; R++)
+    for (int m = 0; m < R; m++) {
+      const long double a = 2.0L * 3.141592653589793238462643383279502884L * m / R;
+      h[R][m] = make_double2((double)cosl(a), (double)sinl(a));
+    }
+  CUDA_OK(cudaMemcpyToSymbol(c_small_tw, h, sizeof(h)));
+  done = true;
+}
+
+std::unique_ptr<PrunedPlan> build_pruned_plan(const pawb200_pswf* wf, int kap, const int* fftg) {
+  auto P = std::make_unique<PrunedPlan>();
+  if (getenv("PAWB200_FFT") && std::string(getenv("PAWB200_FFT")) == "cufft") return P;
+  FftGeom& g = P->g;
+  g.n1 = fftg[0]; g.n2 = fftg[1]; g.n3 = fftg[2];
+  for (int d = 0; d < 3; d++)
+    if (!factor_pair(fftg[d], g.r1[d], g.r2[d])) return P;
+  const KPointInfo& kp = wf->kp[kap];
+  const int npw = wf->npw_half(kap);
+  if (npw == 0) return P;
+  std::vector<int> col_start, col_cnt, col_ypos, zpos(npw), plane_col0, plane_ncol, plane_xpos;
+  int last1 = -1, last2 = -1, lastz = -1;
+  for (int j = 0; j < npw; j++) {
+    const int w = kp.perm[j];
+    const int a = ((kp.G[3 * w] % fftg[0]) + fftg[0]) % fftg[0];
+    const int b = ((kp.G[3 * w + 1] % fftg[1]) + fftg[1]) % fftg[1];
+    const int c = ((kp.G[3 * w + 2] % fftg[2]) + fftg[2]) % fftg[2];
+    if (std::abs(kp.G[3 * w]) >= fftg[0] || std::abs(kp.G[3 * w + 1]) >= fftg[1] || std::abs(kp.G[3 * w + 2]) >= fftg[2])
+      return P;
+    if (a != last1) {
+      if (a < last1) return P;                 // not in box order (aliased grid): use the generic path
+      plane_col0.push_back((int)col_start.size());
+      plane_ncol.push_back(0);
+      plane_xpos.push_back(a);
+      last1 = a;
+      last2 = -1;
+    }
+    if (b != last2) {
+      if (b < last2) return P;
+      col_start.push_back(j);
+      col_cnt.push_back(0);
+      col_ypos.push_back(b);
+      plane_ncol.back()++;
+      last2 = b;
+      lastz = -1;
+    }
+    if (c <= lastz) return P;                  // duplicate / unordered positions
+    lastz = c;
+    zpos[j] = c;
+    col_cnt.back()++;
+  }
+  g.ncol = (int)col_start.size();
+  g.nplane = (int)plane_col0.size();
+  P->col_start = upload(col_start); P->col_cnt = upload(col_cnt); P->col_ypos = upload(col_ypos);
+  P->zpos = upload(zpos); P->plane_col0 = upload(plane_col0); P->plane_ncol = upload(plane_ncol);
+  P->plane_xpos = upload(plane_xpos);
+  g.col_start = P->col_start.as<int>(); g.col_cnt = P->col_cnt.as<int>(); g.col_ypos = P->col_ypos.as<int>();
+  g.zpos = P->zpos.as<int>(); g.plane_col0 = P->plane_col0.as<int>(); g.plane_ncol = P->plane_ncol.as<int>();
+  g.plane_xpos = P->plane_xpos.as<int>();
+  for (int d = 0; d < 3; d++) {
+    std::vector<double2> t(fftg[d]);
+    for (int m = 0; m < fftg[d]; m++) {
+      const long double a = 2.0L * 3.141592653589793238462643383279502884L * m / fftg[d];
+      t[m] = make_double2((double)cosl(a), (double)sinl(a));
+    }
+    P->tw[d] = upload(t);
+    g.tw[d] = P->tw[d].as<double2>();
+  }
+  init_small_twiddles();
+  P->ok = true;
+  return P;
+}
+
+DevBuf g_fft_t1, g_fft_t2;
+
+// Inverse transform of slots [slot0, slot0 + nslot) of kappa into X (interleaved groups of FFT_B slots).
+template <int LPC>
+void pruned_fft_lpc(const pawb200_pswf* wf, int kap, const PrunedPlan& P, int slot0, int nslot, double2* X) {
+  const FftGeom& g = P.g;
+  constexpr int NB = FFT_B * LPC;
+  static bool configured = false;
+  if (!configured) {
+    const int big = 200 * 1024;
+    CUDA_OK(cudaFuncSetAttribute(fft_pass_z_kernel<LPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CUDA_OK(cudaFuncSetAttribute(fft_pass_y_kernel<LPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CUDA_OK(cudaFuncSetAttribute(fft_pass_x_kernel<LPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    configured = true;
+  }
+  const int ngroups = (nslot + FFT_B - 1) / FFT_B;
+  const long ngrid = (long)g.n1 * g.n2 * g.n3;
+  const size_t t1_grp = (size_t)g.ncol * g.n3 * FFT_B * sizeof(double2);
+  const size_t t2_grp = (size_t)g.nplane * g.n2 * g.n3 * FFT_B * sizeof(double2);
+  // groups per launch: enough CTAs per kernel, scratch kept small so pass outputs tend to stay in the 126 MB L2
+  int gc = 1;
+  if (const char* e = getenv("PAWB200_FFT_GROUPS")) gc = std::max(1, atoi(e));
+  gc = std::min(gc, ngroups);
+  g_fft_t1.ensure(t1_grp * gc);
+  g_fft_t2.ensure(t2_grp * gc);
+  const double scale = std::pow(determinant3(wf->lattice), -0.5);
+  const int h = wf->halves();
+  const int nzc = (g.n3 + LPC - 1) / LPC;
+  auto threads = [&](int d) { return ((std::max(g.r1[d], g.r2[d]) * NB + 31) / 32) * 32; };
+  auto smem = [&](int n) { return (size_t)(n * NB + n) * sizeof(double2); };
+  ScopedStage tm(ST_FFT);
+  g_boxes_fft += nslot;
+  for (int g0 = 0; g0 < ngroups; g0 += gc) {
+    const int ng = std::min(gc, ngroups - g0);
+    const int s0 = slot0 + g0 * FFT_B;
+    const int ns = std::min(nslot - g0 * FFT_B, ng * FFT_B);
+    fft_pass_z_kernel<LPC><<<dim3((g.ncol + LPC - 1) / LPC, ng), threads(2), smem(g.n3), g_stream>>>(
+        g, wf->C[kap].as<float2>(), wf->ldc[kap], h, wf->npw_half(kap), s0, ns, scale, g_fft_t1.as<double2>());
+    fft_pass_y_kernel<LPC><<<dim3(g.nplane * nzc, ng), threads(1), smem(g.n2), g_stream>>>(
+        g, g_fft_t1.as<double2>(), g_fft_t2.as<double2>());
+    fft_pass_x_kernel<LPC><<<dim3(g.n2 * nzc, ng), threads(0), smem(g.n1), g_stream>>>(
+        g, g_fft_t2.as<double2>(), X + (long)g0 * ngrid * FFT_B);
+    count_launch(3);
+  }
+  check_launch();
+}
+
+void pruned_fft(const pawb200_pswf* wf, int kap, const PrunedPlan& P, int slot0, int nslot, double2* X) {
+  static const int lpc = getenv("PAWB200_FFT_LPC") ? atoi(getenv("PAWB200_FFT_LPC")) : 1;
+  if (lpc == 2)
+    pruned_fft_lpc<2>(wf, kap, P, slot0, nslot, X);
+  else
+    pruned_fft_lpc<1>(wf, kap, P, slot0, nslot, X);
+}
+
+template <int MT>
+void launch_project_il_mt(const SiteTables& T, const double2* X, long ngrid, int nslot, double2* P, long ldp,
+                          int slot0) {
+  if (T.by_mt[MT].empty()) return;
+  static bool configured = false;
+  const size_t smem = sphere_project_smem(MT);
+  if (!configured) {
+    CUDA_OK(cudaFuncSetAttribute(sphere_project_il_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  dim3 grid((nslot + PROJ_NB - 1) / PROJ_NB, (unsigned)T.by_mt[MT].size());
+  sphere_project_il_kernel<MT><<<grid, 128, smem, g_stream>>>(
+      T.sites.as<SiteDev>(), T.by_mt_dev[MT].as<int>(), T.idx.as<int>(), T.tablek.as<double2>(), X, ngrid, nslot,
+      (nslot + FFT_B - 1) / FFT_B, P, ldp, slot0);
+  count_launch();
+  check_launch();
+}
+
+void launch_project_il(const SiteTables& T, const double2* X, long ngrid, int nslot, double2* P, long ldp,
+                       int slot0) {
+  ScopedStage tm(ST_PROJECT);
+  g_slots_projected += nslot;
+  launch_project_il_mt<1>(T, X, ngrid, nslot, P, ldp, slot0);
+  launch_project_il_mt<2>(T, X, ngrid, nslot, P, ldp, slot0);
+  launch_project_il_mt<3>(T, X, ngrid, nslot, P, ldp, slot0);
+}
+
 size_t keep_boxes_budget() {
   const char* e = getenv("PAWB200_KEEP_BOXES_BYTES");
   if (e) return (size_t)atoll(e);
@@ -896,6 +1079,8 @@ void project_all_bands(pawb200_pswf* wf, SiteTables& T, const int* fftg, std::ve
       for (int d = 0; d < 3; d++) wf->boxes_fftg[d] = fftg[d];
     }
   }
+  const int ngroups_all = (nslot + FFT_B - 1) / FFT_B;
+  const size_t il_bytes = (size_t)ngroups_all * FFT_B * ngrid * sizeof(double2);
   for (int kap = 0; kap < NK; kap++) {
     if (!wf->resident[kap]) continue;
     out[kap].alloc((size_t)nslot * ld * sizeof(double2));
@@ -906,7 +1091,31 @@ void project_all_bands(pawb200_pswf* wf, SiteTables& T, const int* fftg, std::ve
     if (reuse) {
       for (int s0 = 0; s0 < nslot; s0 += 2048) {
         const int nb = std::min(2048, nslot - s0);
-        launch_project(T, wf->boxes[kap].as<double2>() + (long)s0 * ngrid, ngrid, nb, out[kap].as<double2>(), ld, s0);
+        if (wf->boxes_interleaved)
+          launch_project_il(T, wf->boxes[kap].as<double2>() + (long)s0 * ngrid, ngrid, nb, out[kap].as<double2>(), ld, s0);
+        else
+          launch_project(T, wf->boxes[kap].as<double2>() + (long)s0 * ngrid, ngrid, nb, out[kap].as<double2>(), ld, s0);
+      }
+      continue;
+    }
+    std::unique_ptr<PrunedPlan> plan = build_pruned_plan(wf, kap, fftg);
+    if (plan->ok) {
+      // pruned band-interleaved FFT: chunks of whole 32-slot CTAs
+      long chunk = std::max<long>(32, batch / 32 * 32);
+      double2* base;
+      if (keep) {
+        wf->boxes[kap].alloc(il_bytes);
+        wf->boxes_interleaved = true;
+        base = wf->boxes[kap].as<double2>();
+      } else {
+        g_grid.ensure((size_t)chunk * ngrid * sizeof(double2));
+        base = g_grid.as<double2>();
+      }
+      for (int s0 = 0; s0 < nslot; s0 += (int)chunk) {
+        const int nb = (int)std::min<long>(chunk, nslot - s0);
+        double2* x = keep ? base + (long)s0 * ngrid : base;
+        pruned_fft(wf, kap, *plan, s0, nb, x);
+        launch_project_il(T, x, ngrid, nb, out[kap].as<double2>(), ld, s0);
       }
       continue;
     }
@@ -914,6 +1123,7 @@ void project_all_bands(pawb200_pswf* wf, SiteTables& T, const int* fftg, std::ve
     double2* base;
     if (keep) {
       wf->boxes[kap].alloc(box_bytes);
+      wf->boxes_interleaved = false;
       base = wf->boxes[kap].as<double2>();
     } else {
       g_grid.ensure((size_t)batch * ngrid * sizeof(double2));

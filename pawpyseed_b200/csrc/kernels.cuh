@@ -352,6 +352,86 @@ sphere_project_kernel(const SiteDev* __restrict__ sites, const int* __restrict__
   }
 }
 
+// Same contraction on band-interleaved boxes X[group][grid point][IL] (IL = 16 slots = 256 B per point,
+// produced by the pruned FFT of fft3d.cuh): every gathered point is two full 256-B segments, so the DRAM
+// traffic equals the algorithmic 16 B per (point, band).
+template <int MT>
+__global__ void __launch_bounds__(128)
+sphere_project_il_kernel(const SiteDev* __restrict__ sites, const int* __restrict__ site_list,
+                         const int* __restrict__ idx, const double2* __restrict__ tablek,
+                         const double2* __restrict__ X, long ngrid, int nslot, int ngroups,
+                         double2* __restrict__ P, long ldp, int slot0) {
+  constexpr int IL = 16;
+  const SiteDev sd = sites[site_list[blockIdx.y]];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double2* sB = reinterpret_cast<double2*>(smem_raw);                       // [ST][KT][LDB]
+  double2* sA = sB + PROJ_STAGES * PROJ_KT * PROJ_LDB;                      // [ST][8*MT][LDA]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int sbase = blockIdx.x * PROJ_NB;
+  const int nk = sd.npts_pad / PROJ_KT;
+  for (int e = tid; e < PROJ_STAGES * 8 * MT * PROJ_LDA; e += 128) {
+    const int row = (e / PROJ_LDA) % (8 * MT);
+    if (row >= sd.nlm) sA[e] = make_double2(0, 0);
+  }
+  int grp = (sbase + lane) / IL;
+  if (grp >= ngroups) grp = ngroups - 1;          // tail CTA: duplicate the last group, discarded on store
+  const double2* xsrc = X + (long)grp * ngrid * IL + (lane & (IL - 1));
+
+  auto issue = [&](int kt, int st) {
+    if (kt < nk) {
+#pragma unroll
+      for (int q = 0; q < PROJ_KT / 4; q++) {
+        const int pt = warp + 4 * q;
+        const int g = __ldg(idx + sd.pt_off + kt * PROJ_KT + pt);     // warp-uniform -> broadcast
+        cp_async16(sB + (st * PROJ_KT + pt) * PROJ_LDB + lane, xsrc + (long)g * IL);
+      }
+      for (int row = warp; row < sd.nlm; row += 4)
+        cp_async16(sA + (st * 8 * MT + row) * PROJ_LDA + lane,
+                   tablek + sd.tab_off + (long)row * sd.npts_pad + kt * PROJ_KT + lane);
+    }
+    cp_async_commit();
+  };
+
+  double rr[MT][2], ii[MT][2], ri[MT][2];
+#pragma unroll
+  for (int m = 0; m < MT; m++) rr[m][0] = rr[m][1] = ii[m][0] = ii[m][1] = ri[m][0] = ri[m][1] = 0;
+#pragma unroll
+  for (int s = 0; s < PROJ_STAGES - 1; s++) issue(s, s);
+  for (int kt = 0; kt < nk; kt++) {
+    cp_async_wait<PROJ_STAGES - 2>();
+    __syncthreads();
+    issue(kt + PROJ_STAGES - 1, (kt + PROJ_STAGES - 1) % PROJ_STAGES);
+    const int st = kt % PROJ_STAGES;
+    const double2* tB = sB + st * PROJ_KT * PROJ_LDB;
+    const double2* tA = sA + st * 8 * MT * PROJ_LDA;
+#pragma unroll
+    for (int kk = 0; kk < PROJ_KT / 4; kk++) {
+      const double2 b = tB[(4 * kk + (lane & 3)) * PROJ_LDB + 8 * warp + (lane >> 2)];
+#pragma unroll
+      for (int m = 0; m < MT; m++) {
+        const double2 a = tA[(8 * m + (lane >> 2)) * PROJ_LDA + 4 * kk + (lane & 3)];
+        dmma884(rr[m][0], rr[m][1], a.x, b.x);
+        dmma884(ii[m][0], ii[m][1], a.y, b.y);
+        dmma884(ri[m][0], ri[m][1], a.x, b.y);
+        dmma884(ri[m][0], ri[m][1], a.y, b.x);
+      }
+    }
+  }
+  cp_async_wait<0>();
+#pragma unroll
+  for (int m = 0; m < MT; m++) {
+    const int ch = 8 * m + (lane >> 2);
+    if (ch < sd.nlm) {
+#pragma unroll
+      for (int c = 0; c < 2; c++) {
+        const int s = sbase + 8 * warp + 2 * (lane & 3) + c;
+        if (s < nslot)
+          P[(long)(slot0 + s) * ldp + sd.lm_off + ch] = make_double2(rr[m][c] - ii[m][c], ri[m][c]);
+      }
+    }
+  }
+}
+
 inline size_t sphere_project_smem(int MT) {
   return sizeof(double2) * PROJ_STAGES * (PROJ_KT * PROJ_LDB + 8 * MT * PROJ_LDA);
 }
