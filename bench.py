@@ -216,6 +216,7 @@ def run_b200(args):
     nband, NK = w["nband"], world * w["nspin"]
     own = {k for k in range(NK) if k % world == rank}
     L.pawb200_set_read_shard(rank, world)
+    L.pawb200_set_host_threads(max(1, (os.cpu_count() or 1) // world))   # torchrun exports OMP_NUM_THREADS=1
     imgs = make_images(w, own=own, pinned=True)
     h2d_bytes = sum(2 * 8 * nband * len(w["gvecs"][k % world]) for k in own)   # both structures
     d2h_bytes = 16 * nband * nband * len(own)
@@ -296,6 +297,10 @@ def run_b200(args):
         dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
     e2e_value = pairs_total / (float(ms2.item()) / e2e_steps * 1e-3)
 
+    if os.environ.get("PAWB200_BENCH_DEBUG"):
+        sys.stderr.write("[rank %d] dev_ms/step %.2f wall_ms/step %.2f stages %s\n" % (
+            rank, dev_ms / args.steps, wall * 1e3 / args.steps,
+            {k: round(v / args.steps, 2) for k, v in tm.items() if k.endswith("_ms")}))
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

@@ -153,6 +153,9 @@ void pawb200_projection_matrix(pawb200_c128 *out, pawb200_pswf_t *wf_S, pawb200_
  * only the (k,spin) blocks with kappa % world == rank in HBM; blocks of other ranks come back
  * as zeros from pawb200_projection_matrix and are summed/gathered by the caller (NCCL). */
 void pawb200_set_read_shard(int rank, int world);
+/* OpenMP threads for the host-side setup (sphere geometry, NumSBT); launchers such as torchrun export
+ * OMP_NUM_THREADS=1, which would serialise it. */
+void pawb200_set_host_threads(int n);
 /* Drop the (k,spin) blocks outside [kappa_lo, kappa_hi) from this process. */
 void pawb200_set_kappa_range(pawb200_pswf_t *wf, int kappa_lo, int kappa_hi);
 /* Copy <p_i|psi~> for (band, kappa) to host: nproj_total complex128, site-major channel order.

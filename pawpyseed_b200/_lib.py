@@ -89,6 +89,7 @@ _SIGS = {
                                          C.c_int] + [c_int_p] * 6 + [C.c_int, C.c_int, C.c_int, C.c_int]),
     "pawb200_set_kappa_range": (None, [C.c_void_p, C.c_int, C.c_int]),
     "pawb200_set_read_shard": (None, [C.c_int, C.c_int]),
+    "pawb200_set_host_threads": (None, [C.c_int]),
     "pawb200_get_projections": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_dbl_p]),
     "pawb200_num_projections": (C.c_int, [C.c_void_p, C.c_int]),
     "pawb200_get_channel_index": (C.c_int, [C.c_void_p, c_int_p]),

@@ -867,7 +867,7 @@ DevBuf g_grid;   // FFT box batch, reused across calls
 struct PrunedPlan {
   bool ok = false;
   FftGeom g;
-  DevBuf col_start, col_cnt, col_ypos, zpos, plane_col0, plane_ncol, plane_xpos, tw[3];
+  DevBuf col_start, col_cnt, zpos, ysrc, xsrc, tw[3];
 };
 
 bool factor_pair(int n, int& r1, int& r2) {
@@ -942,12 +942,15 @@ std::unique_ptr<PrunedPlan> build_pruned_plan(const pawb200_pswf* wf, int kap, c
   }
   g.ncol = (int)col_start.size();
   g.nplane = (int)plane_col0.size();
-  P->col_start = upload(col_start); P->col_cnt = upload(col_cnt); P->col_ypos = upload(col_ypos);
-  P->zpos = upload(zpos); P->plane_col0 = upload(plane_col0); P->plane_ncol = upload(plane_ncol);
-  P->plane_xpos = upload(plane_xpos);
-  g.col_start = P->col_start.as<int>(); g.col_cnt = P->col_cnt.as<int>(); g.col_ypos = P->col_ypos.as<int>();
-  g.zpos = P->zpos.as<int>(); g.plane_col0 = P->plane_col0.as<int>(); g.plane_ncol = P->plane_ncol.as<int>();
-  g.plane_xpos = P->plane_xpos.as<int>();
+  std::vector<int> ysrc((size_t)g.nplane * fftg[1], -1), xsrc(fftg[0], -1);
+  for (int p = 0; p < g.nplane; p++) {
+    xsrc[plane_xpos[p]] = p;
+    for (int c = plane_col0[p]; c < plane_col0[p] + plane_ncol[p]; c++) ysrc[(size_t)p * fftg[1] + col_ypos[c]] = c;
+  }
+  P->col_start = upload(col_start); P->col_cnt = upload(col_cnt); P->zpos = upload(zpos);
+  P->ysrc = upload(ysrc); P->xsrc = upload(xsrc);
+  g.col_start = P->col_start.as<int>(); g.col_cnt = P->col_cnt.as<int>(); g.zpos = P->zpos.as<int>();
+  g.ysrc = P->ysrc.as<int>(); g.xsrc = P->xsrc.as<int>();
   for (int d = 0; d < 3; d++) {
     std::vector<double2> t(fftg[d]);
     for (int m = 0; m < fftg[d]; m++) {
@@ -965,23 +968,30 @@ std::unique_ptr<PrunedPlan> build_pruned_plan(const pawb200_pswf* wf, int kap, c
 DevBuf g_fft_t1, g_fft_t2;
 
 // Inverse transform of slots [slot0, slot0 + nslot) of kappa into X (interleaved groups of FFT_B slots).
-template <int LPC>
-void pruned_fft_lpc(const pawb200_pswf* wf, int kap, const PrunedPlan& P, int slot0, int nslot, double2* X) {
+template <int RMAX>
+void pruned_fft_r(const pawb200_pswf* wf, int kap, const PrunedPlan& P, int slot0, int nslot, double2* X) {
   const FftGeom& g = P.g;
-  constexpr int NB = FFT_B * LPC;
   static bool configured = false;
+  int occ[3] = {1, 1, 1};
+  const size_t smem_z = (size_t)(2 * g.n3 * FFT_B + g.n3) * sizeof(double2);
+  const size_t smem_y = (size_t)(2 * g.n2 * FFT_B + g.n2) * sizeof(double2);
+  const size_t smem_x = (size_t)(2 * g.n1 * FFT_B + g.n1) * sizeof(double2);
   if (!configured) {
     const int big = 200 * 1024;
-    CUDA_OK(cudaFuncSetAttribute(fft_pass_z_kernel<LPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    CUDA_OK(cudaFuncSetAttribute(fft_pass_y_kernel<LPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    CUDA_OK(cudaFuncSetAttribute(fft_pass_x_kernel<LPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CUDA_OK(cudaFuncSetAttribute(fft_pass_z_kernel<RMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CUDA_OK(cudaFuncSetAttribute(fft_pass_y_kernel<RMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CUDA_OK(cudaFuncSetAttribute(fft_pass_x_kernel<RMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     configured = true;
   }
+  auto threads = [&](int d) { return std::max(g.r1[d], g.r2[d]) * FFT_B; };
+  CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[0], fft_pass_z_kernel<RMAX>, threads(2), smem_z));
+  CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], fft_pass_y_kernel<RMAX>, threads(1), smem_y));
+  CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[2], fft_pass_x_kernel<RMAX>, threads(0), smem_x));
   const int ngroups = (nslot + FFT_B - 1) / FFT_B;
   const long ngrid = (long)g.n1 * g.n2 * g.n3;
   const size_t t1_grp = (size_t)g.ncol * g.n3 * FFT_B * sizeof(double2);
   const size_t t2_grp = (size_t)g.nplane * g.n2 * g.n3 * FFT_B * sizeof(double2);
-  // groups per launch: enough CTAs per kernel, scratch kept small so pass outputs tend to stay in the 126 MB L2
+  // groups per launch: scratch kept small so pass outputs tend to stay in the 126 MB L2
   int gc = 1;
   if (const char* e = getenv("PAWB200_FFT_GROUPS")) gc = std::max(1, atoi(e));
   gc = std::min(gc, ngroups);
@@ -989,32 +999,31 @@ void pruned_fft_lpc(const pawb200_pswf* wf, int kap, const PrunedPlan& P, int sl
   g_fft_t2.ensure(t2_grp * gc);
   const double scale = std::pow(determinant3(wf->lattice), -0.5);
   const int h = wf->halves();
-  const int nzc = (g.n3 + LPC - 1) / LPC;
-  auto threads = [&](int d) { return ((std::max(g.r1[d], g.r2[d]) * NB + 31) / 32) * 32; };
-  auto smem = [&](int n) { return (size_t)(n * NB + n) * sizeof(double2); };
+  auto grid = [&](long lines, int o) { return (unsigned)std::min<long>(lines, (long)g_num_sms * std::max(o, 1)); };
   ScopedStage tm(ST_FFT);
   g_boxes_fft += nslot;
   for (int g0 = 0; g0 < ngroups; g0 += gc) {
     const int ng = std::min(gc, ngroups - g0);
     const int s0 = slot0 + g0 * FFT_B;
     const int ns = std::min(nslot - g0 * FFT_B, ng * FFT_B);
-    fft_pass_z_kernel<LPC><<<dim3((g.ncol + LPC - 1) / LPC, ng), threads(2), smem(g.n3), g_stream>>>(
-        g, wf->C[kap].as<float2>(), wf->ldc[kap], h, wf->npw_half(kap), s0, ns, scale, g_fft_t1.as<double2>());
-    fft_pass_y_kernel<LPC><<<dim3(g.nplane * nzc, ng), threads(1), smem(g.n2), g_stream>>>(
-        g, g_fft_t1.as<double2>(), g_fft_t2.as<double2>());
-    fft_pass_x_kernel<LPC><<<dim3(g.n2 * nzc, ng), threads(0), smem(g.n1), g_stream>>>(
-        g, g_fft_t2.as<double2>(), X + (long)g0 * ngrid * FFT_B);
+    fft_pass_z_kernel<RMAX><<<grid((long)ng * g.ncol, occ[0]), threads(2), smem_z, g_stream>>>(
+        g, wf->C[kap].as<float2>(), wf->ldc[kap], h, wf->npw_half(kap), s0, ns, scale, g_fft_t1.as<double2>(), ng);
+    fft_pass_y_kernel<RMAX><<<grid((long)ng * g.nplane * g.n3, occ[1]), threads(1), smem_y, g_stream>>>(
+        g, g_fft_t1.as<double2>(), g_fft_t2.as<double2>(), ng);
+    fft_pass_x_kernel<RMAX><<<grid((long)ng * g.n2 * g.n3, occ[2]), threads(0), smem_x, g_stream>>>(
+        g, g_fft_t2.as<double2>(), X + (long)g0 * ngrid * FFT_B, ng);
     count_launch(3);
   }
   check_launch();
 }
 
 void pruned_fft(const pawb200_pswf* wf, int kap, const PrunedPlan& P, int slot0, int nslot, double2* X) {
-  static const int lpc = getenv("PAWB200_FFT_LPC") ? atoi(getenv("PAWB200_FFT_LPC")) : 1;
-  if (lpc == 2)
-    pruned_fft_lpc<2>(wf, kap, P, slot0, nslot, X);
+  int rmax = 0;
+  for (int d = 0; d < 3; d++) rmax = std::max({rmax, P.g.r1[d], P.g.r2[d]});
+  if (rmax <= 10)
+    pruned_fft_r<10>(wf, kap, P, slot0, nslot, X);
   else
-    pruned_fft_lpc<1>(wf, kap, P, slot0, nslot, X);
+    pruned_fft_r<16>(wf, kap, P, slot0, nslot, X);
 }
 
 template <int MT>
@@ -1532,6 +1541,10 @@ int pawb200_device_check(void) {
   require_device();
   return 0;
   API_END(-1)
+}
+
+void pawb200_set_host_threads(int n) {
+  if (n > 0) omp_set_num_threads(n);
 }
 
 void pawb200_set_read_shard(int rank, int world) {

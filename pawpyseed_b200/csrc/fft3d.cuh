@@ -105,74 +105,51 @@ struct SmallDFT {
   }
 };
 
-template <int R>
-__device__ __forceinline__ void fft_phase1(double2* __restrict__ data, const double2* __restrict__ tw, int R2,
-                                           int NB, int j2, int e) {
-  double2 v[R];
-#pragma unroll
-  for (int j1 = 0; j1 < R; j1++) v[j1] = data[(j1 * R2 + j2) * NB + e];
-  SmallDFT<R, 1>::run(v);
-#pragma unroll
-  for (int k1 = 0; k1 < R; k1++) {
-    double2 x = v[k1];
-    if (k1 > 0 && j2 > 0) x = cmulf(x, tw[j2 * k1]);
-    data[(k1 * R2 + j2) * NB + e] = x;
-  }
-}
-
-template <int R>
-__device__ __forceinline__ void fft_phase2_load(const double2* __restrict__ data, int NB, int k1, int e,
-                                                double2* v) {
-#pragma unroll
-  for (int j2 = 0; j2 < R; j2++) v[j2] = data[(k1 * R + j2) * NB + e];
-  SmallDFT<R, 1>::run(v);
-}
-template <int R>
-__device__ __forceinline__ void fft_phase2_store(double2* __restrict__ data, int R1, int NB, int k1, int e,
-                                                 const double2* v) {
-#pragma unroll
-  for (int k2 = 0; k2 < R; k2++) data[(k1 + R1 * k2) * NB + e] = v[k2];
-}
-
+// RMAX (template parameter of the pass kernels) prunes the large-radix bodies so that grids whose factors
+// are all <= 10 (e.g. 90 = 9 x 10) compile to a low-register kernel with 6 resident CTAs per SM.
 #define PAWB200_RADIX_SWITCH(R, CALL)                                                            \
   switch (R) {                                                                                    \
     case 2: CALL(2); break;   case 3: CALL(3); break;   case 4: CALL(4); break;                   \
     case 5: CALL(5); break;   case 6: CALL(6); break;   case 7: CALL(7); break;                   \
     case 8: CALL(8); break;   case 9: CALL(9); break;   case 10: CALL(10); break;                 \
-    case 12: CALL(12); break; case 14: CALL(14); break; case 15: CALL(15); break;                 \
-    case 16: CALL(16); break; default: break;                                                     \
+    default:                                                                                      \
+      if constexpr (RMAX > 10) {                                                                  \
+        switch (R) {                                                                              \
+          case 12: CALL(12); break; case 14: CALL(14); break; case 15: CALL(15); break;           \
+          case 16: CALL(16); break; default: break;                                               \
+        }                                                                                         \
+      }                                                                                           \
+      break;                                                                                      \
   }
 
-// In-place inverse DFT of NB independent length-n = R1*R2 sequences stored as data[n][NB].
-// Every thread of the CTA must call this (it contains __syncthreads()); blockDim >= max(R1,R2)*NB.
-__device__ __forceinline__ void fft_lines_smem(double2* data, const double2* tw, int R1, int R2, int NB) {
-  const int tid = threadIdx.x;
-  {
-    const int j2 = tid / NB, e = tid % NB;
-    if (j2 < R2) {
-#define P1(R) fft_phase1<R>(data, tw, R2, NB, j2, e)
-      PAWB200_RADIX_SWITCH(R1, P1)
-#undef P1
-    }
+// Two-factor line transform n = R1*R2 of FFT_B interleaved bands, thread = (q, band):
+//   phase 1 (q = j2 < R2): v[j1] = x[j1*R2 + j2]  (fetched by `load(row)`), R1-point DFT, twiddle
+//                          w_n^(j2*k1), written to shared buf[(k1*R2 + j2)][band];
+//   phase 2 (q = k1 < R1): R2-point DFT over buf[k1*R2 + j2], result X[k1 + R1*k2] handed to `store(row, v)`.
+// Inputs come straight from global memory into registers and outputs go straight back, so a line costs one
+// shared-memory round trip and one barrier (buf is double buffered by the caller).
+template <int R, class Load>
+__device__ __forceinline__ void line_phase1(double2* __restrict__ buf, const double2* __restrict__ tw, int R2,
+                                            int j2, int b, Load load) {
+  double2 v[R];
+#pragma unroll
+  for (int j1 = 0; j1 < R; j1++) v[j1] = load(j1 * R2 + j2);
+  SmallDFT<R, 1>::run(v);
+#pragma unroll
+  for (int k1 = 0; k1 < R; k1++) {
+    double2 x = v[k1];
+    if (k1 > 0 && j2 > 0) x = cmulf(x, tw[j2 * k1]);
+    buf[(k1 * R2 + j2) * FFT_B + b] = x;
   }
-  __syncthreads();
-  {
-    const int k1 = tid / NB, e = tid % NB;
-    double2 v[FFT_MAXR];
-    const bool act = k1 < R1;
-    if (act) {
-#define P2L(R) fft_phase2_load<R>(data, NB, k1, e, v)
-      PAWB200_RADIX_SWITCH(R2, P2L)
-#undef P2L
-    }
-    __syncthreads();
-    if (act) {
-#define P2S(R) fft_phase2_store<R>(data, R1, NB, k1, e, v)
-      PAWB200_RADIX_SWITCH(R2, P2S)
-#undef P2S
-    }
-  }
-  __syncthreads();
+}
+template <int R, class Store>
+__device__ __forceinline__ void line_phase2(const double2* __restrict__ buf, int R1, int k1, int b, Store store) {
+  double2 v[R];
+#pragma unroll
+  for (int j2 = 0; j2 < R; j2++) v[j2] = buf[(k1 * R + j2) * FFT_B + b];
+  SmallDFT<R, 1>::run(v);
+#pragma unroll
+  for (int k2 = 0; k2 < R; k2++) store(k1 + R1 * k2, v[k2]);
 }
 
 struct FftGeom {            // device-side description of one (k-point, grid) pruned transform
@@ -181,114 +158,142 @@ struct FftGeom {            // device-side description of one (k-point, grid) pr
   int ncol, nplane;         // active (g1,g2) columns / active g1 planes
   const int* col_start;     // [ncol] first sorted plane-wave index of the column
   const int* col_cnt;       // [ncol]
-  const int* col_ypos;      // [ncol] wrapped g2
   const int* zpos;          // [npw]  wrapped g3 of each sorted plane wave
-  const int* plane_col0;    // [nplane] first column of the plane
-  const int* plane_ncol;    // [nplane]
-  const int* plane_xpos;    // [nplane] wrapped g1
+  const int* ysrc;          // [nplane][n2] column index holding (plane, y) or -1
+  const int* xsrc;          // [n1] plane index holding x or -1
   const double2* tw[3];     // exp(+2 pi i m / n_d), m < n_d
 };
 
+template <int RMAX> struct FftLaunch {
+  static constexpr int THREADS = RMAX * FFT_B;          // q-slots x 16 bands
+  static constexpr int MINB = RMAX <= 10 ? 5 : 2;       // resident CTAs per SM the register budget is tuned for
+};
+
 // ---- pass Z: coefficients -> T1[group][col][z][FFT_B] ---------------------------------------------
-// slot -> coefficient row like scatter_pw_kernel: band = slot / halves, half = slot % halves
-template <int LPC>
-__global__ void __launch_bounds__(FFT_MAXR * FFT_B * LPC, LPC == 1 ? 3 : 1)
+// slot -> coefficient row like scatter_pw_kernel: band = slot / halves, half = slot % halves.
+// The sparse column (z-run of plane waves) is staged through shared memory with coalesced reads.
+template <int RMAX>
+__global__ void __launch_bounds__(FftLaunch<RMAX>::THREADS, FftLaunch<RMAX>::MINB)
 fft_pass_z_kernel(FftGeom g, const float2* __restrict__ C, long ldc, int halves, int half_len, int slot0,
-                  int nslot, double scale, double2* __restrict__ T1) {
-  constexpr int NB = FFT_B * LPC;
+                  int nslot, double scale, double2* __restrict__ T1, int ngroups) {
   extern __shared__ __align__(16) unsigned char fft_smem[];
-  double2* data = reinterpret_cast<double2*>(fft_smem);      // [n3][NB]
-  double2* tw = data + g.n3 * NB;                             // [n3]
-  const int grp = blockIdx.y, col0 = blockIdx.x * LPC;
-  const int tid = threadIdx.x, nthr = blockDim.x;
-  for (int i = tid; i < g.n3 * NB; i += nthr) data[i] = make_double2(0, 0);
-  for (int i = tid; i < g.n3; i += nthr) tw[i] = g.tw[2][i];
-  __syncthreads();
-  // sparse load: warp <-> (line, band), lanes <-> consecutive plane waves of the column (contiguous 8-B reads)
-  const int warp = tid >> 5, lane = tid & 31, nwarp = nthr >> 5;
-  for (int q = warp; q < NB; q += nwarp) {
-    const int lc = q / FFT_B, b = q % FFT_B;
-    const int col = col0 + lc;
-    if (col >= g.ncol) continue;
-    int slot = slot0 + grp * FFT_B + b;
-    if (slot >= slot0 + nslot) continue;            // pad bands of the last group stay zero
-    const int band = slot / halves, half = slot % halves;
-    const float2* row = C + (long)band * ldc + (long)half * half_len;
+  double2* in = reinterpret_cast<double2*>(fft_smem);        // [n3][FFT_B] sparse input column
+  double2* buf = in + g.n3 * FFT_B;                          // [n3][FFT_B] exchange buffer
+  double2* tw = buf + g.n3 * FFT_B;                          // [n3]
+  const int tid = threadIdx.x, q = tid / FFT_B, b = tid % FFT_B;
+  const int warp = tid >> 5, lane = tid & 31, nwarp = blockDim.x >> 5;
+  const int R1 = g.r1[2], R2 = g.r2[2];
+  for (int i = tid; i < g.n3; i += blockDim.x) tw[i] = g.tw[2][i];
+  const long nlines = (long)ngroups * g.ncol;
+  for (long line = blockIdx.x; line < nlines; line += gridDim.x) {
+    const int grp = (int)(line / g.ncol), col = (int)(line % g.ncol);
+    __syncthreads();                                         // previous line is done with `in` and `buf`
+    for (int i = tid; i < g.n3 * FFT_B; i += blockDim.x) in[i] = make_double2(0, 0);
+    __syncthreads();
     const int s = g.col_start[col], cnt = g.col_cnt[col];
-    for (int j = lane; j < cnt; j += 32) {
-      const float2 c = __ldg(row + s + j);
-      data[g.zpos[s + j] * NB + q] = make_double2(scale * (double)c.x, scale * (double)c.y);
+    for (int bb = warp; bb < FFT_B; bb += nwarp) {           // warp <-> band, lanes <-> consecutive plane waves
+      const int slot = slot0 + grp * FFT_B + bb;
+      if (slot >= slot0 + nslot) continue;                   // pad bands of the last group stay zero
+      const float2* row = C + (long)(slot / halves) * ldc + (long)(slot % halves) * half_len;
+      for (int j = lane; j < cnt; j += 32) {
+        const float2 c = __ldg(row + s + j);
+        in[g.zpos[s + j] * FFT_B + bb] = make_double2(scale * (double)c.x, scale * (double)c.y);
+      }
     }
-  }
-  __syncthreads();
-  fft_lines_smem(data, tw, g.r1[2], g.r2[2], NB);
-  // store: T1[((grp*ncol + col)*n3 + z)*FFT_B + b]
-  for (int i = tid; i < g.n3 * NB; i += nthr) {
-    const int b = i % FFT_B, z = (i / FFT_B) % g.n3, lc = i / (FFT_B * g.n3);
-    const int col = col0 + lc;
-    if (col < g.ncol) T1[(((long)grp * g.ncol + col) * g.n3 + z) * FFT_B + b] = data[z * NB + lc * FFT_B + b];
+    __syncthreads();
+    if (q < R2) {
+      auto load = [&](int row) { return in[row * FFT_B + b]; };
+#define P1(R) line_phase1<R>(buf, tw, R2, q, b, load)
+      PAWB200_RADIX_SWITCH(R1, P1)
+#undef P1
+    }
+    __syncthreads();
+    if (q < R1) {
+      double2* out = T1 + (((long)grp * g.ncol + col) * g.n3) * FFT_B + b;
+      auto store = [&](int row, double2 v) { out[(long)row * FFT_B] = v; };
+#define P2(R) line_phase2<R>(buf, R1, q, b, store)
+      PAWB200_RADIX_SWITCH(R2, P2)
+#undef P2
+    }
   }
 }
 
 // ---- pass Y: T1 -> T2[group][plane][y][z][FFT_B] ------------------------------------------------------
-template <int LPC>
-__global__ void __launch_bounds__(FFT_MAXR * FFT_B * LPC, LPC == 1 ? 3 : 1)
-fft_pass_y_kernel(FftGeom g, const double2* __restrict__ T1, double2* __restrict__ T2) {
-  constexpr int NB = FFT_B * LPC;
+template <int RMAX>
+__global__ void __launch_bounds__(FftLaunch<RMAX>::THREADS, FftLaunch<RMAX>::MINB)
+fft_pass_y_kernel(FftGeom g, const double2* __restrict__ T1, double2* __restrict__ T2, int ngroups) {
   extern __shared__ __align__(16) unsigned char fft_smem[];
-  double2* data = reinterpret_cast<double2*>(fft_smem);      // [n2][NB]
-  double2* tw = data + g.n2 * NB;
-  const int nzc = (g.n3 + LPC - 1) / LPC;
-  const int p = blockIdx.x / nzc, z0 = (blockIdx.x % nzc) * LPC, grp = blockIdx.y;
-  const int tid = threadIdx.x, nthr = blockDim.x;
-  for (int i = tid; i < g.n2 * NB; i += nthr) data[i] = make_double2(0, 0);
-  for (int i = tid; i < g.n2; i += nthr) tw[i] = g.tw[1][i];
+  double2* bufs = reinterpret_cast<double2*>(fft_smem);      // [2][n2][FFT_B]
+  double2* tw = bufs + 2 * g.n2 * FFT_B;
+  const int tid = threadIdx.x, q = tid / FFT_B, b = tid % FFT_B;
+  const int R1 = g.r1[1], R2 = g.r2[1];
+  for (int i = tid; i < g.n2; i += blockDim.x) tw[i] = g.tw[1][i];
   __syncthreads();
-  const int c0 = g.plane_col0[p], nc = g.plane_ncol[p];
-  for (int i = tid; i < nc * NB; i += nthr) {
-    const int e = i % NB, c = c0 + i / NB;
-    const int lz = e / FFT_B, b = e % FFT_B;
-    if (z0 + lz < g.n3)
-      data[g.col_ypos[c] * NB + e] = T1[(((long)grp * g.ncol + c) * g.n3 + z0 + lz) * FFT_B + b];
-  }
-  __syncthreads();
-  fft_lines_smem(data, tw, g.r1[1], g.r2[1], NB);
-  for (int i = tid; i < g.n2 * NB; i += nthr) {
-    const int e = i % NB, y = i / NB;
-    const int lz = e / FFT_B, b = e % FFT_B;
-    if (z0 + lz < g.n3)
-      T2[((((long)grp * g.nplane + p) * g.n2 + y) * g.n3 + z0 + lz) * FFT_B + b] = data[y * NB + e];
+  const long nlines = (long)ngroups * g.nplane * g.n3;
+  int it = 0;
+  for (long line = blockIdx.x; line < nlines; line += gridDim.x, it++) {
+    const int z = (int)(line % g.n3);
+    const int p = (int)((line / g.n3) % g.nplane);
+    const int grp = (int)(line / ((long)g.n3 * g.nplane));
+    double2* buf = bufs + (it & 1) * g.n2 * FFT_B;
+    if (q < R2) {
+      const int* src = g.ysrc + p * g.n2;
+      const double2* in = T1 + ((long)grp * g.ncol * g.n3 + z) * FFT_B + b;
+      auto load = [&](int row) {
+        const int c = __ldg(src + row);
+        return c >= 0 ? in[(long)c * g.n3 * FFT_B] : make_double2(0, 0);
+      };
+#define P1(R) line_phase1<R>(buf, tw, R2, q, b, load)
+      PAWB200_RADIX_SWITCH(R1, P1)
+#undef P1
+    }
+    __syncthreads();
+    if (q < R1) {
+      double2* out = T2 + ((((long)grp * g.nplane + p) * g.n2) * g.n3 + z) * FFT_B + b;
+      auto store = [&](int row, double2 v) { out[(long)row * g.n3 * FFT_B] = v; };
+#define P2(R) line_phase2<R>(buf, R1, q, b, store)
+      PAWB200_RADIX_SWITCH(R2, P2)
+#undef P2
+    }
   }
 }
 
 // ---- pass X: T2 -> X[group][x][y][z][FFT_B] --------------------------------------------------------------
-template <int LPC>
-__global__ void __launch_bounds__(FFT_MAXR * FFT_B * LPC, LPC == 1 ? 3 : 1)
-fft_pass_x_kernel(FftGeom g, const double2* __restrict__ T2, double2* __restrict__ X) {
-  constexpr int NB = FFT_B * LPC;
+template <int RMAX>
+__global__ void __launch_bounds__(FftLaunch<RMAX>::THREADS, FftLaunch<RMAX>::MINB)
+fft_pass_x_kernel(FftGeom g, const double2* __restrict__ T2, double2* __restrict__ X, int ngroups) {
   extern __shared__ __align__(16) unsigned char fft_smem[];
-  double2* data = reinterpret_cast<double2*>(fft_smem);      // [n1][NB]
-  double2* tw = data + g.n1 * NB;
-  const int nzc = (g.n3 + LPC - 1) / LPC;
-  const int y = blockIdx.x / nzc, z0 = (blockIdx.x % nzc) * LPC, grp = blockIdx.y;
-  const int tid = threadIdx.x, nthr = blockDim.x;
-  for (int i = tid; i < g.n1 * NB; i += nthr) data[i] = make_double2(0, 0);
-  for (int i = tid; i < g.n1; i += nthr) tw[i] = g.tw[0][i];
+  double2* bufs = reinterpret_cast<double2*>(fft_smem);      // [2][n1][FFT_B]
+  double2* tw = bufs + 2 * g.n1 * FFT_B;
+  const int tid = threadIdx.x, q = tid / FFT_B, b = tid % FFT_B;
+  const int R1 = g.r1[0], R2 = g.r2[0];
+  for (int i = tid; i < g.n1; i += blockDim.x) tw[i] = g.tw[0][i];
   __syncthreads();
-  for (int i = tid; i < g.nplane * NB; i += nthr) {
-    const int e = i % NB, p = i / NB;
-    const int lz = e / FFT_B, b = e % FFT_B;
-    if (z0 + lz < g.n3)
-      data[g.plane_xpos[p] * NB + e] = T2[((((long)grp * g.nplane + p) * g.n2 + y) * g.n3 + z0 + lz) * FFT_B + b];
-  }
-  __syncthreads();
-  fft_lines_smem(data, tw, g.r1[0], g.r2[0], NB);
-  const long ngrid = (long)g.n1 * g.n2 * g.n3;
-  for (int i = tid; i < g.n1 * NB; i += nthr) {
-    const int e = i % NB, x = i / NB;
-    const int lz = e / FFT_B, b = e % FFT_B;
-    if (z0 + lz < g.n3)
-      X[((long)grp * ngrid + ((long)x * g.n2 + y) * g.n3 + z0 + lz) * FFT_B + b] = data[x * NB + e];
+  const long plane = (long)g.n2 * g.n3;
+  const long nlines = (long)ngroups * plane;
+  int it = 0;
+  for (long line = blockIdx.x; line < nlines; line += gridDim.x, it++) {
+    const long yz = line % plane;
+    const int grp = (int)(line / plane);
+    double2* buf = bufs + (it & 1) * g.n1 * FFT_B;
+    if (q < R2) {
+      const double2* in = T2 + ((long)grp * g.nplane * plane + yz) * FFT_B + b;
+      auto load = [&](int row) {
+        const int p = __ldg(g.xsrc + row);
+        return p >= 0 ? in[(long)p * plane * FFT_B] : make_double2(0, 0);
+      };
+#define P1(R) line_phase1<R>(buf, tw, R2, q, b, load)
+      PAWB200_RADIX_SWITCH(R1, P1)
+#undef P1
+    }
+    __syncthreads();
+    if (q < R1) {
+      double2* out = X + ((long)grp * g.n1 * plane + yz) * FFT_B + b;
+      auto store = [&](int row, double2 v) { out[(long)row * plane * FFT_B] = v; };
+#define P2(R) line_phase2<R>(buf, R1, q, b, store)
+      PAWB200_RADIX_SWITCH(R2, P2)
+#undef P2
+    }
   }
 }
 

@@ -54,12 +54,14 @@ class BesselTransform {
   const std::vector<double>& kgrid() const { return kgrid_; }
 
  private:
-  void dft_backward(std::vector<cdouble>& x) const;             // unnormalised e^{+i} DFT
+  void dft_backward(std::vector<cdouble>& x) const;             // unnormalised e^{+i} DFT (Bluestein)
   int n2_;
   int lmax_;
   std::vector<double> ks_, rs_, kgrid_;
   std::vector<std::vector<cdouble>> mult_;
   std::vector<cdouble> twiddle_;
+  int m2_ = 0;                                                  // power-of-two convolution length
+  std::vector<cdouble> chirp_, chirp_fft_;                      // w[n] = exp(+i pi n^2 / N), FFT of its conjugate kernel
 };
 
 // ---- per-element PAW data ----------------------------------------------------------------

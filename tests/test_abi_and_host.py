@@ -26,7 +26,7 @@ def test_header_symbols_exported():
     L = C.CDLL(_lib.LIB_PATH)
     missing = [s for s in declared if not hasattr(L, s)]
     assert not missing, missing
-    assert set(_lib.exported_symbols()) <= set(declared) | {"pawb200_set_read_shard"}
+    assert set(_lib.exported_symbols()) <= set(declared)
 
 
 def test_no_cpu_fallback_without_gpu():
