@@ -974,8 +974,8 @@ void pruned_fft_r(const pawb200_pswf* wf, int kap, const PrunedPlan& P, int slot
   static bool configured = false;
   int occ[3] = {1, 1, 1};
   const size_t smem_z = (size_t)(2 * g.n3 * FFT_B + g.n3) * sizeof(double2);
-  const size_t smem_y = (size_t)(2 * g.n2 * FFT_B + g.n2) * sizeof(double2);
-  const size_t smem_x = (size_t)(2 * g.n1 * FFT_B + g.n1) * sizeof(double2);
+  const size_t smem_y = (size_t)(2 * g.n2 * FFT_B + g.n2) * sizeof(double2) + g.n2 * sizeof(int);
+  const size_t smem_x = (size_t)(2 * g.n1 * FFT_B + g.n1) * sizeof(double2) + g.n1 * sizeof(int);
   if (!configured) {
     const int big = 200 * 1024;
     CUDA_OK(cudaFuncSetAttribute(fft_pass_z_kernel<RMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
@@ -992,7 +992,7 @@ void pruned_fft_r(const pawb200_pswf* wf, int kap, const PrunedPlan& P, int slot
   const size_t t1_grp = (size_t)g.ncol * g.n3 * FFT_B * sizeof(double2);
   const size_t t2_grp = (size_t)g.nplane * g.n2 * g.n3 * FFT_B * sizeof(double2);
   // groups per launch: scratch kept small so pass outputs tend to stay in the 126 MB L2
-  int gc = 1;
+  int gc = 4;
   if (const char* e = getenv("PAWB200_FFT_GROUPS")) gc = std::max(1, atoi(e));
   gc = std::min(gc, ngroups);
   g_fft_t1.ensure(t1_grp * gc);
@@ -1008,7 +1008,7 @@ void pruned_fft_r(const pawb200_pswf* wf, int kap, const PrunedPlan& P, int slot
     const int ns = std::min(nslot - g0 * FFT_B, ng * FFT_B);
     fft_pass_z_kernel<RMAX><<<grid((long)ng * g.ncol, occ[0]), threads(2), smem_z, g_stream>>>(
         g, wf->C[kap].as<float2>(), wf->ldc[kap], h, wf->npw_half(kap), s0, ns, scale, g_fft_t1.as<double2>(), ng);
-    fft_pass_y_kernel<RMAX><<<grid((long)ng * g.nplane * g.n3, occ[1]), threads(1), smem_y, g_stream>>>(
+    fft_pass_y_kernel<RMAX><<<grid((long)ng * g.nplane * ((g.n3 + FFT_ZC - 1) / FFT_ZC), occ[1]), threads(1), smem_y, g_stream>>>(
         g, g_fft_t1.as<double2>(), g_fft_t2.as<double2>(), ng);
     fft_pass_x_kernel<RMAX><<<grid((long)ng * g.n2 * g.n3, occ[2]), threads(0), smem_x, g_stream>>>(
         g, g_fft_t2.as<double2>(), X + (long)g0 * ngrid * FFT_B, ng);
@@ -1030,16 +1030,19 @@ template <int MT>
 void launch_project_il_mt(const SiteTables& T, const double2* X, long ngrid, int nslot, double2* P, long ldp,
                           int slot0) {
   if (T.by_mt[MT].empty()) return;
-  static bool configured = false;
-  const size_t smem = sphere_project_smem(MT);
-  if (!configured) {
+  int maxpts = 0;
+  for (int s : T.by_mt[MT]) maxpts = std::max(maxpts, T.host[s].npts_pad);
+  const int idx_cap = std::min(maxpts, 16384);
+  const size_t smem = sphere_project_smem(MT) + (size_t)idx_cap * sizeof(int);
+  static size_t configured = 0;
+  if (smem > configured) {
     CUDA_OK(cudaFuncSetAttribute(sphere_project_il_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
+    configured = smem;
   }
   dim3 grid((nslot + PROJ_NB - 1) / PROJ_NB, (unsigned)T.by_mt[MT].size());
   sphere_project_il_kernel<MT><<<grid, 128, smem, g_stream>>>(
       T.sites.as<SiteDev>(), T.by_mt_dev[MT].as<int>(), T.idx.as<int>(), T.tablek.as<double2>(), X, ngrid, nslot,
-      (nslot + FFT_B - 1) / FFT_B, P, ldp, slot0);
+      (nslot + FFT_B - 1) / FFT_B, P, ldp, slot0, idx_cap);
   count_launch();
   check_launch();
 }

@@ -219,41 +219,50 @@ fft_pass_z_kernel(FftGeom g, const float2* __restrict__ C, long ldc, int halves,
 }
 
 // ---- pass Y: T1 -> T2[group][plane][y][z][FFT_B] ------------------------------------------------------
+// Work unit = (group, plane, chunk of FFT_ZC z-lines): the plane's row->column table is fetched into shared
+// memory once per unit, so the data loads do not wait behind a dependent global lookup.
+constexpr int FFT_ZC = 9;
 template <int RMAX>
 __global__ void __launch_bounds__(FftLaunch<RMAX>::THREADS, FftLaunch<RMAX>::MINB)
 fft_pass_y_kernel(FftGeom g, const double2* __restrict__ T1, double2* __restrict__ T2, int ngroups) {
   extern __shared__ __align__(16) unsigned char fft_smem[];
   double2* bufs = reinterpret_cast<double2*>(fft_smem);      // [2][n2][FFT_B]
   double2* tw = bufs + 2 * g.n2 * FFT_B;
+  int* ssrc = reinterpret_cast<int*>(tw + g.n2);             // [n2] column holding each y row of the plane
   const int tid = threadIdx.x, q = tid / FFT_B, b = tid % FFT_B;
   const int R1 = g.r1[1], R2 = g.r2[1];
   for (int i = tid; i < g.n2; i += blockDim.x) tw[i] = g.tw[1][i];
-  __syncthreads();
-  const long nlines = (long)ngroups * g.nplane * g.n3;
+  const int nzc = (g.n3 + FFT_ZC - 1) / FFT_ZC;
+  const long nunits = (long)ngroups * g.nplane * nzc;
   int it = 0;
-  for (long line = blockIdx.x; line < nlines; line += gridDim.x, it++) {
-    const int z = (int)(line % g.n3);
-    const int p = (int)((line / g.n3) % g.nplane);
-    const int grp = (int)(line / ((long)g.n3 * g.nplane));
-    double2* buf = bufs + (it & 1) * g.n2 * FFT_B;
-    if (q < R2) {
-      const int* src = g.ysrc + p * g.n2;
-      const double2* in = T1 + ((long)grp * g.ncol * g.n3 + z) * FFT_B + b;
-      auto load = [&](int row) {
-        const int c = __ldg(src + row);
-        return c >= 0 ? in[(long)c * g.n3 * FFT_B] : make_double2(0, 0);
-      };
-#define P1(R) line_phase1<R>(buf, tw, R2, q, b, load)
-      PAWB200_RADIX_SWITCH(R1, P1)
-#undef P1
-    }
+  for (long unit = blockIdx.x; unit < nunits; unit += gridDim.x) {
+    const int zc = (int)(unit % nzc);
+    const int p = (int)((unit / nzc) % g.nplane);
+    const int grp = (int)(unit / ((long)nzc * g.nplane));
+    __syncthreads();                                         // previous unit no longer reads ssrc
+    for (int i = tid; i < g.n2; i += blockDim.x) ssrc[i] = g.ysrc[p * g.n2 + i];
     __syncthreads();
-    if (q < R1) {
-      double2* out = T2 + ((((long)grp * g.nplane + p) * g.n2) * g.n3 + z) * FFT_B + b;
-      auto store = [&](int row, double2 v) { out[(long)row * g.n3 * FFT_B] = v; };
+    const int z1 = min(g.n3, (zc + 1) * FFT_ZC);
+    for (int z = zc * FFT_ZC; z < z1; z++, it++) {
+      double2* buf = bufs + (it & 1) * g.n2 * FFT_B;
+      if (q < R2) {
+        const double2* in = T1 + ((long)grp * g.ncol * g.n3 + z) * FFT_B + b;
+        auto load = [&](int row) {
+          const int c = ssrc[row];
+          return c >= 0 ? in[(long)c * g.n3 * FFT_B] : make_double2(0, 0);
+        };
+#define P1(R) line_phase1<R>(buf, tw, R2, q, b, load)
+        PAWB200_RADIX_SWITCH(R1, P1)
+#undef P1
+      }
+      __syncthreads();
+      if (q < R1) {
+        double2* out = T2 + ((((long)grp * g.nplane + p) * g.n2) * g.n3 + z) * FFT_B + b;
+        auto store = [&](int row, double2 v) { out[(long)row * g.n3 * FFT_B] = v; };
 #define P2(R) line_phase2<R>(buf, R1, q, b, store)
-      PAWB200_RADIX_SWITCH(R2, P2)
+        PAWB200_RADIX_SWITCH(R2, P2)
 #undef P2
+      }
     }
   }
 }
@@ -265,9 +274,13 @@ fft_pass_x_kernel(FftGeom g, const double2* __restrict__ T2, double2* __restrict
   extern __shared__ __align__(16) unsigned char fft_smem[];
   double2* bufs = reinterpret_cast<double2*>(fft_smem);      // [2][n1][FFT_B]
   double2* tw = bufs + 2 * g.n1 * FFT_B;
+  int* sxsrc = reinterpret_cast<int*>(tw + g.n1);            // [n1] plane holding each x row (or -1)
   const int tid = threadIdx.x, q = tid / FFT_B, b = tid % FFT_B;
   const int R1 = g.r1[0], R2 = g.r2[0];
-  for (int i = tid; i < g.n1; i += blockDim.x) tw[i] = g.tw[0][i];
+  for (int i = tid; i < g.n1; i += blockDim.x) {
+    tw[i] = g.tw[0][i];
+    sxsrc[i] = g.xsrc[i];
+  }
   __syncthreads();
   const long plane = (long)g.n2 * g.n3;
   const long nlines = (long)ngroups * plane;
@@ -279,7 +292,7 @@ fft_pass_x_kernel(FftGeom g, const double2* __restrict__ T2, double2* __restrict
     if (q < R2) {
       const double2* in = T2 + ((long)grp * g.nplane * plane + yz) * FFT_B + b;
       auto load = [&](int row) {
-        const int p = __ldg(g.xsrc + row);
+        const int p = sxsrc[row];
         return p >= 0 ? in[(long)p * plane * FFT_B] : make_double2(0, 0);
       };
 #define P1(R) line_phase1<R>(buf, tw, R2, q, b, load)

@@ -360,19 +360,24 @@ __global__ void __launch_bounds__(128)
 sphere_project_il_kernel(const SiteDev* __restrict__ sites, const int* __restrict__ site_list,
                          const int* __restrict__ idx, const double2* __restrict__ tablek,
                          const double2* __restrict__ X, long ngrid, int nslot, int ngroups,
-                         double2* __restrict__ P, long ldp, int slot0) {
+                         double2* __restrict__ P, long ldp, int slot0, int idx_cap) {
   constexpr int IL = 16;
   const SiteDev sd = sites[site_list[blockIdx.y]];
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double2* sB = reinterpret_cast<double2*>(smem_raw);                       // [ST][KT][LDB]
   double2* sA = sB + PROJ_STAGES * PROJ_KT * PROJ_LDB;                      // [ST][8*MT][LDA]
+  int* sIdx = reinterpret_cast<int*>(sA + PROJ_STAGES * 8 * MT * PROJ_LDA);  // [idx_cap] sphere index list
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int sbase = blockIdx.x * PROJ_NB;
   const int nk = sd.npts_pad / PROJ_KT;
+  // the gather addresses come from the index list: keep it in shared memory so the cp.async issue does
+  // not wait on a global load per stage
+  for (int e = tid; e < sd.npts_pad && e < idx_cap; e += 128) sIdx[e] = __ldg(idx + sd.pt_off + e);
   for (int e = tid; e < PROJ_STAGES * 8 * MT * PROJ_LDA; e += 128) {
     const int row = (e / PROJ_LDA) % (8 * MT);
     if (row >= sd.nlm) sA[e] = make_double2(0, 0);
   }
+  __syncthreads();
   int grp = (sbase + lane) / IL;
   if (grp >= ngroups) grp = ngroups - 1;          // tail CTA: duplicate the last group, discarded on store
   const double2* xsrc = X + (long)grp * ngrid * IL + (lane & (IL - 1));
@@ -382,7 +387,8 @@ sphere_project_il_kernel(const SiteDev* __restrict__ sites, const int* __restric
 #pragma unroll
       for (int q = 0; q < PROJ_KT / 4; q++) {
         const int pt = warp + 4 * q;
-        const int g = __ldg(idx + sd.pt_off + kt * PROJ_KT + pt);     // warp-uniform -> broadcast
+        const int ip = kt * PROJ_KT + pt;
+        const int g = ip < idx_cap ? sIdx[ip] : __ldg(idx + sd.pt_off + ip);   // warp-uniform -> broadcast
         cp_async16(sB + (st * PROJ_KT + pt) * PROJ_LDB + lane, xsrc + (long)g * IL);
       }
       for (int row = warp; row < sd.nlm; row += 4)
