@@ -385,11 +385,15 @@ std::vector<Element> build_elements(int num_els, const int* labels, const int* l
 
     BesselTransform sbt(1e7, 0, el.lmax, WG, el.wave_grid.data());
     el.kwave_grid = sbt.kgrid();
-    for (auto& f : el.funcs) {
+#pragma omp parallel for schedule(dynamic)
+    for (int fi = 0; fi < el.num_projs; fi++) {
+      RadialFunc& f = el.funcs[fi];
       f.kwave = sbt.forward(f.diffwave.data(), f.l);
       f.kwave_s = make_spline(el.kwave_grid.data(), f.kwave.data(), WG);
     }
-    for (auto& f : el.funcs) {
+#pragma omp parallel for schedule(dynamic)
+    for (int fi = 0; fi < el.num_projs; fi++) {
+      RadialFunc& f = el.funcs[fi];
       std::vector<double> lowpass(WG, 0.0);
       for (int q = 0; q < WG && el.kwave_grid[q] < cutoff_k; q++) lowpass[q] = f.kwave[q];
       std::vector<double> smooth = sbt.inverse(lowpass.data(), f.l);
