@@ -174,6 +174,7 @@ typedef struct {
   long long boxes_scattered; /* FFT boxes filled by scatter_pw_kernel */
   long long boxes_fft;       /* FFT boxes transformed */
   long long slots_projected; /* (band, table-set) sphere projections */
+  long long sphere_samples;  /* psi~ samples gathered by the projection kernels (slots x sphere points) */
 } pawb200_timers;
 void pawb200_get_timers(pawb200_timers *t);
 void pawb200_reset_timers(void);

@@ -27,7 +27,7 @@ class Timers(C.Structure):
     _fields_ = [(n, C.c_double) for n in (
         "h2d_ms", "scatter_ms", "fft_ms", "project_ms", "table_ms", "gemm_pseudo_ms",
         "gemm_aug_ms", "augment_ms", "d2h_ms")] + [(n, C.c_longlong) for n in (
-        "launches", "boxes_scattered", "boxes_fft", "slots_projected")]
+        "launches", "boxes_scattered", "boxes_fft", "slots_projected", "sphere_samples")]
 
 
 _lib = None

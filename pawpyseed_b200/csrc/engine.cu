@@ -72,7 +72,7 @@ void set_error(const std::string& m) {
 
 cudaStream_t g_stream = 0;   // legacy default stream: ordered with torch's default stream
 std::atomic<long long> g_launches{0};
-long long g_boxes_scattered = 0, g_boxes_fft = 0, g_slots_projected = 0;
+long long g_boxes_scattered = 0, g_boxes_fft = 0, g_slots_projected = 0, g_sphere_samples = 0;
 int g_num_sms = 0;
 
 void require_device() {
@@ -839,6 +839,7 @@ void launch_project(const SiteTables& T, const double2* x, long ngrid, int nslot
                     int slot0) {
   ScopedStage tm(ST_PROJECT);
   g_slots_projected += nslot;
+  for (auto& sd : T.host) g_sphere_samples += (long long)nslot * sd.npts;
   launch_project_mt<1>(T, x, ngrid, nslot, P, ldp, slot0);
   launch_project_mt<2>(T, x, ngrid, nslot, P, ldp, slot0);
   launch_project_mt<3>(T, x, ngrid, nslot, P, ldp, slot0);
@@ -1051,6 +1052,7 @@ void launch_project_il(const SiteTables& T, const double2* X, long ngrid, int ns
                        int slot0) {
   ScopedStage tm(ST_PROJECT);
   g_slots_projected += nslot;
+  for (auto& sd : T.host) g_sphere_samples += (long long)nslot * sd.npts;
   launch_project_il_mt<1>(T, X, ngrid, nslot, P, ldp, slot0);
   launch_project_il_mt<2>(T, X, ngrid, nslot, P, ldp, slot0);
   launch_project_il_mt<3>(T, X, ngrid, nslot, P, ldp, slot0);
@@ -2010,7 +2012,7 @@ void pawb200_get_timers(pawb200_timers* t) {
   t->gemm_pseudo_ms = g_stage_ms[ST_GEMM_PS]; t->gemm_aug_ms = g_stage_ms[ST_GEMM_AUG];
   t->augment_ms = g_stage_ms[ST_AUGMENT]; t->d2h_ms = g_stage_ms[ST_D2H];
   t->launches = g_launches.load();
-  t->boxes_scattered = g_boxes_scattered; t->boxes_fft = g_boxes_fft; t->slots_projected = g_slots_projected;
+  t->boxes_scattered = g_boxes_scattered; t->boxes_fft = g_boxes_fft; t->slots_projected = g_slots_projected; t->sphere_samples = g_sphere_samples;
 }
 void pawb200_reset_timers(void) {
   drain_timers();
@@ -2018,7 +2020,7 @@ void pawb200_reset_timers(void) {
   g_hostprof.calls.clear();
   for (auto& v : g_stage_ms) v = 0;
   g_launches = 0;
-  g_boxes_scattered = g_boxes_fft = g_slots_projected = 0;
+  g_boxes_scattered = g_boxes_fft = g_slots_projected = g_sphere_samples = 0;
 }
 
 }  // extern "C"
