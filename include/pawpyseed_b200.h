@@ -153,6 +153,11 @@ void pawb200_projection_matrix(pawb200_c128 *out, pawb200_pswf_t *wf_S, pawb200_
  * only the (k,spin) blocks with kappa % world == rank in HBM; blocks of other ranks come back
  * as zeros from pawb200_projection_matrix and are summed/gathered by the caller (NCCL). */
 void pawb200_set_read_shard(int rank, int world);
+/* With on != 0, pawb200_read_wavefunctions_from_str returns while the host->device copies are still in
+ * flight: the CALLER MUST KEEP THE BUFFER ALIVE AND UNMODIFIED until the wavefunction has been used in a call
+ * that returns results (or is freed). Later launches wait per band chunk, so the transfer overlaps the
+ * transforms. Default off (the copy is complete on return, like the reference reader). */
+void pawb200_set_async_ingest(int on);
 /* OpenMP threads for the host-side setup (sphere geometry, NumSBT); launchers such as torchrun export
  * OMP_NUM_THREADS=1, which would serialise it. */
 void pawb200_set_host_threads(int n);

@@ -90,6 +90,7 @@ _SIGS = {
     "pawb200_set_kappa_range": (None, [C.c_void_p, C.c_int, C.c_int]),
     "pawb200_set_read_shard": (None, [C.c_int, C.c_int]),
     "pawb200_set_host_threads": (None, [C.c_int]),
+    "pawb200_set_async_ingest": (None, [C.c_int]),
     "pawb200_get_projections": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_dbl_p]),
     "pawb200_num_projections": (C.c_int, [C.c_void_p, C.c_int]),
     "pawb200_get_channel_index": (C.c_int, [C.c_void_p, c_int_p]),

@@ -536,6 +536,12 @@ struct pawb200_pswf {
   std::vector<DevBuf> C;               // per kappa: float2 [nband][ldc]
   std::vector<long> ldc;
   std::vector<char> resident;          // per kappa: this process holds the block
+  std::vector<DevBuf> perm_dev;        // per kappa: device copy of the box-order permutation
+  struct Chunk { int kap, band_lo, band_hi; cudaEvent_t ready; };
+  std::vector<Chunk> chunks;           // ingest chunks: coefficients of [band_lo, band_hi) are valid after `ready`
+  ~pawb200_pswf() {
+    for (auto& c : chunks) cudaEventDestroy(c.ready);
+  }
   // projector state
   std::unique_ptr<pawb200_ppot> pps;
   int num_sites = 0;
@@ -590,29 +596,25 @@ struct ByteSource {
   }
 };
 
-// Staging ring for raw WAVECAR records: copies run on their own stream so the H2D of one wavefunction
-// overlaps the kernels of the previous one; events order copy -> permute -> next copy per slot.
+// Staging ring for raw WAVECAR records.  Copies and the column permutation run on their own stream in band
+// chunks; each chunk records an event that the consumers of those bands (FFT / scatter / GEMM launches on the
+// main stream) wait on.  The H2D of a wavefunction therefore overlaps both the kernels of the previous
+// wavefunction and - with pawb200_set_async_ingest(1) - its own transform pipeline.
 struct IngestRing {
   struct Slot {
     void* p = nullptr;
     size_t bytes = 0;
-    cudaEvent_t filled = nullptr, consumed = nullptr;
   };
   cudaStream_t copy = nullptr;
-  Slot slots[2];
+  Slot slots[3];
   unsigned next = 0;
 };
 IngestRing& ingest_ring() {
   static IngestRing r;
-  if (!r.copy) {
-    CUDA_OK(cudaStreamCreateWithFlags(&r.copy, cudaStreamNonBlocking));
-    for (auto& s : r.slots) {
-      CUDA_OK(cudaEventCreateWithFlags(&s.filled, cudaEventDisableTiming));
-      CUDA_OK(cudaEventCreateWithFlags(&s.consumed, cudaEventDisableTiming));
-    }
-  }
+  if (!r.copy) CUDA_OK(cudaStreamCreateWithFlags(&r.copy, cudaStreamNonBlocking));
   return r;
 }
+bool g_async_ingest = false;
 
 // Storage order of the plane waves = FFT-box index order (wrap(g1), wrap(g2), wrap(g3)) with
 // wrap(g) = g for g >= 0 and negatives after all non-negatives (independent of the grid size).
@@ -684,6 +686,7 @@ pawb200_pswf* ingest(ByteSource src, const double* kws) {
   const int NK = hd.nwk * hd.nspin;
   wf->kp.resize(NK); wf->weight.resize(NK); wf->C.resize(NK); wf->ldc.assign(NK, 0);
   wf->resident.assign(NK, 0);
+  wf->perm_dev.resize(NK);
   unsigned char* stage = nullptr;
   size_t stage_bytes = 0;
   IngestRing& ring = ingest_ring();
@@ -737,39 +740,58 @@ pawb200_pswf* ingest(ByteSource src, const double* kws) {
       src.read(stage, (base + 1) * hd.nrecl, need);
       from = stage;
     }
-    // raw records -> HBM on the copy stream (overlaps compute queued on the main stream), then the
-    // column permutation into box order on the main stream
-    IngestRing::Slot& sl = ring.slots[ring.next++ % 2];
-    const size_t raw_bytes = (size_t)hd.nband * ld * sizeof(float2);
-    if (raw_bytes > sl.bytes) {
-      CUDA_OK(cudaEventSynchronize(sl.consumed));
-      if (sl.p) cudaFree(sl.p);
-      CUDA_OK(cudaMalloc(&sl.p, raw_bytes));
-      sl.bytes = raw_bytes;
-    }
-    CUDA_OK(cudaStreamWaitEvent(ring.copy, sl.consumed, 0));
+    // raw records -> HBM in band chunks on the copy stream, each followed by its column permutation into
+    // box order; consumers wait on the per-chunk events (wait_coeffs)
     {
-      ScopedStage tm(ST_H2D, ring.copy);
-      CUDA_OK(cudaMemcpy2DAsync(sl.p, ld * sizeof(float2), from, hd.nrecl, (size_t)kp.nplane * sizeof(float2),
-                                hd.nband, cudaMemcpyHostToDevice, ring.copy));
-    }
-    CUDA_OK(cudaEventRecord(sl.filled, ring.copy));
-    CUDA_OK(cudaStreamWaitEvent(g_stream, sl.filled, 0));
-    {
+      wf->perm_dev[kap] = upload(kp.perm);
+      cudaEvent_t alloc_ev;   // the pool block / permutation upload are ordered on the main stream
+      CUDA_OK(cudaEventCreateWithFlags(&alloc_ev, cudaEventDisableTiming));
+      CUDA_OK(cudaEventRecord(alloc_ev, g_stream));
+      CUDA_OK(cudaStreamWaitEvent(ring.copy, alloc_ev, 0));
+      CUDA_OK(cudaEventDestroy(alloc_ev));
       const int half_len = kp.nplane / (wf->ncl ? 2 : 1);
-      DevBuf dperm = upload(kp.perm);
-      dim3 grid((half_len + 255) / 256, std::min(hd.nband, 64));
-      permute_coeff_kernel<<<grid, 256, 0, g_stream>>>((const float2*)sl.p, wf->C[kap].as<float2>(), ld, hd.nband,
-                                                      wf->ncl ? 2 : 1, half_len, dperm.as<int>());
-      count_launch();
-      check_launch();
+      const int nchunk = std::max(1, std::min(8, hd.nband / 16));
+      const int per = (hd.nband + nchunk - 1) / nchunk;
+      for (int b0 = 0; b0 < hd.nband; b0 += per) {
+        const int nb = std::min(per, hd.nband - b0);
+        IngestRing::Slot& sl = ring.slots[ring.next++ % 3];
+        const size_t raw_bytes = (size_t)per * ld * sizeof(float2);
+        if (raw_bytes > sl.bytes) {
+          CUDA_OK(cudaStreamSynchronize(ring.copy));
+          if (sl.p) cudaFree(sl.p);
+          CUDA_OK(cudaMalloc(&sl.p, raw_bytes));
+          sl.bytes = raw_bytes;
+        }
+        {
+          ScopedStage tm(ST_H2D, ring.copy);
+          CUDA_OK(cudaMemcpy2DAsync(sl.p, ld * sizeof(float2), from + (size_t)b0 * hd.nrecl, hd.nrecl,
+                                    (size_t)kp.nplane * sizeof(float2), nb, cudaMemcpyHostToDevice, ring.copy));
+        }
+        dim3 grid((half_len + 255) / 256, std::min(nb, 64));
+        permute_coeff_kernel<<<grid, 256, 0, ring.copy>>>((const float2*)sl.p, wf->C[kap].as<float2>() + (long)b0 * ld,
+                                                         ld, nb, wf->ncl ? 2 : 1, half_len,
+                                                         wf->perm_dev[kap].as<int>());
+        count_launch();
+        check_launch();
+        pawb200_pswf::Chunk ck{kap, b0, b0 + nb, nullptr};
+        CUDA_OK(cudaEventCreateWithFlags(&ck.ready, cudaEventDisableTiming));
+        CUDA_OK(cudaEventRecord(ck.ready, ring.copy));
+        wf->chunks.push_back(ck);
+      }
     }
-    CUDA_OK(cudaEventRecord(sl.consumed, g_stream));
   }
-  // the caller may release its buffer after we return: wait for the copies only, not for compute
-  CUDA_OK(cudaStreamSynchronize(ring.copy));
+  // Unless the caller promised to keep its buffer alive (async ingest), wait for the copies - but not for
+  // any compute - before returning
+  if (!(g_async_ingest && src.mem)) CUDA_OK(cudaStreamSynchronize(ring.copy));
   if (stage) cudaFreeHost(stage);
   return wf.release();
+}
+
+// Make the main stream wait until the coefficient rows of bands [band_lo, band_hi) of `kap` have landed.
+void wait_coeffs(const pawb200_pswf* wf, int kap, int band_lo, int band_hi) {
+  for (auto& c : wf->chunks)
+    if (c.kap == kap && c.band_lo < band_hi && c.band_hi > band_lo)
+      CUDA_OK(cudaStreamWaitEvent(g_stream, c.ready, 0));
 }
 
 // ---- inverse scatter map -------------------------------------------------------------------
@@ -800,6 +822,7 @@ void launch_scatter(const pawb200_pswf* wf, int kap, int slot0, int nslot, const
   if (slot0 % h) throw std::runtime_error("slot batches must start on a band boundary");
   const int threads = 256;
   long blocks = std::min<long>((ngrid + threads - 1) / threads, (long)g_num_sms * 16);
+  wait_coeffs(wf, kap, slot0 / h, (slot0 + nslot + h - 1) / h);
   ScopedStage tm(ST_SCATTER);
   g_boxes_scattered += nslot;
   scatter_pw_kernel<<<(unsigned)blocks, threads, 0, g_stream>>>(
@@ -1007,6 +1030,7 @@ void pruned_fft_r(const pawb200_pswf* wf, int kap, const PrunedPlan& P, int slot
     const int ng = std::min(gc, ngroups - g0);
     const int s0 = slot0 + g0 * FFT_B;
     const int ns = std::min(nslot - g0 * FFT_B, ng * FFT_B);
+    wait_coeffs(wf, kap, s0 / h, (s0 + ns + h - 1) / h);
     fft_pass_z_kernel<RMAX><<<grid((long)ng * g.ncol, occ[0]), threads(2), smem_z, g_stream>>>(
         g, wf->C[kap].as<float2>(), wf->ldc[kap], h, wf->npw_half(kap), s0, ns, scale, g_fft_t1.as<double2>(), ng);
     fft_pass_y_kernel<RMAX><<<grid((long)ng * g.nplane * ((g.n3 + FFT_ZC - 1) / FFT_ZC), occ[1]), threads(1), smem_y, g_stream>>>(
@@ -1223,6 +1247,8 @@ void pseudo_block(pawb200_pswf* S, pawb200_pswf* R, int kap, int flip, double2* 
   // the reference takes num_waves from wf_ref->kpts[kpt_num] (pseudoprojector.c:84) for both vectors
   if (S->kp[kap].nplane != R->kp[kr].nplane)
     throw std::runtime_error("plane-wave bases differ between the two wavefunctions at kappa " + std::to_string(kap));
+  wait_coeffs(S, kap, 0, S->nband);
+  wait_coeffs(R, kr, 0, R->nband);
   run_zgemm<float2>(S->C[kap].as<float2>(), S->ldc[kap], R->C[kr].as<float2>(), R->ldc[kr], S->nband,
                     R->nband, S->ldc[kap], out, ldo, false, ST_GEMM_PS);
 }
@@ -1548,6 +1574,8 @@ int pawb200_device_check(void) {
   API_END(-1)
 }
 
+void pawb200_set_async_ingest(int on) { g_async_ingest = on != 0; }
+
 void pawb200_set_host_threads(int n) {
   if (n > 0) omp_set_num_threads(n);
 }
@@ -1586,6 +1614,7 @@ pawb200_pswf_t* pawb200_read_wavefunctions_from_str(const char* start, const dou
 
 void pawb200_free_pswf(pawb200_pswf_t* wf) {
   if (!wf) return;
+  cudaStreamSynchronize(ingest_ring().copy);
   cudaStreamSynchronize(g_stream);
   delete wf;
 }

@@ -144,14 +144,14 @@ class PWFPointer:
             buf = np.frombuffer(source, dtype=np.uint8) if not isinstance(source, np.ndarray) else source
             self._buf = np.ascontiguousarray(buf, dtype=np.uint8)
             self.ptr = L.pawb200_read_wavefunctions_from_str(self._buf.ctypes.data_as(C.c_void_p), dp(kws))
-            self._buf = None   # the engine copied what it needs to HBM
+            # kept alive with the wavefunction: with pawb200_set_async_ingest(1) the copy may still be in flight
         else:
             filename = str(source)
             if ".gz" in filename or ".bz2" in filename:
                 opener = gzip.open if ".gz" in filename else bz2.open
                 with opener(filename, "rb") as f:
-                    contents = np.frombuffer(f.read(), dtype=np.uint8)
-                self.ptr = L.pawb200_read_wavefunctions_from_str(contents.ctypes.data_as(C.c_void_p), dp(kws))
+                    self._buf = np.frombuffer(f.read(), dtype=np.uint8)
+                self.ptr = L.pawb200_read_wavefunctions_from_str(self._buf.ctypes.data_as(C.c_void_p), dp(kws))
             else:
                 self.ptr = L.pawb200_read_wavefunctions(filename.encode("utf-8"), dp(kws))
         check()
@@ -168,6 +168,7 @@ class PseudoWavefunction:
             raise Exception("NULL PWFPointer ptr!")
         L = _lib.lib()
         self.wf_ptr = pwf.ptr
+        self._src_buf = getattr(pwf, "_buf", None)
         pwf.ptr = None   # ownership moves, like the C pointer in the reference
         self.kpts = pwf.kpts.copy(order="C")
         self.kws = pwf.weights.copy(order="C")
