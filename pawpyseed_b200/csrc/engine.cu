@@ -788,10 +788,10 @@ pawb200_pswf* ingest(ByteSource src, const double* kws) {
 }
 
 // Make the main stream wait until the coefficient rows of bands [band_lo, band_hi) of `kap` have landed.
-void wait_coeffs(const pawb200_pswf* wf, int kap, int band_lo, int band_hi) {
+void wait_coeffs(const pawb200_pswf* wf, int kap, int band_lo, int band_hi, cudaStream_t st = nullptr) {
   for (auto& c : wf->chunks)
     if (c.kap == kap && c.band_lo < band_hi && c.band_hi > band_lo)
-      CUDA_OK(cudaStreamWaitEvent(g_stream, c.ready, 0));
+      CUDA_OK(cudaStreamWaitEvent(st ? st : g_stream, c.ready, 0));
 }
 
 // ---- inverse scatter map -------------------------------------------------------------------
@@ -1179,10 +1179,44 @@ void project_all_bands(pawb200_pswf* wf, SiteTables& T, const int* fftg, std::ve
 
 // ---- GEMM driver ------------------------------------------------------------------------------
 DevBuf g_zg_ws;
+// The pseudo-overlap GEMM only needs the plane-wave coefficients, and it is tensor-pipe bound while the FFT /
+// projection pipeline is HBM bound: it runs on its own high-priority stream with one persistent CTA per SM and
+// can overlap the transforms queued on the main stream (PAWB200_GEMM_OVERLAP=1; off by default).
+cudaStream_t g_stream2 = nullptr;
+struct RawBuf {            // plain cudaMalloc buffer (not from the stream-ordered pool: used across streams)
+  void* p = nullptr;
+  size_t bytes = 0;
+  void ensure(size_t n) {
+    if (n <= bytes) return;
+    CUDA_OK(cudaDeviceSynchronize());
+    if (p) cudaFree(p);
+    CUDA_OK(cudaMalloc(&p, n));
+    bytes = n;
+  }
+};
+RawBuf g_zg_ws2, g_pblk[2];
+cudaEvent_t g_pblk_free[2] = {nullptr, nullptr}, g_pblk_done[2] = {nullptr, nullptr};
+bool gemm_overlap_enabled() {
+  // measured on B200 (config 2): concurrent execution stretches both sides and nets nothing, so it is opt-in
+  static const bool on = getenv("PAWB200_GEMM_OVERLAP") && atoi(getenv("PAWB200_GEMM_OVERLAP")) != 0;
+  return on;
+}
+cudaStream_t gemm_stream() {
+  if (!g_stream2) {
+    int lo = 0, hi = 0;
+    CUDA_OK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CUDA_OK(cudaStreamCreateWithPriority(&g_stream2, cudaStreamNonBlocking, hi));
+    for (int i = 0; i < 2; i++) {
+      CUDA_OK(cudaEventCreateWithFlags(&g_pblk_free[i], cudaEventDisableTiming));
+      CUDA_OK(cudaEventCreateWithFlags(&g_pblk_done[i], cudaEventDisableTiming));
+    }
+  }
+  return g_stream2;
+}
 
 template <typename T, bool K3M>
 void run_zgemm_variant(const T* A, long lda, const T* B, long ldb, int M, int N, long Kpad, double2* out,
-                       long ldo, bool accumulate, int stage) {
+                       long ldo, bool accumulate, int stage, cudaStream_t st, bool side_stream) {
   static bool configured = false;
   constexpr size_t smem = zgemm_smem_bytes<T, K3M>();
   constexpr int BN = ZgShape<K3M>::BN;
@@ -1198,19 +1232,26 @@ void run_zgemm_variant(const T* A, long lda, const T* B, long ldb, int M, int N,
   if (Kpad % ZgTraits<T>::KT) throw std::runtime_error("GEMM K dimension is not padded");
   plan.kiters = Kpad / ZgTraits<T>::KT;
   if (plan.kiters == 0) {
-    if (!accumulate) CUDA_OK(cudaMemset2DAsync(out, ldo * sizeof(double2), 0, N * sizeof(double2), M, g_stream));
+    if (!accumulate) CUDA_OK(cudaMemset2DAsync(out, ldo * sizeof(double2), 0, N * sizeof(double2), M, st));
     return;
   }
   plan.total = (long)plan.tiles_m * plan.tiles_n * plan.kiters;
-  plan.G = (int)std::min<long>(2L * g_num_sms, plan.total);
-  g_zg_ws.ensure((size_t)plan.G * 2 * ZG_BM * BN * sizeof(double2));
-  ScopedStage tm(stage);
-  zgemm_abh_kernel<T, K3M><<<plan.G, ZG_THREADS, smem, g_stream>>>(A, lda, B, ldb, plan, out, ldo,
-                                                                    accumulate ? 1 : 0, g_zg_ws.as<double2>());
+  // side stream: one CTA per SM so the transforms on the main stream keep most of the register file / smem
+  plan.G = (int)std::min<long>((side_stream ? 1L : 2L) * g_num_sms, plan.total);
+  const size_t ws_bytes = (size_t)plan.G * 2 * ZG_BM * BN * sizeof(double2);
+  double2* ws;
+  if (side_stream) {
+    g_zg_ws2.ensure(ws_bytes);
+    ws = (double2*)g_zg_ws2.p;
+  } else {
+    g_zg_ws.ensure(ws_bytes);
+    ws = g_zg_ws.as<double2>();
+  }
+  ScopedStage tm(stage, st);
+  zgemm_abh_kernel<T, K3M><<<plan.G, ZG_THREADS, smem, st>>>(A, lda, B, ldb, plan, out, ldo, accumulate ? 1 : 0, ws);
   count_launch();
   check_launch();
-  zgemm_fixup_kernel<<<plan.tiles_m * plan.tiles_n, 256, 0, g_stream>>>(plan, g_zg_ws.as<double2>(), out,
-                                                                         ldo, accumulate ? 1 : 0);
+  zgemm_fixup_kernel<<<plan.tiles_m * plan.tiles_n, 256, 0, st>>>(plan, ws, out, ldo, accumulate ? 1 : 0);
   count_launch();
   check_launch();
 }
@@ -1218,12 +1259,13 @@ void run_zgemm_variant(const T* A, long lda, const T* B, long ldb, int M, int N,
 // PAWB200_GEMM_4M=1 selects the 4-real-product variant (default: 3M, 25 % fewer DMMA instructions)
 template <typename T>
 void run_zgemm(const T* A, long lda, const T* B, long ldb, int M, int N, long Kpad, double2* out,
-               long ldo, bool accumulate, int stage) {
+               long ldo, bool accumulate, int stage, cudaStream_t st = nullptr, bool side_stream = false) {
   static const bool use4m = getenv("PAWB200_GEMM_4M") != nullptr;
+  if (!st) st = g_stream;
   if (use4m)
-    run_zgemm_variant<T, false>(A, lda, B, ldb, M, N, Kpad, out, ldo, accumulate, stage);
+    run_zgemm_variant<T, false>(A, lda, B, ldb, M, N, Kpad, out, ldo, accumulate, stage, st, side_stream);
   else
-    run_zgemm_variant<T, true>(A, lda, B, ldb, M, N, Kpad, out, ldo, accumulate, stage);
+    run_zgemm_variant<T, true>(A, lda, B, ldb, M, N, Kpad, out, ldo, accumulate, stage, st, side_stream);
 }
 
 int flipped(const pawb200_pswf* wf, int kap, int flip) {
@@ -1241,16 +1283,17 @@ void check_pair(const pawb200_pswf* S, const pawb200_pswf* R) {
 }
 
 // pseudo overlap block for one kappa into dev [nbS][nbR]
-void pseudo_block(pawb200_pswf* S, pawb200_pswf* R, int kap, int flip, double2* out, long ldo) {
+void pseudo_block(pawb200_pswf* S, pawb200_pswf* R, int kap, int flip, double2* out, long ldo,
+                  cudaStream_t st = nullptr, bool side_stream = false) {
   const int kr = flipped(R, kap, flip);
   if (!S->resident[kap] || !R->resident[kr]) throw std::runtime_error("(k,spin) block not resident on this rank");
   // the reference takes num_waves from wf_ref->kpts[kpt_num] (pseudoprojector.c:84) for both vectors
   if (S->kp[kap].nplane != R->kp[kr].nplane)
     throw std::runtime_error("plane-wave bases differ between the two wavefunctions at kappa " + std::to_string(kap));
-  wait_coeffs(S, kap, 0, S->nband);
-  wait_coeffs(R, kr, 0, R->nband);
+  wait_coeffs(S, kap, 0, S->nband, st);
+  wait_coeffs(R, kr, 0, R->nband, st);
   run_zgemm<float2>(S->C[kap].as<float2>(), S->ldc[kap], R->C[kr].as<float2>(), R->ldc[kr], S->nband,
-                    R->nband, S->ldc[kap], out, ldo, false, ST_GEMM_PS);
+                    R->nband, S->ldc[kap], out, ldo, false, ST_GEMM_PS, st, side_stream);
 }
 
 struct SiteLists {
@@ -1415,9 +1458,13 @@ void overlap_matrix(pawb200_pswf* S, pawb200_pswf* R, const SiteLists* L, int fl
   HostSection hs_("overlap_matrix");
   check_pair(S, R);
   const int nS = S->nband, nR = R->nband;
-  DevBuf blk((size_t)nS * nR * sizeof(double2));
+  const size_t blk_bytes = (size_t)nS * nR * sizeof(double2);
+  const bool side = pseudo && gemm_overlap_enabled();
+  DevBuf blk;
+  if (!side) blk.alloc(blk_bytes);
   AugPlan A;
   if (aug) A = plan_aug(S, R, *L);
+  int use = 0;
   for (int kap = lo; kap < hi; kap++) {
     cdouble* dst = out + (size_t)(kap - lo) * nS * nR;
     const int kr = flipped(R, kap, flip);
@@ -1425,10 +1472,29 @@ void overlap_matrix(pawb200_pswf* S, pawb200_pswf* R, const SiteLists* L, int fl
       std::fill(dst, dst + (size_t)nS * nR, cdouble(0, 0));   // another rank's block
       continue;
     }
-    if (pseudo) pseudo_block(S, R, kap, flip, blk.as<double2>(), nR);
-    if (aug) aug_block(S, R, A, kap, flip, blk.as<double2>(), nR, pseudo);
+    double2* b;
+    if (side) {
+      // pseudo block on the GEMM stream into a dedicated buffer; the main stream joins before it adds the
+      // augmentation GEMM and copies the block out
+      cudaStream_t st2 = gemm_stream();
+      const int slot = use++ & 1;
+      g_pblk[slot].ensure(blk_bytes);
+      b = (double2*)g_pblk[slot].p;
+      CUDA_OK(cudaStreamWaitEvent(st2, g_pblk_free[slot], 0));
+      pseudo_block(S, R, kap, flip, b, nR, st2, true);
+      CUDA_OK(cudaEventRecord(g_pblk_done[slot], st2));
+      CUDA_OK(cudaStreamWaitEvent(g_stream, g_pblk_done[slot], 0));
+      if (aug) aug_block(S, R, A, kap, flip, b, nR, true);
+      ScopedStage tm(ST_D2H);
+      CUDA_OK(cudaMemcpyAsync(dst, b, blk_bytes, cudaMemcpyDeviceToHost, g_stream));
+      CUDA_OK(cudaEventRecord(g_pblk_free[slot], g_stream));
+      continue;
+    }
+    b = blk.as<double2>();
+    if (pseudo) pseudo_block(S, R, kap, flip, b, nR);
+    if (aug) aug_block(S, R, A, kap, flip, b, nR, pseudo);
     ScopedStage tm(ST_D2H);
-    CUDA_OK(cudaMemcpyAsync(dst, blk.p, (size_t)nS * nR * sizeof(double2), cudaMemcpyDeviceToHost, g_stream));
+    CUDA_OK(cudaMemcpyAsync(dst, b, blk_bytes, cudaMemcpyDeviceToHost, g_stream));
   }
   stream_sync();
 }
@@ -1615,6 +1681,7 @@ pawb200_pswf_t* pawb200_read_wavefunctions_from_str(const char* start, const dou
 void pawb200_free_pswf(pawb200_pswf_t* wf) {
   if (!wf) return;
   cudaStreamSynchronize(ingest_ring().copy);
+  if (g_stream2) cudaStreamSynchronize(g_stream2);
   cudaStreamSynchronize(g_stream);
   delete wf;
 }

@@ -263,6 +263,7 @@ phase_table_kernel(const SiteDev* __restrict__ sites, const double* __restrict__
 // (the gather is the HBM-bound stream: 16 B per point per band, read once); the table tile is
 // staged alongside (re-read from L2 by the other band blocks of the same site).
 // ---------------------------------------------------------------------------------------
+constexpr int PROJ_IL = 16;       // band interleave of the pruned-FFT boxes (== FFT_B)
 constexpr int PROJ_KT = 32;       // points per stage
 constexpr int PROJ_NB = 32;       // grid slots per CTA
 constexpr int PROJ_STAGES = 4;
@@ -361,7 +362,7 @@ sphere_project_il_kernel(const SiteDev* __restrict__ sites, const int* __restric
                          const int* __restrict__ idx, const double2* __restrict__ tablek,
                          const double2* __restrict__ X, long ngrid, int nslot, int ngroups,
                          double2* __restrict__ P, long ldp, int slot0, int idx_cap) {
-  constexpr int IL = 16;
+  constexpr int IL = PROJ_IL;
   const SiteDev sd = sites[site_list[blockIdx.y]];
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double2* sB = reinterpret_cast<double2*>(smem_raw);                       // [ST][KT][LDB]
