@@ -1,0 +1,117 @@
+"""The pruned band-interleaved FFT + interleaved projection against the oracle on awkward grids, the generic
+(cuFFT) fallback for unsupported sizes, sharded and asynchronous ingest."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import cases
+from oracle import paw_numpy as pn
+from pawpyseed_b200 import _lib, pawpyc
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def rel(a, b):
+    return np.abs(np.asarray(a) - np.asarray(b)).max() / max(np.abs(b).max(), 1e-300)
+
+
+def gpu(c):
+    wf = (pawpyc.CNCLWavefunction if c["ncl"] else pawpyc.CWavefunction)(
+        pawpyc.PWFPointer.from_arrays(c["image"], c["kpts"], c["kws"]))
+    wf._c_projector_setup(len(c["pps"]), len(c["labels"]), c["grid_encut"], c["labels"], c["coords"], c["dim"],
+                          c["pps"])
+    return wf
+
+
+def oracle(c):
+    w = pn.Wavefunction.from_image(c["image"], c["kws"])
+    w.setup_projections(c["pps"], c["labels"], c["coords"], c["dim"], c["grid_encut"])
+    return w
+
+
+@pytest.mark.parametrize("dim", [
+    (18, 20, 24),    # 3x6, 4x5, 4x6            (small radices)
+    (28, 30, 32),    # 4x7, 5x6, 4x8            (radix 7, 8)
+    (45, 48, 56),    # 5x9, 3x16|6x8, 7x8       (radix 9, 16)
+    (60, 42, 75),    # 6x10, 6x7, 5x15          (radix 10, 15) - non-cubic
+    (22, 26, 20),    # 2x11 / 2x13: unsupported radices -> generic cuFFT path
+    (19, 20, 20),    # prime size -> generic path
+])
+def test_projections_on_awkward_grids(dim):
+    c = cases.small_case(seed=5, nband=5, encut=120.0, dim=dim)
+    wf, o = gpu(c), oracle(c)
+    got = np.array([[wf._get_projections(b, k) for b in range(5)] for k in range(4)])
+    assert rel(got, np.array(o.P)) < TOL
+    assert rel(wf._get_realspace_state(2, 1, 0), o.realspace_state(2, 1)) < TOL
+
+
+def test_17_bands_group_tail_and_offsite_reuse_of_resident_boxes():
+    # 17 bands = one full interleave group + a one-band tail group; overlap_setup_real re-projects from the
+    # boxes kept in HBM (no second transform)
+    cR = cases.small_case(seed=21, nband=17)
+    cS = cases.small_case(seed=22, nband=17, perturb=0.02)
+    R, S, oR, oS = gpu(cR), gpu(cS), oracle(cR), oracle(cS)
+    cat = [[0, 1], [0, 1], [2, 3], [2, 3], [2, 3], [2, 3]]
+    pr = pawpyc.CProjector(S, R)
+    _lib.reset_timers()
+    pr._setup_overlap(cat, False)
+    t = _lib.timers()
+    assert t["boxes_fft"] == 0 and t["slots_projected"] == 2 * 17 * 4      # W_S and W_R, 4 kappa, no FFT
+    want = np.array([pn.Projector(oS, oR, cat).single_band_projection(b) for b in range(17)])
+    assert rel(pr._projection_matrix(), want.reshape(17, 17, 4).transpose(2, 0, 1)) < TOL
+
+
+def test_generic_path_env_switch_matches():
+    """PAWB200_FFT=cufft forces the scatter + cuFFT + contiguous projection path; same numbers."""
+    code = (
+        "import sys, numpy as np; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import cases; from pawpyseed_b200 import pawpyc\n"
+        "c = cases.small_case(seed=5, nband=6)\n"
+        "wf = pawpyc.CWavefunction(pawpyc.PWFPointer.from_arrays(c['image'], c['kpts'], c['kws']))\n"
+        "wf._c_projector_setup(len(c['pps']), len(c['labels']), c['grid_encut'], c['labels'], c['coords'], c['dim'], c['pps'])\n"
+        "np.save(sys.argv[1], np.array([[wf._get_projections(b, k) for b in range(6)] for k in range(4)]))\n"
+    ) % (ROOT, os.path.join(ROOT, "tests"))
+    outs = []
+    for mode in ("pruned", "cufft"):
+        path = os.path.join("/tmp", "pawb200_proj_%s.npy" % mode)
+        env = dict(os.environ)
+        if mode == "cufft":
+            env["PAWB200_FFT"] = "cufft"
+        subprocess.run([sys.executable, "-c", code, path], check=True, env=env)
+        outs.append(np.load(path))
+    assert rel(outs[0], outs[1]) < 1e-12
+    c = cases.small_case(seed=5, nband=6)
+    assert rel(outs[0], np.array(oracle(c).P)) < TOL
+
+
+def test_sharded_and_async_ingest():
+    c = cases.small_case(seed=9, nband=6)
+    o = oracle(c)
+    L = _lib.lib()
+    try:
+        L.pawb200_set_async_ingest(1)       # the image stays alive in `c` for the whole test
+        parts = []
+        for rank in range(2):
+            L.pawb200_set_read_shard(rank, 2)
+            wf = gpu(c)
+            pr = pawpyc.CProjector(wf, wf)
+            pr._setup_overlap([[0, 1, 2, 3], [0, 1, 2, 3], [], [], [], []], False)
+            m = pr._projection_matrix()
+            own = [k for k in range(4) if k % 2 == rank]
+            other = [k for k in range(4) if k % 2 != rank]
+            assert np.all(m[other] == 0)                     # blocks of the other rank come back as zeros
+            with pytest.raises(_lib.PAWpyError):
+                wf._get_projections(0, other[0])             # not resident here
+            parts.append(m)
+    finally:
+        L.pawb200_set_read_shard(0, 1)
+        L.pawb200_set_async_ingest(0)
+    full = parts[0] + parts[1]                                # disjoint blocks: SUM == all-gather
+    opr = pn.Projector(o, o, [[0, 1, 2, 3], [0, 1, 2, 3], [], [], [], []])
+    want = np.array([opr.single_band_projection(b) for b in range(6)]).reshape(6, 6, 4).transpose(2, 0, 1)
+    assert rel(full, want) < TOL
