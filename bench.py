@@ -198,6 +198,7 @@ def run_b200(args):
     import torch
     import torch.distributed as dist
     from pawpyseed_b200 import _lib, pawpyc
+    from pawpyseed_b200 import distributed as pdist
 
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -222,6 +223,9 @@ def run_b200(args):
     d2h_bytes = 16 * nband * nband * len(own)
     pairs_total = nband * nband * NK
 
+    per = -(-NK // world)
+    gather_pin = torch.empty(world * per * nband * nband * 2, dtype=torch.float64).pin_memory() if world > 1 else None
+
     def read(i):
         pwf = pawpyc.PWFPointer.from_arrays(imgs[i][0], w["kpts"], w["kws"])
         return pawpyc.CWavefunction(pwf)
@@ -237,12 +241,13 @@ def run_b200(args):
             setup(wf, 1)
         pr = pawpyc.CProjector(wf, basis)
         pr._setup_overlap(w["site_cat"], False)
-        out = pr._projection_matrix()          # [NK][nbS][nbR] on host; other ranks' blocks are zero
-        if world > 1:
-            t = torch.from_numpy(out.view(np.float64)).cuda()
-            dist.all_reduce(t)                 # disjoint blocks: SUM == all-gather of per-k matrices
-            out = t.cpu().numpy().view(np.complex128)
-        return out
+        if world == 1:
+            return pr._projection_matrix()     # [NK][nbS][nbR] on host
+        # one process per GPU: compute only the owned (k,spin) blocks, then all-gather the per-k matrices over NCCL
+        ks = sorted(own)
+        mine = np.concatenate([pr._projection_matrix(kappa_range=(k, k + 1)) for k in ks]) if ks else \
+            np.zeros((0, nband, nband), np.complex128)
+        return pdist.all_gather_own_blocks(mine, ks, NK, pinned_out=gather_pin, want_host=(rank == 0))
 
     def barrier():
         if world > 1:
@@ -273,7 +278,7 @@ def run_b200(args):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_per_step = float(ms.item()) / args.steps
     value = pairs_total / (ms_per_step * 1e-3)
-    checksum = float(np.abs(res).sum())
+    checksum = float(np.abs(res).sum()) if rank == 0 else 0.0
 
     # ---- end-to-end from host images (e2e) -----------------------------------------------------
     del basis, wf

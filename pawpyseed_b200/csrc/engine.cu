@@ -424,7 +424,7 @@ std::unique_ptr<SiteTables> build_site_tables(const std::vector<Element>& els, c
       const int ndiv = els[labels[s]].proj_gridsize;
       radius = (el.proj_gridsize - 1) * rmax / ndiv;
     }
-    geom[s] = sphere_geometry(coords + 3 * p, lattice, fftg, rmax, radius);
+    geom[s] = sphere_geometry(coords + 3 * p, lattice, fftg, rmax, radius, mode == 2);
   }
   delete hs_geom;
   long pt = 0, tab = 0;
@@ -514,6 +514,8 @@ struct pawb200_ppot {
   ElementList list;
 };
 
+namespace { struct PrunedPlan; }
+
 struct HostMatrixCache {
   uint64_t other_id = 0, other_gen = 0, self_gen = 0;
   int flip = -1;
@@ -566,7 +568,10 @@ struct pawb200_pswf {
   // overlap_setup_real does not scatter + transform the bands a second time
   std::vector<DevBuf> boxes;
   int boxes_fftg[3] = {0, 0, 0};
-  bool boxes_interleaved = false;   // layout of `boxes`: [group][grid][16] (pruned FFT) or [slot][grid] (cuFFT)
+  bool boxes_interleaved = false;
+  // pruned-FFT plans (column / plane tables) per kappa for the grid in plan_fftg
+  std::vector<std::shared_ptr<PrunedPlan>> fft_plans;
+  int plan_fftg[3] = {0, 0, 0};   // layout of `boxes`: [group][grid][16] (pruned FFT) or [slot][grid] (cuFFT)
   // real-space table cache (mode 2), keyed by grid + coords
   std::unique_ptr<SiteTables> ae_sites;
   // per-band call caches
@@ -923,8 +928,8 @@ void init_small_twiddles() {
   done = true;
 }
 
-std::unique_ptr<PrunedPlan> build_pruned_plan(const pawb200_pswf* wf, int kap, const int* fftg) {
-  auto P = std::make_unique<PrunedPlan>();
+std::shared_ptr<PrunedPlan> build_pruned_plan(const pawb200_pswf* wf, int kap, const int* fftg) {
+  auto P = std::make_shared<PrunedPlan>();
   if (getenv("PAWB200_FFT") && std::string(getenv("PAWB200_FFT")) == "cufft") return P;
   FftGeom& g = P->g;
   g.n1 = fftg[0]; g.n2 = fftg[1]; g.n3 = fftg[2];
@@ -987,6 +992,17 @@ std::unique_ptr<PrunedPlan> build_pruned_plan(const pawb200_pswf* wf, int kap, c
   init_small_twiddles();
   P->ok = true;
   return P;
+}
+
+std::shared_ptr<PrunedPlan> get_pruned_plan(pawb200_pswf* wf, int kap, const int* fftg) {
+  const int NK = wf->nkappa();
+  if ((int)wf->fft_plans.size() != NK || wf->plan_fftg[0] != fftg[0] || wf->plan_fftg[1] != fftg[1] ||
+      wf->plan_fftg[2] != fftg[2]) {
+    wf->fft_plans.assign(NK, nullptr);
+    for (int d = 0; d < 3; d++) wf->plan_fftg[d] = fftg[d];
+  }
+  if (!wf->fft_plans[kap]) wf->fft_plans[kap] = build_pruned_plan(wf, kap, fftg);
+  return wf->fft_plans[kap];
 }
 
 DevBuf g_fft_t1, g_fft_t2;
@@ -1088,6 +1104,32 @@ size_t keep_boxes_budget() {
   return (size_t)32 << 30;
 }
 
+// setup_projections, step 1: transform every band of every resident (k,spin) block into resident interleaved
+// boxes.  Nothing here depends on the atomic sites, so the kernels are queued before the host builds the sphere
+// geometry and tables (which then overlaps the transforms).  Returns false when the boxes do not fit the
+// budget or the grid needs the generic path; project_all_bands then transforms batch by batch.
+bool prefft_all_bands(pawb200_pswf* wf, const int* fftg) {
+  const int NK = wf->nkappa(), nslot = wf->nslot();
+  const long ngrid = (long)fftg[0] * fftg[1] * fftg[2];
+  const int ngroups_all = (nslot + FFT_B - 1) / FFT_B;
+  const size_t il_bytes = (size_t)ngroups_all * FFT_B * ngrid * sizeof(double2);
+  int nres = 0;
+  for (int kap = 0; kap < NK; kap++) nres += wf->resident[kap] ? 1 : 0;
+  wf->boxes.clear();
+  if (il_bytes * (size_t)std::max(nres, 1) > keep_boxes_budget()) return false;
+  for (int kap = 0; kap < NK; kap++)
+    if (wf->resident[kap] && !get_pruned_plan(wf, kap, fftg)->ok) return false;
+  wf->boxes.resize(NK);
+  for (int d = 0; d < 3; d++) wf->boxes_fftg[d] = fftg[d];
+  wf->boxes_interleaved = true;
+  for (int kap = 0; kap < NK; kap++) {
+    if (!wf->resident[kap]) continue;
+    wf->boxes[kap].alloc(il_bytes);
+    pruned_fft(wf, kap, *get_pruned_plan(wf, kap, fftg), 0, nslot, wf->boxes[kap].as<double2>());
+  }
+  return true;
+}
+
 // All bands of all resident (k,spin) blocks of `wf` -> <table|psi~>, written to out[kap] [nslot][ld].
 // main_pass: this is setup_projections (boxes may be kept); otherwise kept boxes are reused when present.
 void project_all_bands(pawb200_pswf* wf, SiteTables& T, const int* fftg, std::vector<DevBuf>& out,
@@ -1136,7 +1178,7 @@ void project_all_bands(pawb200_pswf* wf, SiteTables& T, const int* fftg, std::ve
       }
       continue;
     }
-    std::unique_ptr<PrunedPlan> plan = build_pruned_plan(wf, kap, fftg);
+    std::shared_ptr<PrunedPlan> plan = get_pruned_plan(wf, kap, fftg);
     if (plan->ok) {
       // pruned band-interleaved FFT: chunks of whole 32-slot CTAs
       long chunk = std::max<long>(32, batch / 32 * 32);
@@ -1749,8 +1791,9 @@ void pawb200_setup_projections(pawb200_pswf_t* wf, pawb200_ppot_t* pps, int num_
   wf->wp_num = 0;
   std::vector<int> all(num_sites);
   for (int i = 0; i < num_sites; i++) all[i] = i;
+  const bool pre = prefft_all_bands(wf, fftg);     // queue the transforms first; the host work below overlaps them
   wf->proj_sites = build_site_tables(pps->list.el, all.data(), num_sites, labels, coords, wf->lattice, fftg, 0, true);
-  project_all_bands(wf, *wf->proj_sites, fftg, wf->P, wf->ldp, true);
+  project_all_bands(wf, *wf->proj_sites, fftg, wf->P, wf->ldp, !pre);
   wf->has_projections = true;
   API_END_VOID
 }

@@ -413,7 +413,7 @@ std::vector<Element> build_elements(int num_els, const int* labels, const int* l
 // sphere geometry
 // ---------------------------------------------------------------------------------------
 SphereGeom sphere_geometry(const double* coord, const double* L, const int* fftg,
-                           double rmax_box, double radius_test) {
+                           double rmax_box, double radius_test, bool want_wrap) {
   SphereGeom g;
   const double vol = determinant3(L);
   double res[3];
@@ -428,19 +428,36 @@ SphereGeom sphere_geometry(const double* coord, const double* L, const int* fftg
   for (int d = 0; d < 3; d++) cen[d] = (int)std::round(coord[d] * fftg[d]);
   const int N0 = fftg[0], N1 = fftg[1], N2 = fftg[2];
   const double r2_lo = radius_test * radius_test * (1 - 1e-12), r2_hi = radius_test * radius_test * (1 + 1e-12);
+  {
+    const double dv = std::fabs(vol) / ((double)N0 * N1 * N2);
+    const size_t guess = (size_t)(4.19 * radius_test * radius_test * radius_test / dv * 1.15) + 64;
+    g.index.reserve(guess);
+    g.path.reserve(3 * guess);
+    if (want_wrap) g.wrap.reserve(3 * guess);
+  }
+  // per-axis fractional offsets of the box (exactly (double)i / N - coord like utils.c:656-658)
+  std::vector<double> tz(2 * half[2] + 1);
+  std::vector<int> kz(2 * half[2] + 1);
+  for (int q = 0; q <= 2 * half[2]; q++) {
+    const int k = -half[2] + cen[2] + q;
+    tz[q] = (double)k / N2 - coord[2];
+    kz[q] = (k % N2 + N2) % N2;
+  }
   for (int i = -half[0] + cen[0]; i <= half[0] + cen[0]; i++) {
     const double t0 = (double)i / N0 - coord[0];
     const int ii = (i % N0 + N0) % N0;
     for (int j = -half[1] + cen[1]; j <= half[1] + cen[1]; j++) {
       const double t1 = (double)j / N1 - coord[1];
       const int jj = (j % N1 + N1) % N1;
-      for (int k = -half[2] + cen[2]; k <= half[2] + cen[2]; k++) {
-        double t[3] = {t0, t1, (double)k / N2 - coord[2]};
-        frac_to_cart(t, L);
+      // frac_to_cartesian evaluates (t0*L0 + t1*L3) + t2*L6 left to right: the first two terms are hoisted
+      const double p0 = t0 * L[0] + t1 * L[3], p1 = t0 * L[1] + t1 * L[4], p2 = t0 * L[2] + t1 * L[5];
+      const int rowbase = ii * N1 * N2 + jj * N2;
+      for (int q = 0; q <= 2 * half[2]; q++) {
+        const double x = p0 + tz[q] * L[6], y = p1 + tz[q] * L[7], z = p2 + tz[q] * L[8];
         // The reference tests pow(dot, 0.5) < R0.  Away from the surface the comparison of the squares
         // decides identically; only within a relative 1e-12 shell is the exact libm expression evaluated,
         // so the index lists stay bit-identical while pow() is skipped for all but a handful of points.
-        const double d2 = t[0] * t[0] + t[1] * t[1] + t[2] * t[2];
+        const double d2 = x * x + y * y + z * z;
         bool inside;
         if (d2 < r2_lo)
           inside = true;
@@ -449,14 +466,16 @@ SphereGeom sphere_geometry(const double* coord, const double* L, const int* fftg
         else
           inside = std::pow(d2, 0.5) < radius_test;
         if (inside) {
-          const int kk = (k % N2 + N2) % N2;
-          g.index.push_back(ii * N1 * N2 + jj * N2 + kk);
-          g.path.push_back(t[0]);
-          g.path.push_back(t[1]);
-          g.path.push_back(t[2]);
-          g.wrap.push_back((ii - i) / N0);
-          g.wrap.push_back((jj - j) / N1);
-          g.wrap.push_back((kk - k) / N2);
+          g.index.push_back(rowbase + kz[q]);
+          g.path.push_back(x);
+          g.path.push_back(y);
+          g.path.push_back(z);
+          if (want_wrap) {
+            const int k = -half[2] + cen[2] + q;
+            g.wrap.push_back((ii - i) / N0);
+            g.wrap.push_back((jj - j) / N1);
+            g.wrap.push_back((kz[q] - k) / N2);
+          }
         }
       }
     }

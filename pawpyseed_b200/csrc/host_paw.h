@@ -96,7 +96,7 @@ struct SphereGeom {
 };
 // radius_test: points with |r| < radius_test are kept; box from rmax_box.
 SphereGeom sphere_geometry(const double* coord, const double* lattice, const int* fftg,
-                           double rmax_box, double radius_test);
+                           double rmax_box, double radius_test, bool want_wrap);
 
 // ---- off-site partial-wave overlap (radial.c:116-196, SBTFACS regenerated) ----------------
 double wigner3j(int j1, int j2, int j3, int m1, int m2, int m3);

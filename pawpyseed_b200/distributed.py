@@ -37,6 +37,45 @@ def gather_blocks(local: np.ndarray, group=None, device=None) -> np.ndarray:
     return t.cpu().numpy().view(np.complex128).reshape(local.shape)
 
 
+def all_gather_own_blocks(own: np.ndarray, own_kappas, nkappa: int, group=None, device=None, pinned_out=None,
+                          want_host=True):
+    """All-gather of the per-kappa result blocks each rank owns (kappa % world == rank).
+
+    `own` is [len(own_kappas), nS, nR] complex128 - only this rank's blocks, so the exchange moves
+    nkappa * nS * nR * 16 B in total (NCCL all_gather over NVLink on GPUs, gloo on CPU).  Returns the full
+    [nkappa, nS, nR] array on the host (want_host=False: the gathered device tensor, rank-major).  Ranks may own different block counts; shorter ones are padded."""
+    import torch
+    import torch.distributed as dist
+    own = np.ascontiguousarray(own)
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        full = np.zeros((nkappa,) + own.shape[1:], dtype=own.dtype)
+        full[list(own_kappas)] = own
+        return full
+    world = dist.get_world_size(group)
+    if device is None:
+        device = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    per = -(-nkappa // world)                       # blocks per rank, padded
+    blk = int(np.prod(own.shape[1:]))
+    send = torch.zeros(per * blk * 2, dtype=torch.float64, device=device)
+    if len(own_kappas):
+        send[: own.size * 2] = torch.from_numpy(own.reshape(-1).view(np.float64)).to(device, non_blocking=True)
+    recv = torch.empty(world * per * blk * 2, dtype=torch.float64, device=device)
+    dist.all_gather_into_tensor(recv, send, group=group)
+    if not want_host:
+        return recv          # every rank holds all blocks in HBM; only callers that ask pay the D2H
+    if pinned_out is not None:
+        pinned_out.copy_(recv, non_blocking=False)
+        host = pinned_out.numpy()
+    else:
+        host = recv.cpu().numpy()
+    host = host.view(np.complex128).reshape(world, per, *own.shape[1:])
+    full = np.zeros((nkappa,) + own.shape[1:], dtype=np.complex128)
+    for r in range(world):
+        ks = shard_kappas(nkappa, r, world)
+        full[ks] = host[r, : len(ks)]
+    return full
+
+
 def max_over_ranks(value: float, group=None) -> float:
     import torch
     import torch.distributed as dist

@@ -28,8 +28,9 @@ def _worker(rank, world, port, nk, q):
     local = np.zeros_like(full)
     local[own] = full[own]
     got = pd.gather_blocks(local)
+    got2 = pd.all_gather_own_blocks(full[own], own, nk)
     tmax = pd.max_over_ranks(float(rank + 1))
-    q.put((rank, bool(np.array_equal(got, full)), tmax, own))
+    q.put((rank, bool(np.array_equal(got, full) and np.array_equal(got2, full)), tmax, own))
     dist.destroy_process_group()
 
 
