@@ -134,3 +134,14 @@ def test_api_error_behaviour_mirrors_reference():
     # pawpyc.pyx:296-297: NULL pointer -> Exception; projector.py:270-271 index checks live in Python
     with pytest.raises(Exception):
         pawpyc.PseudoWavefunction(pawpyc.PWFPointer())
+
+
+def test_write_volumetric_matches_reference_text(tmp_path):
+    # density.c:461-477: "%E   " five per line, x fastest / z slowest; golden text written by the reference C
+    g = np.load(os.path.join(cases.GOLDEN, "volumetric.npz"), allow_pickle=True)
+    x = np.ascontiguousarray(g["x"])
+    dim = np.ascontiguousarray(g["dim"], dtype=np.int32)
+    fn = str(tmp_path / "v.txt")
+    _lib.lib().pawb200_write_volumetric(fn.encode(), _lib.dp(x), _lib.ip(dim), float(g["scale"]))
+    _lib.check()
+    assert open(fn).read() == str(g["text"])

@@ -1,0 +1,125 @@
+"""The reference's Python-facing API (Wavefunction / CoreRegion / Projector / NCLWavefunction) on the GPU engine."""
+import os
+
+import numpy as np
+import pytest
+
+import cases
+from oracle import paw_numpy as pn
+from pawpyseed_b200 import CoreRegion, NCLWavefunction, PAWpyError, Projector, Wavefunction, synth
+from pawpyseed_b200.structure import Structure
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+def rel(a, b):
+    return np.abs(np.asarray(a) - np.asarray(b)).max() / max(np.abs(b).max(), 1e-300)
+
+
+def build(c, symbols):
+    pps = c["pps"]
+    cr = CoreRegion({sym: pps[i] for i, sym in enumerate(dict.fromkeys(symbols))})
+    struct = Structure(c["lattice"], symbols, c["coords"])
+    return Wavefunction.from_arrays(struct, c["image"], cr, c["dim"], c["kpts"], c["kws"])
+
+
+def oracle(c):
+    w = pn.Wavefunction.from_image(c["image"], c["kws"])
+    w.setup_projections(c["pps"], c["labels"], c["coords"], c["dim"], c["grid_encut"])
+    return w
+
+
+@pytest.fixture(scope="module")
+def pair():
+    # basis: 4 sites; wf: same cell with site 3 displaced by 0.35 A -> M = {0,1,2}, N_R = N_S = {3}, N_RS = {(3,3)}
+    cR = cases.small_case(seed=31, nband=8)
+    coordsS = cR["coords"].copy()
+    coordsS[3] += np.linalg.solve(cR["lattice"].T, np.array([0.35, 0.0, 0.0]))
+    cS = cases.small_case(seed=32, nband=8, coords=coordsS)
+    sym = ["Ga", "N", "Ga", "N"]
+    return cR, cS, build(cR, sym), build(cS, sym), oracle(cR), oracle(cS)
+
+
+def test_projector_aug_real_matches_oracle(pair):
+    cR, cS, basis, wf, oR, oS = pair
+    pr = Projector(wf, basis)                                   # method="aug_real", runs setup_overlap
+    M_R, M_S, N_R, N_S, N_RS = pr.make_site_lists()
+    assert (M_R, M_S, N_R, N_S, N_RS) == ([0, 1, 2], [0, 1, 2], [3], [3], [(3, 3)])
+    cat = [M_R, M_S, N_R, N_S, [3], [3]]
+    opr = pn.Projector(oS, oR, cat)
+    for b in (0, 7):
+        assert rel(pr.single_band_projection(b), opr.single_band_projection(b)) < TOL
+    res = pr.single_band_projection(2, flip_spin=True)
+    assert rel(res, opr.single_band_projection(2, True)) < TOL
+    full = pr.projection_matrix()
+    assert rel(full[1, 5], opr.single_band_projection(5).reshape(8, 4)[:, 1]) < TOL
+    with pytest.raises(ValueError):
+        pr.single_band_projection(99)                           # projector.py:270-271
+
+
+def test_proportion_conduction_and_defect_band_analysis(pair):
+    cR, cS, basis, wf, oR, oS = pair
+    pr = Projector(wf, basis)
+    opr = pn.Projector(oS, oR, pr.site_cat)
+    occs = basis._get_occs()
+    nb, nwk, nspin = 8, 2, 2
+    assert occs.shape == (nb * nwk * nspin,)
+    res = opr.single_band_projection(3)
+    v = sum(abs(res[i]) ** 2 * cS["kws"][i % nwk] / nspin for i in range(len(res)) if occs[i] > 0.5)
+    c = sum(abs(res[i]) ** 2 * cS["kws"][i % nwk] / nspin for i in range(len(res)) if occs[i] <= 0.5)
+    gv, gc = pr.proportion_conduction(3)
+    assert abs(gv - v) < 1e-10 and abs(gc - c) < 1e-10
+    sv, sc = pr.proportion_conduction(3, spinpol=True)
+    assert len(sv) == 2 and abs(sum(sv) / nspin - v) < 1e-10
+    out, energies = pr.defect_band_analysis(num_below_ef=1, num_above_ef=1, return_energies=True)
+    assert sorted(out) == [2, 3, 4]                             # vbm = 3 (4 of 8 bands occupied)
+    assert len(energies[3]) == nwk * nspin
+    assert pr.defect_band_analysis(analyze_all=True).keys() == set(range(8))
+
+
+def test_pseudo_method_and_errors(pair):
+    cR, cS, basis, wf, oR, oS = pair
+    pr = Projector(wf, basis, method="pseudo")
+    assert rel(pr.single_band_projection(1), oS.pseudoprojection(1, oR)) < 1e-12
+    v, c = pr.proportion_conduction(1)
+    assert abs(v + c - 1) < 1e-12                               # normalised for method='pseudo' (projector.py:428-431)
+    with pytest.raises(PAWpyError):
+        Projector(wf, basis, method="nonsense")
+    with pytest.raises(PAWpyError):
+        Projector(wf, basis, method="aug_recip")                # outside the hot path, named in the error
+
+
+def test_wavefunction_realspace_and_files(pair, tmp_path):
+    cR, _, basis, _, oR, _ = pair
+    x = basis.get_state_realspace(2, 1, 0)
+    assert rel(x, oR.realspace_state(2, 1)) < TOL
+    os.chdir(tmp_path)
+    rho = basis.write_density_realspace("AECCAR_test.vasp", scale=2.0)
+    assert rho.shape == tuple(2 * cR["dim"])
+    assert rel(rho, oR.chg_density(cR["dim"] * 2)) < TOL
+    lines = open("AECCAR_test.vasp").read().split("\n")
+    assert lines[0] == "AECCAR_test.vasp" and lines[7] == "Direct"
+    hdr = 8 + 4 + 1
+    assert lines[hdr].split() == [str(2 * d) for d in cR["dim"]]
+    vals = np.array(" ".join(lines[hdr + 1:]).split(), dtype=float)
+    # VASP order: x fastest, z slowest (density.c:461-477), scaled
+    assert np.allclose(vals, 2.0 * rho.transpose(2, 1, 0).reshape(-1), rtol=1e-6)
+    basis.write_state_realspace(1, 0, 1, fileprefix="st_")
+    assert os.path.exists("st_B1K0S1_REAL.vasp") and os.path.exists("st_B1K0S1_IMAG.vasp")
+    with pytest.raises(ValueError):
+        basis.get_state_realspace(0, 0, 5)
+
+
+def test_ncl_wavefunction_api():
+    g = np.load(os.path.join(cases.GOLDEN, "ncl.npz"), allow_pickle=True)
+    cr = CoreRegion({"Ga": synth.synthetic_pps(["Ga"])[0]})
+    struct = Structure(cases.GA4_LATTICE, ["Ga"] * 4, cases.GA4_COORDS)
+    wf = NCLWavefunction.from_arrays(struct, g["image"], cr, g["dim"], g["kpts"], g["kws"])
+    s0, s1 = wf.get_state_realspace(2, 1, 0)
+    assert rel(np.stack([s0, s1]), g["state_b2_k1"]) < TOL
+    assert rel(wf.get_realspace_density(), g["density"]) < TOL
+    with pytest.raises(PAWpyError):
+        Projector(wf, wf)                                       # projector.py:74-75
+    with pytest.raises(PAWpyError):
+        Wavefunction.from_arrays(struct, g["image"], cr, g["dim"], g["kpts"], g["kws"])   # wavefunction.py:205-208
