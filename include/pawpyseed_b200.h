@@ -109,6 +109,11 @@ void pawb200_ncl_ae_chg_density(double *P, pawb200_pswf_t *wf, const int *fftg,
                                 const int *labels, const double *coords);
 void pawb200_write_volumetric(const char *filename, const double *x, const int *fftg,
                               double scale);
+/* Projector method 'realspace' (density.h: project_realspace_state, density.c:205-230): band BAND_NUM of wf
+ * against every band of wf_R by brute-force integration of the AE states on the grid; projs[b*NK + kappa]. */
+void pawb200_project_realspace_state(pawb200_c128 *projs, int BAND_NUM, pawb200_pswf_t *wf,
+                                     pawb200_pswf_t *wf_R, const int *fftg, const int *labels,
+                                     const double *coords, const int *labels_R, const double *coords_R);
 
 /* ---- FFT box (linalg.h:20-24) - one band, host buffers, GPU transform ----------------- */
 void pawb200_fft3d(pawb200_c128 *x, const int *G_bounds, const double *lattice,

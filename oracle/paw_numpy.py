@@ -772,6 +772,21 @@ class Projector:
             + self.compensation_terms(band_num, flip_spin)
 
 
+def project_realspace_state(band_num, wf: Wavefunction, wf_R: Wavefunction, fftg):
+    """density.c:205-230: <psi_R,b | psi_band> by brute-force integration of the AE states on `fftg`."""
+    fftg = np.asarray(fftg, dtype=np.int32)
+    NK = wf.nwk * wf.nspin
+    n = int(np.prod(fftg))
+    vol = determinant(wf.lattice)
+    out = np.zeros(wf_R.nband * NK, dtype=np.complex128)
+    for k in range(NK):
+        st = wf.realspace_state(band_num, k, fftg).reshape(-1)
+        for b in range(wf_R.nband):
+            sr = wf_R.realspace_state(b, k, fftg).reshape(-1)
+            out[b * NK + k] = np.vdot(sr, st) * (vol / n)
+    return out
+
+
 def make_site_lists(coords_R, labels_R, coords_S, labels_S, lattice, rmax_R, rmax_S, tol=0.02):
     """projector.py:115-160 with pymatgen's periodic distance restated through
     min_cart_path; element identity is label equality.  rmax_* : per-label list."""

@@ -128,6 +128,7 @@ def lib():
         L.ae_chg_density.argtypes = [c_dbl_p, P, c_int_p, c_int_p, c_dbl_p]
         L.ncl_ae_chg_density.argtypes = [c_dbl_p, P, c_int_p, c_int_p, c_dbl_p]
         L.write_volumetric.argtypes = [C.c_char_p, c_dbl_p, c_int_p, C.c_double]
+        L.project_realspace_state.argtypes = [c_dbl_p, C.c_int, P, P, c_int_p, c_int_p, c_dbl_p, c_int_p, c_dbl_p]
         L.fft3d.argtypes = [c_dbl_p, c_int_p, c_dbl_p, c_dbl_p, c_int_p,
                             C.POINTER(C.c_float), C.c_int, c_int_p]
         L.fwd_fft3d.argtypes = L.fft3d.argtypes
@@ -335,6 +336,15 @@ class RefProjector:
                                  _ip(M_R), _ip(M_S), _ip(N_R), _ip(N_S), _ip(N_RS_R), _ip(N_RS_S),
                                  _ip(self.wf.nums), _dp(self.wf.coords), _ip(self.basis.nums),
                                  _dp(self.basis.coords), _ip(self.wf.dimv), int(flip_spin))
+        return res
+
+    def realspace_projection(self, band_num, dim):
+        """pawpyc.pyx:723-736 -> project_realspace_state (density.c:205-230)."""
+        res = np.zeros(self.basis.nband * self.basis.nwk * self.basis.nspin, dtype=np.complex128)
+        dimv = np.ascontiguousarray(dim, dtype=np.int32)
+        lib().project_realspace_state(res.ctypes.data_as(c_dbl_p), int(band_num), self.wf.ptr, self.basis.ptr,
+                                      _ip(dimv), _ip(self.wf.nums), _dp(self.wf.coords), _ip(self.basis.nums),
+                                      _dp(self.basis.coords))
         return res
 
     def single_band_projection(self, band_num, flip_spin=False):

@@ -70,6 +70,8 @@ _SIGS = {
     "pawb200_ae_chg_density": (None, [c_dbl_p, C.c_void_p, c_int_p, c_int_p, c_dbl_p]),
     "pawb200_ncl_ae_chg_density": (None, [c_dbl_p, C.c_void_p, c_int_p, c_int_p, c_dbl_p]),
     "pawb200_write_volumetric": (None, [C.c_char_p, c_dbl_p, c_int_p, C.c_double]),
+    "pawb200_project_realspace_state": (None, [c_dbl_p, C.c_int, C.c_void_p, C.c_void_p, c_int_p, c_int_p, c_dbl_p,
+                                              c_int_p, c_dbl_p]),
     "pawb200_fft3d": (None, [c_dbl_p, c_int_p, c_dbl_p, c_dbl_p, c_int_p, C.c_void_p, C.c_int, c_int_p]),
     "pawb200_fwd_fft3d": (None, [c_dbl_p, c_int_p, c_dbl_p, c_dbl_p, c_int_p, C.c_void_p, C.c_int, c_int_p]),
     "pawb200_legendre": (C.c_double, [C.c_int, C.c_int, C.c_double]),

@@ -1967,6 +1967,55 @@ void pawb200_ncl_ae_chg_density(double* P, pawb200_pswf_t* wf, const int* fftg, 
   API_END_VOID
 }
 
+// density.c:205-230 (Projector method 'realspace'): AE states on the grid, brute-force overlap
+void pawb200_project_realspace_state(pawb200_c128* projs, int BAND_NUM, pawb200_pswf_t* wf, pawb200_pswf_t* wf_R,
+                                     const int* fftg, const int* labels, const double* coords, const int* labels_R,
+                                     const double* coords_R) {
+  API_BEGIN
+  require_device();
+  check_pair(wf, wf_R);
+  if (BAND_NUM < 0 || BAND_NUM >= wf->nband) throw std::runtime_error("band index out of range");
+  const long ngrid = (long)fftg[0] * fftg[1] * fftg[2];
+  const int NK = wf->nkappa(), nR = wf_R->nband;
+  SiteTables& TS = ae_tables(wf, fftg, labels, coords);
+  SiteTables& TR = ae_tables(wf_R, fftg, labels_R, coords_R);
+  DevBuf state(ngrid * sizeof(double2));
+  const double scale = determinant3(wf->lattice) / (double)ngrid;   // density.c:224
+  long batch = std::max<long>(1, (long)(fft_budget_bytes() / (sizeof(double2) * ngrid)));
+  batch = std::min<long>(batch, 64);
+  const int nchunk = 64;
+  DevBuf partial((size_t)batch * nchunk * sizeof(double2)), dres((size_t)nR * sizeof(double2));
+  std::vector<cdouble> host(nR);
+  cdouble* out = (cdouble*)projs;
+  for (int kap = 0; kap < NK; kap++) {
+    if (!wf->resident[kap] || !wf_R->resident[kap]) {
+      for (int b = 0; b < nR; b++) out[(size_t)b * NK + kap] = cdouble(0, 0);
+      continue;
+    }
+    {
+      DevBuf inv = build_inverse_map(wf, kap, fftg);
+      realspace_boxes(wf, kap, BAND_NUM, 1, fftg, TS, inv);
+      CUDA_OK(cudaMemcpyAsync(state.p, g_grid.p, ngrid * sizeof(double2), cudaMemcpyDeviceToDevice, g_stream));
+    }
+    DevBuf invR = build_inverse_map(wf_R, kap, fftg);
+    for (int b0 = 0; b0 < nR; b0 += (int)batch) {
+      const int nb = (int)std::min<long>(batch, nR - b0);
+      realspace_boxes(wf_R, kap, b0, nb, fftg, TR, invR);
+      ScopedStage tm(ST_AUGMENT);
+      grid_dot_partial_kernel<<<dim3(nchunk, nb), 256, 0, g_stream>>>(g_grid.as<double2>(), state.as<double2>(), ngrid,
+                                                                      nchunk, partial.as<double2>());
+      grid_dot_final_kernel<<<(nb + 127) / 128, 128, 0, g_stream>>>(partial.as<double2>(), nchunk, nb, scale,
+                                                                    dres.as<double2>() + b0);
+      count_launch(2);
+      check_launch();
+    }
+    CUDA_OK(cudaMemcpyAsync(host.data(), dres.p, (size_t)nR * sizeof(double2), cudaMemcpyDeviceToHost, g_stream));
+    stream_sync();
+    for (int b = 0; b < nR; b++) out[(size_t)b * NK + kap] = host[b];
+  }
+  API_END_VOID
+}
+
 void pawb200_write_volumetric(const char* filename, const double* x, const int* fftg, double scale) {
   API_BEGIN
   // density.c:461-477: x fastest, z slowest, "%E   " five per line.  Host I/O by design.

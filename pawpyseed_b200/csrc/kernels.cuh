@@ -551,4 +551,43 @@ density_accum_kernel(const double2* __restrict__ x, long ngrid, int nbox,
   }
 }
 
+// (f4) brute-force real-space overlap  [density.c:205-230]: partial[b][chunk] = sum_{g in chunk} conj(xR[b][g]) x[g]
+// Deterministic two-stage reduction (fixed chunking, tree inside the block, ordered sum over chunks).
+__global__ void __launch_bounds__(256)
+grid_dot_partial_kernel(const double2* __restrict__ xR, const double2* __restrict__ x, long ngrid, int nchunk,
+                        double2* __restrict__ partial) {
+  const int b = blockIdx.y, c = blockIdx.x;
+  const long per = (ngrid + nchunk - 1) / nchunk;
+  const long g0 = (long)c * per, g1 = min(ngrid, g0 + per);
+  double re = 0, im = 0;
+  for (long g = g0 + threadIdx.x; g < g1; g += blockDim.x) {
+    const double2 a = xR[(long)b * ngrid + g], v = x[g];
+    re += a.x * v.x + a.y * v.y;
+    im += a.x * v.y - a.y * v.x;
+  }
+  __shared__ double sr[256], si[256];
+  sr[threadIdx.x] = re;
+  si[threadIdx.x] = im;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) {
+      sr[threadIdx.x] += sr[threadIdx.x + s];
+      si[threadIdx.x] += si[threadIdx.x + s];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[(long)b * nchunk + c] = make_double2(sr[0], si[0]);
+}
+__global__ void grid_dot_final_kernel(const double2* __restrict__ partial, int nchunk, int nb, double scale,
+                                      double2* __restrict__ out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nb) return;
+  double re = 0, im = 0;
+  for (int c = 0; c < nchunk; c++) {
+    re += partial[(long)b * nchunk + c].x;
+    im += partial[(long)b * nchunk + c].y;
+  }
+  out[b] = make_double2(re * scale, im * scale);
+}
+
 }  // namespace pawb200

@@ -443,7 +443,14 @@ class CProjector:
         raise PAWpyError("method 'aug_recip' is not part of the B200 hot path (SURVEY 8f3)")
 
     def _realspace_projection(self, band_num, dim):
-        raise PAWpyError("method 'realspace' is not part of the B200 hot path (SURVEY 8f4)")
+        """pawpyc.pyx:723-736 -> project_realspace_state (density.c:205-230)."""
+        res = np.zeros(self.basis.nband * self.basis.nwk * self.basis.nspin, dtype=np.complex128, order="C")
+        dimv = self.wf.dimv if dim is None else np.array(dim, dtype=np.int32, order="C")
+        _lib.lib().pawb200_project_realspace_state(
+            res.ctypes.data_as(_lib.c_dbl_p), int(band_num), self.wf.wf_ptr, self.basis.wf_ptr, ip(dimv),
+            ip(self.wf.nums), dp(self.wf.coords), ip(self.basis.nums), dp(self.basis.coords))
+        check()
+        return res
 
     # ---- extension: all band pairs in one call ---------------------------------------------------
     def _projection_matrix(self, flip_spin=False, kappa_range=None, pseudo_only=False):

@@ -21,9 +21,11 @@ class Projector(pawpyc.CProjector):
             self._single_band_projection = self._single_band_projection_pseudo
         elif self.method == "aug_real":
             self._single_band_projection = self._single_band_projection_aug_real
-        elif self.method in ("realspace", "aug_recip"):
-            raise PAWpyError("method '%s' is outside the B200 hot path (SURVEY 8f); use 'aug_real' or 'pseudo'"
-                             % self.method)
+        elif self.method == "realspace":
+            self._single_band_projection = self._single_band_projection_realspace
+        elif self.method == "aug_recip":
+            raise PAWpyError("method 'aug_recip' is outside the B200 hot path (SURVEY 8f3); use 'aug_real', "
+                             "'realspace' or 'pseudo'")
         else:
             raise PAWpyError("method not recognized for Projector")
         if wf.ncl or basis.ncl:
@@ -83,6 +85,12 @@ class Projector(pawpyc.CProjector):
 
     def _single_band_projection_pseudo(self, band_num):
         return self.wf.pseudoprojection(band_num, self.basis)
+
+    def _single_band_projection_realspace(self, band_num, dim=None):
+        """projector.py:199-208: AE states on a real-space grid (default: the fine grid 2*dim), integrated."""
+        if dim is None:
+            dim = self.wf.dim * 2
+        return self._realspace_projection(band_num, dim)
 
     def _single_band_projection_aug_real(self, band_num, flip_spin=False):
         """projector.py:210-223."""

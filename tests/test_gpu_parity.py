@@ -229,3 +229,12 @@ def test_error_behaviour():
         pawpyc.CProjector(from_case(c1), wf)._projection_matrix()
     with pytest.raises(_lib.PAWpyError):
         pawpyc.PWFPointer.from_arrays(np.zeros(4096, np.uint8), c["kpts"], c["kws"])   # not a WAVECAR
+
+
+def test_ga4_realspace_projection_method(ga4):
+    # project_realspace_state (density.c:205-230), golden from the reference C
+    g, R, S = ga4
+    gp = np.load(os.path.join(G, "realspace_proj.npz"))
+    pr = pawpyc.CProjector(S, R)
+    got = pr._realspace_projection(int(gp["band"]), gp["dim"])
+    assert rel(got, gp["res"]) < TOL

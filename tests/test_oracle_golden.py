@@ -99,3 +99,11 @@ def test_noncollinear_fixture():
     assert rel(P[:, :, 0], g["up"]) < TOL
     assert rel(P[:, :, 1], g["down"]) < TOL
     assert rel(N.realspace_state(2, 1), g["state_b2_k1"]) < TOL
+
+
+def test_realspace_projection_method(ga4):
+    # Projector(method="realspace") -> project_realspace_state (density.c:205-230)
+    g, R, S = ga4
+    gp = np.load(os.path.join(G, "realspace_proj.npz"))
+    got = pn.project_realspace_state(int(gp["band"]), S, R, gp["dim"])
+    assert rel(got, gp["res"]) < TOL
