@@ -53,6 +53,14 @@ pawb200_pswf_t *pawb200_read_wavefunctions(const char *filename, const double *k
 pawb200_pswf_t *pawb200_read_wavefunctions_from_str(const char *start, const double *kpt_weights);
 void pawb200_free_pswf(pawb200_pswf_t *wf);                                   /* utils.h:242 */
 
+/* ---- k-point desymmetrisation (utils.h:388-393; utils.c:829-1098), SURVEY 8 row f2 --------------- */
+/* New wavefunction with num_kpts k-points: k-point q is ops[q] (3x3, reciprocal fractional) applied to
+ * source k-point maps[q] (time-reversed when trs[q] == 1) with fractional translation drs[q]; weights kws.
+ * The plane-wave remap + phase runs on the GPU; the result lives in HBM like any other wavefunction. */
+pawb200_pswf_t *pawb200_expand_symm_wf(pawb200_pswf_t *rwf, int num_kpts, const int *maps,
+                                       const double *ops, const double *drs, const double *kws,
+                                       const int *trs);
+
 /* ---- accessors (utils.h:257-279) ----------------------------------------------------- */
 int pawb200_get_nband(pawb200_pswf_t *wf);
 int pawb200_get_nwk(pawb200_pswf_t *wf);
@@ -172,6 +180,10 @@ void pawb200_set_kappa_range(pawb200_pswf_t *wf, int kappa_lo, int kappa_hi);
  * which: 0 projections, 1 up_projections, 2 down_projections, 3 wave_projections. */
 int pawb200_get_projections(pawb200_pswf_t *wf, int band, int kappa, int which, pawb200_c128 *out);
 int pawb200_num_projections(pawb200_pswf_t *wf, int which);
+/* Plane-wave coefficients of (band, kappa) in WAVECAR file order; returns the count (test accessor). */
+int pawb200_get_coefficients(pawb200_pswf_t *wf, int band, int kappa, pawb200_c64 *out);
+/* k-point (fractional) and weight of block kappa; returns its plane-wave count. */
+int pawb200_get_kpoint(pawb200_pswf_t *wf, int kappa, double *k3, double *weight);
 /* (site, n, l, m) per channel, int32[4*nproj_total] - the bit-exact index contract. */
 int pawb200_get_channel_index(pawb200_pswf_t *wf, int *out);
 /* sphere index list of one site as built by setup_projections (grid linear indices). */

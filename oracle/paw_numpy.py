@@ -457,6 +457,7 @@ class Wavefunction:
         self.Gs = Gs            # list per k (len nwk) of int[npw,3]
         self.Cs = Cs            # list per kappa of complex64 [nband, npw_file]
         self.occs = np.asarray(occs, dtype=np.float64)   # [nkappa, nband]
+        self.energies = None if energies is None else np.asarray(energies, dtype=np.float64)
         self.encut, self.ncl = encut, ncl
         self.P = None
         self.W = None
@@ -612,6 +613,73 @@ class Wavefunction:
                     P += d * self.kws[kap % self.nwk] * occ * mult
         return P
 
+
+
+# --------------------------------------------------------------------------- #
+# k-point desymmetrisation (utils.c:829-1098 `expand_symm_wf`)
+# --------------------------------------------------------------------------- #
+def expand_symm_wf(rwf: "Wavefunction", maps, ops, drs, kws, trs):
+    """New Wavefunction whose k-point q is ops[q] applied to rwf's k-point maps[q]
+    (time-reversed if trs[q]) with fractional translation drs[q].  Coefficients and
+    phase factors are complex64 like the reference's (utils.c:1040-1081)."""
+    from pawpyseed_b200.synth import enumerate_gvectors
+    if rwf.ncl:
+        raise NotImplementedError("utils.c:994-1056 cannot map the duplicated spinor G list")
+    maps = np.asarray(maps, dtype=np.int64)
+    ops = np.asarray(ops, dtype=np.float64).reshape(-1, 3, 3)
+    drs = np.asarray(drs, dtype=np.float64).reshape(-1, 3)
+    nk = len(maps)
+    kpts, Gs, Cs, occs, ens = [], [], [], [], []
+    kdiffs = []
+    for q in range(nk):
+        k = ops[q] @ rwf.kpts[maps[q]]                     # utils.c:885-889 rotate_frac
+        if trs[q] == 1:
+            k = -k
+        kd = np.array([math.floor(v + 0.5) if v >= 0 else -math.floor(-v + 0.5) for v in k])  # C round()
+        k = k - kd
+        for i in range(3):                                  # utils.c:900-905
+            if abs(k[i] + 0.5) < 0.0001:
+                kd[i] -= 1
+                k[i] += 1
+        kpts.append(k)
+        kdiffs.append(kd)
+        g = enumerate_gvectors(rwf.lattice, rwf.encut, k)   # utils.c:928-975 (same order, integer bounds)
+        if len(g) != len(rwf.Gs[maps[q]]):
+            raise ValueError("plane-wave count mismatch in expand_symm_wf")
+        Gs.append(g)
+    for kap in range(nk * rwf.nspin):
+        q = kap % nk
+        rnum = int(maps[q]) + (rwf.nwk if (kap >= nk and rwf.nspin == 2) else 0)
+        g_new, g_old = Gs[q], rwf.Gs[maps[q]]
+        lookup = {tuple(v): w for w, v in enumerate(g_new.tolist())}
+        pw = (g_old.astype(np.float64) @ ops[q].T)
+        if trs[q] == 1:
+            pw = -pw
+        pw = pw + kdiffs[q]
+        gi = np.rint(pw).astype(np.int64)
+        npw = len(g_new)
+        gmaps = np.full(npw, -1, dtype=np.int64)
+        factors = np.zeros(npw, dtype=np.complex64)
+        sign = -1.0 if trs[q] == 0 else 1.0
+        for g in range(npw):
+            w = lookup.get((int(gi[g, 0]), int(gi[g, 1]), int(gi[g, 2])), -1)
+            if w < 0:
+                raise ValueError("bad plane-wave mapping")
+            gmaps[w] = g
+            ph = float(np.dot(kpts[q], drs[q]) + np.dot(pw[g], drs[q]))
+            arg = np.float32(sign * 2 * PI * ph)
+            factors[w] = np.complex64(complex(math.cos(float(arg)), math.sin(float(arg))))
+        if (gmaps < 0).any():
+            raise ValueError("incomplete plane-wave mapping")
+        src = rwf.Cs[rnum][:, gmaps].astype(np.complex64)
+        new = (factors[None, :] * src).astype(np.complex64)
+        if trs[q] == 1:
+            new = np.conj(new)
+        Cs.append(new)
+        occs.append(rwf.occs[rnum])
+        ens.append(rwf.energies[rnum] if getattr(rwf, "energies", None) is not None else np.zeros(rwf.nband))
+    return Wavefunction(rwf.lattice, kpts, kws, rwf.nspin, rwf.nband, Gs, Cs, np.array(occs), np.array(ens),
+                        rwf.encut, False)
 
 # --------------------------------------------------------------------------- #
 # off-site partial-wave overlap (radial.c:116-196, gaunt.py:17-30)

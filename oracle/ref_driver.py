@@ -109,6 +109,8 @@ def lib():
         L.read_wavefunctions_from_str.restype = P
         L.read_wavefunctions_from_str.argtypes = [C.c_void_p, c_dbl_p]
         L.free_pswf.argtypes = [P]
+        L.expand_symm_wf.restype = P
+        L.expand_symm_wf.argtypes = [P, C.c_int, c_int_p, c_dbl_p, c_dbl_p, c_dbl_p, c_int_p]
         L.get_projector_list.restype = C.POINTER(ppot_t)
         L.get_projector_list.argtypes = [C.c_int, c_int_p, c_int_p, c_dbl_p, c_dbl_p,
                                          c_dbl_p, c_dbl_p, c_dbl_p, C.c_double]
@@ -184,11 +186,28 @@ class RefWavefunction:
             self._img = np.ascontiguousarray(image_or_path, dtype=np.uint8)
             self.ptr = L.read_wavefunctions_from_str(                # pawpyc.pyx:221
                 self._img.ctypes.data_as(C.c_void_p), _dp(self.kws))
+        self._describe()
+
+    def _describe(self):
         w = self.ptr.contents
         self.nband, self.nwk, self.nspin, self.ncl = w.nband, w.nwk, w.nspin, bool(w.is_ncl)
         self.encut = w.encut
         self.lattice = np.array([w.lattice[i] for i in range(9)]).reshape(3, 3)
         self.projector_owner = False
+
+    def expand_symm(self, maps, ops, drs, kws, trs):
+        """pawpyc.pyx:227-292 (`PWFPointer.from_pointer_and_kpts`) -> expand_symm_wf (utils.c:829)."""
+        maps = np.ascontiguousarray(maps, dtype=np.int32)
+        ops = np.ascontiguousarray(ops, dtype=np.float64).reshape(-1)
+        drs = np.ascontiguousarray(drs, dtype=np.float64).reshape(-1)
+        trs = np.ascontiguousarray(trs, dtype=np.int32)
+        new = object.__new__(RefWavefunction)
+        new.kws = np.ascontiguousarray(kws, dtype=np.float64)
+        new.ptr = lib().expand_symm_wf(self.ptr, len(maps), _ip(maps), _dp(ops), _dp(drs), _dp(new.kws), _ip(trs))
+        # expand_symm_wf leaves encut unset on the new struct (utils.c:836-866); carry it over like pawpyc.pyx:290
+        new.ptr.contents.encut = self.ptr.contents.encut
+        new._describe()
+        return new
 
     def free(self):
         if self.ptr:

@@ -41,6 +41,9 @@ _SIGS = {
     "pawb200_read_wavefunctions": (C.c_void_p, [C.c_char_p, c_dbl_p]),
     "pawb200_read_wavefunctions_from_str": (C.c_void_p, [C.c_void_p, c_dbl_p]),
     "pawb200_free_pswf": (None, [C.c_void_p]),
+    "pawb200_expand_symm_wf": (C.c_void_p, [C.c_void_p, C.c_int, c_int_p, c_dbl_p, c_dbl_p, c_dbl_p, c_int_p]),
+    "pawb200_get_coefficients": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "pawb200_get_kpoint": (C.c_int, [C.c_void_p, C.c_int, c_dbl_p, c_dbl_p]),
     "pawb200_get_nband": (C.c_int, [C.c_void_p]),
     "pawb200_get_nwk": (C.c_int, [C.c_void_p]),
     "pawb200_get_nspin": (C.c_int, [C.c_void_p]),

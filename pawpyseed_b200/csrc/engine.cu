@@ -1916,6 +1916,140 @@ void pawb200_compensation_terms(pawb200_c128* overlap, int BAND_NUM, pawb200_psw
   API_END_VOID
 }
 
+// ---- (f2) k-point desymmetrisation: utils.h:392-393, utils.c:829-1098 -------------------------------------
+pawb200_pswf_t* pawb200_expand_symm_wf(pawb200_pswf_t* rwf, int num_kpts, const int* maps, const double* ops,
+                                       const double* drs, const double* kws, const int* trs) {
+  API_BEGIN
+  require_device();
+  if (!rwf || num_kpts <= 0) throw std::runtime_error("bad arguments to expand_symm_wf");
+  if (rwf->ncl) throw std::runtime_error("desymmetrisation of noncollinear wavefunctions is not defined "
+                                         "(NCLWavefunction.desymmetrized_copy raises in the reference too)");
+  auto wf = std::make_unique<pawb200_pswf>();
+  wf->nspin = rwf->nspin; wf->nband = rwf->nband; wf->nwk = num_kpts; wf->encut = rwf->encut; wf->ncl = 0;
+  memcpy(wf->lattice, rwf->lattice, sizeof(wf->lattice));
+  memcpy(wf->reclattice, rwf->reclattice, sizeof(wf->reclattice));
+  const int NK = num_kpts * wf->nspin;
+  wf->kp.resize(NK); wf->weight.resize(NK); wf->C.resize(NK); wf->ldc.assign(NK, 0);
+  wf->resident.assign(NK, 0); wf->perm_dev.resize(NK);
+  WavecarHeader hd;
+  hd.encut = rwf->encut;
+  memcpy(hd.lattice, rwf->lattice, sizeof(hd.lattice));
+  memcpy(hd.reclattice, rwf->reclattice, sizeof(hd.reclattice));
+  for (int d = 0; d < 3; d++) hd.nbmax[d] = rwf->G_bounds[2 * d + 1] - rwf->G_bounds[2 * d] + 2;   // utils.c:925-927
+  for (int knum = 0; knum < NK; knum++) {
+    const int kq = knum % num_kpts;
+    if (maps[kq] < 0 || maps[kq] >= rwf->nwk) throw std::runtime_error("k-point map out of range");
+    int rnum = maps[kq];
+    const int tr = trs[kq];
+    if (knum >= num_kpts && rwf->nspin == 2) rnum += rwf->nwk;
+    const KPointInfo& rk = rwf->kp[rnum];
+    KPointInfo& nk = wf->kp[knum];
+    const double* op = ops + 9 * kq;
+    const double* dr = drs + 3 * kq;
+    for (int i = 0; i < 3; i++) nk.k[i] = op[3 * i] * rk.k[0] + op[3 * i + 1] * rk.k[1] + op[3 * i + 2] * rk.k[2];
+    if (tr == 1) for (int i = 0; i < 3; i++) nk.k[i] *= -1;
+    double kdiff[3];
+    for (int i = 0; i < 3; i++) {
+      kdiff[i] = std::round(nk.k[i]);
+      nk.k[i] -= kdiff[i];
+      if (std::fabs(nk.k[i] + 0.5) < 0.0001) {
+        kdiff[i] -= 1;
+        nk.k[i] += 1;
+      }
+    }
+    wf->weight[knum] = kws[kq];
+    nk.nplane = rk.nplane;
+    nk.energy = rk.energy;
+    nk.occ = rk.occ;
+    nk.G = enumerate_g(hd, nk.k, wf->G_bounds);
+    const int npw = (int)(nk.G.size() / 3);
+    if (npw != rk.nplane)
+      throw std::runtime_error("desymmetrised k-point has " + std::to_string(npw) + " plane waves, source has " +
+                               std::to_string(rk.nplane) + " (operation is not a symmetry of the reciprocal lattice?)");
+    box_order(nk);
+    // G -> index map of the new list, then source index + phase per new plane wave  (utils.c:994-1050)
+    int lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+    for (int w = 0; w < npw; w++)
+      for (int d = 0; d < 3; d++) {
+        lo[d] = std::min(lo[d], (int)nk.G[3 * w + d]);
+        hi[d] = std::max(hi[d], (int)nk.G[3 * w + d]);
+      }
+    const int ng[3] = {hi[0] - lo[0] + 1, hi[1] - lo[1] + 1, hi[2] - lo[2] + 1};
+    std::vector<int> kptinds((size_t)ng[0] * ng[1] * ng[2], -1);
+    for (int w = 0; w < npw; w++)
+      kptinds[((size_t)(nk.G[3 * w] - lo[0]) * ng[1] + (nk.G[3 * w + 1] - lo[1])) * ng[2] + (nk.G[3 * w + 2] - lo[2])] = w;
+    std::vector<int> gmaps(npw, -1);
+    std::vector<float2> factors(npw);
+    for (int g = 0; g < npw; g++) {
+      double pw[3] = {(double)rk.G[3 * g], (double)rk.G[3 * g + 1], (double)rk.G[3 * g + 2]};
+      double r[3];
+      for (int i = 0; i < 3; i++) r[i] = op[3 * i] * pw[0] + op[3 * i + 1] * pw[1] + op[3 * i + 2] * pw[2];
+      for (int i = 0; i < 3; i++) pw[i] = (tr == 1 ? -r[i] : r[i]) + kdiff[i];
+      const int gx = (int)std::round(pw[0]), gy = (int)std::round(pw[1]), gz = (int)std::round(pw[2]);
+      int w = -1;
+      if (gx >= lo[0] && gx <= hi[0] && gy >= lo[1] && gy <= hi[1] && gz >= lo[2] && gz <= hi[2])
+        w = kptinds[((size_t)(gx - lo[0]) * ng[1] + (gy - lo[1])) * ng[2] + (gz - lo[2])];
+      if (w < 0) throw std::runtime_error("bad plane-wave mapping in expand_symm_wf (operation does not map the basis onto itself)");
+      gmaps[w] = g;
+      const double ph = nk.k[0] * dr[0] + nk.k[1] * dr[1] + nk.k[2] * dr[2] + pw[0] * dr[0] + pw[1] * dr[1] + pw[2] * dr[2];
+      // cexpf of the double argument converted to float complex, like utils.c:1040-1044
+      const std::complex<float> f = std::exp(std::complex<float>(0.0f, (float)((tr == 0 ? -1.0 : 1.0) * 2 * kPi * ph)));
+      factors[w] = make_float2(f.real(), f.imag());
+    }
+    for (int w = 0; w < npw; w++)
+      if (gmaps[w] < 0) throw std::runtime_error("incomplete plane-wave mapping in expand_symm_wf");
+    if (!rwf->resident[rnum]) continue;
+    wf->resident[knum] = 1;
+    // storage (box) order on both sides: new position j holds file index perm[j]; its source sits at pos_old[...]
+    std::vector<int> src(npw);
+    std::vector<float2> fac(npw);
+    for (int j = 0; j < npw; j++) {
+      const int w = nk.perm[j];
+      src[j] = rk.pos[gmaps[w]];
+      fac[j] = factors[w];
+    }
+    const long ld = ((long)npw + 31) / 32 * 32;
+    wf->ldc[knum] = ld;
+    wf->C[knum].alloc((size_t)wf->nband * ld * sizeof(float2));
+    wf->C[knum].zero((size_t)wf->nband * ld * sizeof(float2));
+    wf->perm_dev[knum] = upload(nk.perm);
+    DevBuf dsrc = upload(src), dfac = upload(fac);
+    wait_coeffs(rwf, rnum, 0, rwf->nband);
+    dim3 grid((npw + 255) / 256, std::min(wf->nband, 64));
+    symm_map_kernel<<<grid, 256, 0, g_stream>>>(rwf->C[rnum].as<float2>(), rwf->ldc[rnum], wf->C[knum].as<float2>(), ld,
+                                                wf->nband, npw, dsrc.as<int>(), dfac.as<float2>(), tr == 1 ? 1 : 0);
+    count_launch();
+    check_launch();
+  }
+  return wf.release();
+  API_END(nullptr)
+}
+
+// Plane-wave coefficients of (band, kappa) in WAVECAR file order (complex64, nplane entries) - test accessor.
+int pawb200_get_coefficients(pawb200_pswf_t* wf, int band, int kappa, pawb200_c64* out) {
+  API_BEGIN
+  check_kpoint(wf, band, kappa);
+  const KPointInfo& kp = wf->kp[kappa];
+  const int hl = wf->npw_half(kappa);
+  std::vector<float2> row(kp.nplane);
+  wait_coeffs(wf, kappa, band, band + 1);
+  CUDA_OK(cudaMemcpyAsync(row.data(), wf->C[kappa].as<float2>() + (long)band * wf->ldc[kappa],
+                          (size_t)kp.nplane * sizeof(float2), cudaMemcpyDeviceToHost, g_stream));
+  stream_sync();
+  float2* o = (float2*)out;
+  for (int h = 0; h < wf->halves(); h++)
+    for (int j = 0; j < hl; j++) o[h * hl + kp.perm[j]] = row[h * hl + j];
+  return kp.nplane;
+  API_END(-1)
+}
+
+int pawb200_get_kpoint(pawb200_pswf_t* wf, int kappa, double* k3, double* weight) {
+  if (!wf || kappa < 0 || kappa >= wf->nkappa()) return -1;
+  for (int i = 0; i < 3; i++) k3[i] = wf->kp[kappa].k[i];
+  if (weight) *weight = wf->weight[kappa];
+  return wf->kp[kappa].nplane;
+}
+
 // ---- real space ---------------------------------------------------------------------------------
 void pawb200_realspace_state(pawb200_c128* x, int BAND_NUM, int KPOINT_NUM, pawb200_pswf_t* wf, const int* fftg,
                              const int* labels, const double* coords) {

@@ -71,6 +71,25 @@ permute_coeff_kernel(const float2* __restrict__ raw, float2* __restrict__ C, lon
       C[(long)b * ld + (long)h * half_len + j] = raw[(long)b * ld + (long)h * half_len + src];
 }
 
+// (f2) k-point desymmetrisation  [utils.c:1070-1081]: Cnew[b][j] = fac[j] * Cold[b][src[j]] (conjugated under
+// time reversal), in single precision without FMA contraction so it rounds like the reference's complex float
+// multiply.
+__global__ void __launch_bounds__(256)
+symm_map_kernel(const float2* __restrict__ Cold, long ldo, float2* __restrict__ Cnew, long ldn, int nband,
+                int npw, const int* __restrict__ src, const float2* __restrict__ fac, int tr) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= npw) return;
+  const int sj = src[j];
+  const float2 f = fac[j];
+  for (int b = blockIdx.y; b < nband; b += gridDim.y) {
+    const float2 c = Cold[(long)b * ldo + sj];
+    float re = __fsub_rn(__fmul_rn(f.x, c.x), __fmul_rn(f.y, c.y));
+    float im = __fadd_rn(__fmul_rn(f.x, c.y), __fmul_rn(f.y, c.x));
+    if (tr) im = -im;
+    Cnew[(long)b * ldn + j] = make_float2(re, im);
+  }
+}
+
 // (a3) gather back after a forward FFT  [linalg.c:72-77]; narrow to complex64
 __global__ void gather_pw_kernel(const double2* __restrict__ x, const int* __restrict__ gidx,
                                  float2* __restrict__ Cout, int npw, double scale) {

@@ -137,6 +137,34 @@ class PWFPointer:
         self._read(source)
         return self
 
+    @staticmethod
+    def from_pointer_and_kpts(ptr, structure, kpts, band_props, allkpts, weights, symprec,
+                              time_reversal_symmetry, symmops=None):
+        """pawpyc.pyx:227-267: desymmetrised copy of the wavefunction behind `ptr` (the source is left
+        untouched).  `symmops` (reciprocal-fractional operators) skips the pymatgen space-group search."""
+        from .symmetry import get_kpt_mapping, get_nosym_kpoints, make_c_ops
+        if allkpts is None or weights is None:
+            allkpts, orig_kptnums, op_nums, symmops, trs = get_nosym_kpoints(
+                kpts, structure, symprec=symprec, fil_trsym=time_reversal_symmetry, symmops=symmops)
+            weights = np.ones(allkpts.shape[0], dtype=np.float64)
+            weights[np.linalg.norm(allkpts, axis=1) < 1e-10] *= 0.5
+            weights /= np.sum(weights)
+        else:
+            orig_kptnums, op_nums, symmops, trs = get_kpt_mapping(allkpts, kpts, structure, symprec=symprec,
+                                                                  symmops=symmops)
+        ops, drs = make_c_ops(op_nums, symmops)
+        pwfp = PWFPointer()
+        pwfp.kpts = np.ascontiguousarray(allkpts, dtype=np.float64).reshape(-1, 3)
+        pwfp.weights = f64(weights)
+        pwfp.band_props = np.array(band_props)
+        maps, trs = i32(orig_kptnums), i32(trs)
+        pwfp.ptr = _lib.lib().pawb200_expand_symm_wf(ptr, len(maps), ip(maps), dp(ops), dp(drs), dp(pwfp.weights),
+                                                    ip(trs))
+        check()
+        if not pwfp.ptr:
+            raise PAWpyError("expand_symm_wf returned NULL")
+        return pwfp
+
     def _read(self, source):
         L = _lib.lib()
         kws = f64(self.weights)
@@ -185,6 +213,24 @@ class PseudoWavefunction:
                 self.wf_ptr = None
         except Exception:
             pass
+
+    def _desymmetrized_pwf(self, structure, band_props, allkpts=None, weights=None, symprec=1e-4,
+                           time_reversal_symmetry=True, symmops=None):
+        """pawpyc.pyx:317-325."""
+        return PWFPointer.from_pointer_and_kpts(self.wf_ptr, structure, self.kpts, band_props, allkpts, weights,
+                                                symprec, time_reversal_symmetry, symmops=symmops)
+
+    def _get_coefficients(self, b, kappa):
+        """Plane-wave coefficients of (band, kappa) in WAVECAR order (test accessor, complex64)."""
+        L = _lib.lib()
+        k3 = np.zeros(3)
+        n = L.pawb200_get_kpoint(self.wf_ptr, int(kappa), dp(k3), None)
+        if n < 0:
+            raise ValueError("Invalid kpoint index %d" % kappa)
+        out = np.zeros(n, dtype=np.complex64)
+        L.pawb200_get_coefficients(self.wf_ptr, int(b), int(kappa), out.ctypes.data_as(C.c_void_p))
+        check()
+        return out
 
     def pseudoprojection(self, band_num, basis, flip_spin=False):
         """<psibt_n1k|psit_n2k> for all n1, k and a given n2 (pawpyc.pyx:311-325)."""

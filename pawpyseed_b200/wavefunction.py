@@ -124,9 +124,16 @@ class Wavefunction(pawpyc.CWavefunction):
         self.dim = np.array(dim, dtype=np.int32)
         self.update_dimv(dim)
 
-    def desymmetrized_copy(self, allkpts=None, weights=None, symprec=None, time_reversal_symmetry=True):
-        raise PAWpyError("k-point desymmetrisation (expand_symm_wf) is outside the B200 hot path "
-                         "(SURVEY 8f2); pass wavefunctions computed with ISYM=0/-1")
+    def desymmetrized_copy(self, allkpts=None, weights=None, symprec=None, time_reversal_symmetry=True,
+                           symmops=None):
+        """Copy of self on a k-point mesh that is not reduced by crystal symmetry (wavefunction.py:249-279).
+        The remap runs on the GPU (pawb200_expand_symm_wf).  `symmops` (operators in reciprocal fractional
+        coordinates, see symmetry.get_symmops) is an extension that skips the pymatgen space-group search."""
+        if not symprec:
+            symprec = self.symprec
+        pwf = self._desymmetrized_pwf(self.structure, self.band_props, allkpts, weights, symprec,
+                                      time_reversal_symmetry, symmops=symmops)
+        return Wavefunction(self.structure, pwf, self.cr, self.dim, symprec=symprec)
 
     # -- constructors (wavefunction.py:281-384) ---------------------------------------------------
     @staticmethod

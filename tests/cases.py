@@ -37,3 +37,40 @@ def small_case(seed=7, nband=12, nspin=2, encut=200.0, kpts=((0.25, 0.25, 0.25),
     return dict(image=img, kws=kws, kpts=kpts, lattice=lattice, coords=coords,
                 labels=np.asarray(labels, dtype=np.int32), dim=np.asarray(dim, dtype=np.int32), pps=pps,
                 grid_encut=synth.grid_encut(dim, lattice), nband=nband, nspin=nspin, ncl=ncl)
+
+
+def desymm_case(seed=21, nband=5, nspin=2, encut=180.0):
+    """Cubic two-element cell with an irreducible k-set and the operations (reciprocal fractional
+    coordinates) that expand it: rotations, inversion, time reversal, fractional translations."""
+    a = 4.6
+    lattice = np.eye(3) * a
+    kpts = np.array([[0.25, 0.25, 0.25], [0.0, 0.25, 0.5], [0.0, 0.0, 0.0]])
+    c = small_case(seed=seed, nband=nband, nspin=nspin, encut=encut, kpts=kpts, lattice=lattice,
+                   coords=[[0.0, 0.0, 0.0], [0.5, 0.5, 0.5], [0.5, 0.5, 0.0], [0.0, 0.0, 0.5]])
+    E = np.eye(3)
+    C4z = np.array([[0.0, -1.0, 0.0], [1.0, 0.0, 0.0], [0.0, 0.0, 1.0]])
+    C3 = np.array([[0.0, 0.0, 1.0], [1.0, 0.0, 0.0], [0.0, 1.0, 0.0]])
+    Mx = np.diag([-1.0, 1.0, 1.0])
+    # (source k, operator, translation, time reversal); the k = (0,1/4,1/2) images exercise the -1/2 -> +1/2 fold
+    spec = [(0, E, (0, 0, 0), 0), (0, C4z, (0.5, 0.0, 0.0), 0), (0, -E, (0, 0, 0), 0), (0, Mx, (0.0, 0.5, 0.25), 1),
+            (1, E, (0, 0, 0), 0), (1, C3, (0.5, 0.5, 0.5), 0), (1, C4z @ C3, (0.25, 0.0, 0.5), 1),
+            (1, -E, (0.0, 0.0, 0.5), 0), (2, E, (0, 0, 0), 0), (2, C3, (0.5, 0.5, 0.0), 1)]
+    c["maps"] = np.array([s[0] for s in spec], dtype=np.int32)
+    c["ops"] = np.array([s[1] for s in spec], dtype=np.float64)
+    c["drs"] = np.array([s[2] for s in spec], dtype=np.float64)
+    c["trs"] = np.array([s[3] for s in spec], dtype=np.int32)
+    c["new_kws"] = np.full(len(spec), 1.0 / len(spec))
+    return c
+
+
+def cubic_point_group():
+    """The 48 signed permutation matrices (O_h in the fractional coordinates of a cubic cell)."""
+    import itertools
+    mats = []
+    for perm in itertools.permutations(range(3)):
+        for signs in itertools.product((1.0, -1.0), repeat=3):
+            m = np.zeros((3, 3))
+            for r in range(3):
+                m[r, perm[r]] = signs[r]
+            mats.append(m)
+    return mats

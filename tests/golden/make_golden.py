@@ -1,7 +1,7 @@
 """Generates tests/golden/*.npz from the UNMODIFIED reference C (oracle/_ref/libpawpy_ref.so).
 
 Run in the build container (needs /root/reference for the bundled WAVECARs):
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py [base] [realspace_proj] [volumetric] [desymm]    (default: all)
 Inputs are (a) the first bands of the reference's own fixtures test_files/WAVECAR,
 WAVECAR2.gz and noncollinear/WAVECAR re-packed into small WAVECAR images, and (b) seeded
 synthetic cells from tests/cases.py.  Every stored output comes from the reference library
@@ -76,8 +76,7 @@ def run_pair(imgR, imgS, kws, pps, labelsR, coordsR, labelsS, coordsS, dim, cats
     return out
 
 
-def main():
-    os.makedirs(HERE, exist_ok=True)
+def make_base():
     pps_ga = synth.synthetic_pps(["Ga"])
     kws = np.array([0.5, 0.5])
     dim = np.array([20, 20, 20], np.int32)
@@ -121,8 +120,63 @@ def main():
     N.free()
     np.savez_compressed(os.path.join(HERE, "ncl.npz"), image=imgn, kpts=kptsn, kws=kwsn, dim=dimn, up=up, down=dn,
                         state_b2_k1=st, density=dens, grid_encut=gen)
-    for f in ("ga4.npz", "synth_gan.npz", "ncl.npz"):
-        print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")
+
+
+def make_realspace_proj():
+    """Projector(method="realspace") on the Ga4 pair: project_realspace_state (density.c:205-230), band 3, 24^3."""
+    g = np.load(os.path.join(HERE, "ga4.npz"), allow_pickle=True)
+    pps_ga = synth.synthetic_pps(["Ga"])
+    labels = np.zeros(4, np.int32)
+    R, S = rd.RefWavefunction(g["image_R"], g["kws"]), rd.RefWavefunction(g["image_S"], g["kws"])
+    for w in (R, S):
+        w.setup_projections(pps_ga, labels, cases.GA4_COORDS, g["dim"], float(g["grid_encut"]))
+    pr = rd.RefProjector(S, R, [[], [], [], [], [], []])
+    dim = np.array([24, 24, 24], np.int32)
+    res = pr.realspace_projection(3, dim)
+    R.free(); S.free()
+    np.savez_compressed(os.path.join(HERE, "realspace_proj.npz"), band=3, dim=dim, res=res)
+
+
+def make_volumetric():
+    """Text written by the reference's write_volumetric (density.c:461-477) for a seeded 3x4x5 grid."""
+    import tempfile
+    rng = np.random.default_rng(5)
+    dim = np.array([3, 4, 5], np.int32)
+    x = rng.standard_normal(60) * 10.0 ** rng.integers(-4, 5, 60)
+    fn = os.path.join(tempfile.mkdtemp(), "v.txt")
+    rd.lib().write_volumetric(fn.encode(), rd._dp(x), rd._ip(dim), 1.5)
+    np.savez_compressed(os.path.join(HERE, "volumetric.npz"), x=x, dim=dim, scale=1.5, text=open(fn).read())
+
+
+def make_desymm():
+    """expand_symm_wf (utils.c:829-1098) on a seeded cubic, spin-polarised cell: rotations, an inversion,
+    time reversal and fractional translations; stores the new coefficients and the projections after
+    setup_projections on the expanded wavefunction."""
+    c = cases.desymm_case()
+    R = rd.RefWavefunction(c["image"], c["kws"])
+    E = R.expand_symm(c["maps"], c["ops"], c["drs"], c["new_kws"], c["trs"])
+    NK = E.nwk * E.nspin
+    kpts = np.array([E.kpt(k) for k in range(E.nwk)])
+    gvecs = np.array([E.gvecs(k) for k in range(E.nwk)], dtype=object)
+    coeffs = np.array([[E.coeffs(kap, b) for b in range(E.nband)] for kap in range(NK)], dtype=object)
+    E.setup_projections(c["pps"], c["labels"], c["coords"], c["dim"], c["grid_encut"])
+    proj = np.array([[E.projections(k, b) for b in range(E.nband)] for k in range(NK)])
+    occ = np.array([[rd.lib().get_occ(E.ptr, b, k % E.nwk, k // E.nwk) for b in range(E.nband)] for k in range(NK)])
+    np.savez_compressed(os.path.join(HERE, "desymm.npz"), kpts=kpts, gvecs=gvecs, coeffs=coeffs, proj=proj, occ=occ)
+    R.free()
+
+
+MAKERS = {"base": make_base, "realspace_proj": make_realspace_proj, "volumetric": make_volumetric,
+          "desymm": make_desymm}
+
+
+def main():
+    os.makedirs(HERE, exist_ok=True)
+    for name in (sys.argv[1:] or list(MAKERS)):
+        MAKERS[name]()
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")
 
 
 if __name__ == "__main__":

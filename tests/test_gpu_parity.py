@@ -238,3 +238,40 @@ def test_ga4_realspace_projection_method(ga4):
     pr = pawpyc.CProjector(S, R)
     got = pr._realspace_projection(int(gp["band"]), gp["dim"])
     assert rel(got, gp["res"]) < TOL
+
+
+def test_desymmetrisation_vs_reference_and_oracle():
+    # expand_symm_wf (utils.c:829-1098) remapped on the GPU.  The phase factors come from the
+    # same cexpf and the complex64 product is unfused, so coefficients match the reference C bit for bit; the
+    # FP64 projections of the expanded wavefunction then meet the 1e-10 bar.
+    c = cases.desymm_case()
+    g = np.load(os.path.join(G, "desymm.npz"), allow_pickle=True)
+    src = pawpyc.CWavefunction(pawpyc.PWFPointer.from_arrays(c["image"], c["kpts"], c["kws"]))
+    L = _lib.lib()
+    pw = pawpyc.PWFPointer()
+    pw.kpts, pw.weights, pw.band_props = g["kpts"], c["new_kws"], np.zeros(4)
+    ops, drs = np.ascontiguousarray(c["ops"]).reshape(-1), np.ascontiguousarray(c["drs"]).reshape(-1)
+    pw.ptr = L.pawb200_expand_symm_wf(src.wf_ptr, len(c["maps"]), _lib.ip(c["maps"]), _lib.dp(ops), _lib.dp(drs),
+                                      _lib.dp(pw.weights), _lib.ip(c["trs"]))
+    _lib.check()
+    E = pawpyc.CWavefunction(pw)
+    assert (E.nwk, E.nspin, E.nband) == (len(c["maps"]), 2, c["nband"])
+    k3 = np.zeros(3)
+    for kap in range(E.nwk * E.nspin):
+        n = L.pawb200_get_kpoint(E.wf_ptr, kap, _lib.dp(k3), None)
+        assert np.array_equal(k3, g["kpts"][kap % E.nwk]) and n == len(g["gvecs"][kap % E.nwk])
+        for b in range(E.nband):
+            assert np.array_equal(E._get_coefficients(b, kap), g["coeffs"][kap][b])
+            assert L.pawb200_get_occ(E.wf_ptr, b, kap % E.nwk, kap // E.nwk) == g["occ"][kap][b]
+    E._c_projector_setup(len(c["pps"]), len(c["labels"]), c["grid_encut"], c["labels"], c["coords"], c["dim"], c["pps"])
+    P = np.array([[E._get_projections(b, kap) for b in range(E.nband)] for kap in range(E.nwk * E.nspin)])
+    assert rel(P, g["proj"]) < TOL
+    # the source wavefunction is untouched and still usable
+    assert np.array_equal(src._get_coefficients(1, 0), pn.Wavefunction.from_image(c["image"], c["kws"]).Cs[0][1])
+    # bad operator (not a symmetry of the reciprocal lattice) is reported, not silently mis-mapped
+    bad = ops.copy()
+    bad[:9] = np.array([[1.0, 0.3, 0.0], [0.0, 1.0, 0.0], [0.0, 0.0, 1.0]]).reshape(-1)
+    assert not L.pawb200_expand_symm_wf(src.wf_ptr, len(c["maps"]), _lib.ip(c["maps"]), _lib.dp(bad), _lib.dp(drs),
+                                        _lib.dp(pw.weights), _lib.ip(c["trs"]))
+    with pytest.raises(_lib.PAWpyError):
+        _lib.check()

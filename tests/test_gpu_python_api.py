@@ -123,3 +123,29 @@ def test_ncl_wavefunction_api():
         Projector(wf, wf)                                       # projector.py:74-75
     with pytest.raises(PAWpyError):
         Wavefunction.from_arrays(struct, g["image"], cr, g["dim"], g["kpts"], g["kws"])   # wavefunction.py:205-208
+
+
+def test_desymmetrized_copy_matches_oracle():
+    # wavefunction.py:249-279 with explicit operators (no pymatgen here): irreducible k-set -> half zone
+    from pawpyseed_b200 import symmetry
+    c = cases.desymm_case()
+    wf = build(c, ["Ga", "N", "Ga", "N"])
+    ops = [symmetry.SymmOp(m) for m in cases.cubic_point_group()]
+    new = wf.desymmetrized_copy(symmops=ops)
+    allk, orig, opn, _, trs = symmetry.get_nosym_kpoints(c["kpts"], symmops=ops)
+    assert new.nwk == len(allk) == 14 and np.allclose(new.kpts, allk)
+    assert abs(new.kws.sum() - 1) < 1e-14 and new.kws[2] == pytest.approx(0.5 * new.kws[0])
+    R = pn.Wavefunction.from_image(c["image"], c["kws"])
+    o_ops, o_drs = symmetry.make_c_ops(opn, ops)
+    E = pn.expand_symm_wf(R, orig, o_ops.reshape(-1, 3, 3), o_drs.reshape(-1, 3), new.kws, trs)
+    for kap in (0, 5, 13, 14 + 9):
+        for b in (0, c["nband"] - 1):
+            assert rel(new._get_coefficients(b, kap), E.Cs[kap][b]) < 5e-7
+    # a projection from the expanded set onto itself is the identity on the pseudo + augmentation level
+    new.check_c_projectors()
+    E.setup_projections(c["pps"], c["labels"], c["coords"], c["dim"], c["grid_encut"])
+    P = np.array([new._get_projections(b, 3) for b in range(new.nband)])
+    assert rel(P, np.asarray(E.P)[3]) < 5e-6
+    # mapping onto a given mesh
+    sub = wf.desymmetrized_copy(allkpts=allk[[2, 7]], weights=np.array([0.5, 0.5]), symmops=ops)
+    assert sub.nwk == 2 and np.allclose(sub.kpts, allk[[2, 7]])

@@ -107,3 +107,43 @@ def test_realspace_projection_method(ga4):
     gp = np.load(os.path.join(G, "realspace_proj.npz"))
     got = pn.project_realspace_state(int(gp["band"]), S, R, gp["dim"])
     assert rel(got, gp["res"]) < TOL
+
+
+def test_desymmetrisation_restatement_vs_reference():
+    # expand_symm_wf (utils.c:829-1098); golden from the reference C (make_golden.py desymm).
+    # k-points, G lists and occupations are exact; coefficients carry complex64 phase factors (cexpf), so the
+    # numpy restatement may differ from the C value by float rounding.
+    c = cases.desymm_case()
+    g = np.load(os.path.join(G, "desymm.npz"), allow_pickle=True)
+    R = pn.Wavefunction.from_image(c["image"], c["kws"])
+    E = pn.expand_symm_wf(R, c["maps"], c["ops"], c["drs"], c["new_kws"], c["trs"])
+    assert np.array_equal(E.kpts, g["kpts"])
+    assert all(np.array_equal(E.Gs[k], g["gvecs"][k]) for k in range(E.nwk))
+    assert np.array_equal(E.occs, g["occ"])
+    for kap in range(E.nwk * E.nspin):
+        for b in range(E.nband):
+            assert rel(E.Cs[kap][b], g["coeffs"][kap][b]) < 5e-7
+    E.setup_projections(c["pps"], c["labels"], c["coords"], c["dim"], c["grid_encut"])
+    assert rel(np.asarray(E.P), g["proj"]) < 5e-7
+
+
+def test_symmetry_kpoint_generation_round_trip():
+    # host side of row f2 (symmetry.py:34-164): every generated k-point maps back to its source
+    from pawpyseed_b200 import symmetry
+    ops = [symmetry.SymmOp(m) for m in cases.cubic_point_group()]
+    assert len(ops) == 48
+    kpts = np.array([[0.25, 0.25, 0.25], [0.0, 0.25, 0.5], [0.0, 0.0, 0.0]])
+    allk, orig, opn, _, trs = symmetry.get_nosym_kpoints(kpts, symmops=ops)
+    assert len(allk) == len(orig) == len(opn) == len(trs)
+    # stars mod the lattice: 8 x (1/4,1/4,1/4), 12 x (0,1/4,1/2), Gamma; the half-zone filter of
+    # symmetry.py:58-67 keeps 4 + 9 + 1 of them (zone-boundary members are their own -k image)
+    assert len(allk) == 4 + 9 + 1
+    for q, k in enumerate(allk):
+        img = (-1.0 if trs[q] else 1.0) * ops[opn[q]].rotation_matrix @ kpts[orig[q]]
+        assert np.allclose((img - k + 0.5) % 1 - 0.5, 0, atol=1e-9) or np.allclose(np.abs((img - k) % 1), [0, 0, 0], atol=1e-9)
+    o2, n2, _, t2 = symmetry.get_kpt_mapping(allk, kpts, symmops=ops)
+    assert list(o2) == list(orig)
+    full, *_ = symmetry.get_nosym_kpoints(kpts, symmops=ops, fil_trsym=False)
+    assert len(full) == 8 + 12 + 1
+    with pytest.raises(Exception):
+        symmetry.get_kpt_mapping(np.array([[0.1, 0.2, 0.3]]), kpts, symmops=ops)
