@@ -102,6 +102,24 @@ void pawb200_compensation_terms(pawb200_c128 *overlap, int BAND_NUM, pawb200_psw
                                 const int *ref_labels, const double *ref_coords,
                                 const int *fft_grid, int spin_flip);
 
+/* ---- method "aug_recip" (projector.h:114-121, 130-137; projector.c:727-848, 965-1077), SURVEY 8 row f3.
+ * Same arguments as the _real pair.  The (phi - phit) augmentation of the unmatched sites is put on the FFT
+ * grid, transformed forward and kept as complex64 plane-wave coefficients in HBM; compensation_terms_recip
+ * accumulates (+=) <CA_R|C_S> + <C_R|CA_S> + O_M + O_N.  The plane-wave dot products accumulate in FP64
+ * (the reference: single-precision cblas_cdotc_sub, projector.c:1016, 1025). */
+void pawb200_overlap_setup_recip(pawb200_pswf_t *wf_R, pawb200_pswf_t *wf_S,
+                                 const int *labels_R, const int *labels_S,
+                                 const double *coords_R, const double *coords_S,
+                                 const int *N_R, const int *N_S, const int *N_RS_R,
+                                 const int *N_RS_S, int num_N_R, int num_N_S, int num_N_RS);
+void pawb200_compensation_terms_recip(pawb200_c128 *overlap, int BAND_NUM, pawb200_pswf_t *wf_S,
+                                      pawb200_pswf_t *wf_R, int num_M, int num_N_R, int num_N_S,
+                                      int num_N_RS, const int *M_R, const int *M_S,
+                                      const int *N_R, const int *N_S, const int *N_RS_R,
+                                      const int *N_RS_S, const int *proj_labels,
+                                      const double *proj_coords, const int *ref_labels,
+                                      const double *ref_coords, const int *fft_grid, int spin_flip);
+
 /* ---- real-space states / densities (density.h:15-67) --------------------------------- */
 void pawb200_realspace_state(pawb200_c128 *x, int BAND_NUM, int KPOINT_NUM, pawb200_pswf_t *wf,
                              const int *fftg, const int *labels, const double *coords);
@@ -156,7 +174,8 @@ void pawb200_reciprocal_offsite_wave_overlap(const double *dcoord, const double 
 /* ---- extensions (no reference counterpart; used by bench.py / batched callers) -------- */
 /* Whole PAW-corrected overlap block in one call: out[kappa][b_S][b_R] (complex128,
  * nkappa*nband_S*nband_R), i.e. row b_S of block kappa is what single_band_projection(b_S)
- * returns for that kappa.  kappa_lo/kappa_hi select a shard (multi-GPU: one rank per shard). */
+ * returns for that kappa.  kappa_lo/kappa_hi select a shard (multi-GPU: one rank per shard).
+ * pseudo_only: 0 = pseudo + aug_real augmentation, 1 = pseudo overlap only, 2 = pseudo + aug_recip. */
 void pawb200_projection_matrix(pawb200_c128 *out, pawb200_pswf_t *wf_S, pawb200_pswf_t *wf_R,
                                int num_M, int num_N_R, int num_N_S, int num_N_RS,
                                const int *M_R, const int *M_S, const int *N_R, const int *N_S,

@@ -758,12 +758,42 @@ def reciprocal_offsite_wave_overlap(dcoord, k1, f1, s1, k2, f2, s2, l1, m1, l2, 
 # --------------------------------------------------------------------------- #
 # Projector: overlap_setup_real + compensation_terms (projector.c:604-725, 850-963)
 # --------------------------------------------------------------------------- #
+def aug_freqs(wf: "Wavefunction", site_nums):
+    """get_aug_freqs + helper over all bands (projector.c:276-331, 420-453): the (phi - phit)
+    augmentation of the listed sites, weighted by the band's projector overlaps, summed on the FFT
+    grid with phase e^{-i k_cart.path}, forward-transformed and narrowed to complex64.
+    Returns list per kappa of complex64 [nband, npw]."""
+    st = setup_site(wf.ppots, site_nums, wf.labels, wf.coords, wf.lattice, wf.fftg, 1)
+    n = int(np.prod(wf.fftg))
+    out = []
+    for kap in range(wf.nwk * wf.nspin):
+        k = kap % wf.nwk
+        kc = frac_to_cartesian(np.asarray(wf.kpts[k], dtype=np.float64), wf.reclattice)
+        rows = []
+        for b in range(wf.nband):
+            x = np.zeros(n, dtype=np.complex128)
+            for site in st:
+                pth = site["paths"]
+                phase = np.exp(-1j * (kc[0] * pth[:, 0] + kc[1] * pth[:, 1] + kc[2] * pth[:, 2]))
+                p = wf.P[kap][b][wf.site_off[site["index"]]:wf.site_off[site["index"] + 1]]
+                np.add.at(x, site["indices"], (p @ site["values"]) * phase)
+            rows.append(fwd_fft3d(x, wf.Gs[k], wf.lattice, wf.fftg))
+        out.append(np.array(rows))
+    return out
+
+
 class Projector:
-    def __init__(self, wf: Wavefunction, basis: Wavefunction, site_cat):
+    def __init__(self, wf: Wavefunction, basis: Wavefunction, site_cat, recip=False):
         self.S, self.R = wf, basis
         self.cat = [list(map(int, x)) for x in site_cat]
         M_R, M_S, N_R, N_S, N_RS_R, N_RS_S = self.cat
         R, S = self.R, self.S
+        self.recip = recip
+        if recip:
+            # overlap_setup_recip parts 1-2 (projector.c:748-792); part 3 below is shared
+            self.CA_R = aug_freqs(R, N_R) if N_R else None
+            self.CA_S = aug_freqs(S, N_S) if N_S else None
+            N_R, N_S = [], []
         # part 1: <(phi-phit)_R sites | psi_S>  on S's lattice / grid      (:625-646)
         self.W_S = None
         if N_R:
@@ -834,10 +864,31 @@ class Projector:
             out[:, kap::NK] = t
         return out if parts else out.sum(axis=0)
 
+    def compensation_terms_recip(self, band_num, flip_spin=False, fp32_dots=False):
+        """projector.c:965-1077: <CA_R|C_S> + <C_R|CA_S> + O_M + O_N.  The reference accumulates the two
+        plane-wave dot products in single precision (cblas_cdotc_sub); default here is FP64."""
+        M_R, M_S, _, _, N_RS_R, N_RS_S = self.cat
+        R, S = self.R, self.S
+        NK = R.nwk * R.nspin
+        saved = self.cat
+        self.cat = [M_R, M_S, [], [], N_RS_R, N_RS_S]
+        out = self.compensation_terms(band_num, flip_spin)
+        self.cat = saved
+        acc = np.complex64 if fp32_dots else np.complex128
+        for kap in range(NK):
+            kr = kap
+            if R.nspin == 2 and flip_spin:
+                kr = kap + R.nwk if kap < R.nwk else kap - R.nwk
+            if self.CA_R is not None:
+                out[kap::NK] += (np.conj(self.CA_R[kr].astype(acc)) @ S.Cs[kap][band_num].astype(acc))
+            if self.CA_S is not None:
+                out[kap::NK] += (np.conj(R.Cs[kr].astype(acc)) @ self.CA_S[kap][band_num].astype(acc))
+        return out
+
     def single_band_projection(self, band_num, flip_spin=False):
-        """projector.py:210-223."""
-        return self.S.pseudoprojection(band_num, self.R, flip_spin) \
-            + self.compensation_terms(band_num, flip_spin)
+        """projector.py:210-236."""
+        comp = self.compensation_terms_recip if self.recip else self.compensation_terms
+        return self.S.pseudoprojection(band_num, self.R, flip_spin) + comp(band_num, flip_spin)
 
 
 def project_realspace_state(band_num, wf: Wavefunction, wf_R: Wavefunction, fftg):

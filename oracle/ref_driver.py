@@ -123,6 +123,8 @@ def lib():
         L.compensation_terms.argtypes = [c_dbl_p, C.c_int, P, P, C.c_int, C.c_int,
                                          C.c_int, C.c_int] + [c_int_p] * 6 + \
             [c_int_p, c_dbl_p, c_int_p, c_dbl_p, c_int_p, C.c_int]
+        L.overlap_setup_recip.argtypes = L.overlap_setup_real.argtypes
+        L.compensation_terms_recip.argtypes = L.compensation_terms.argtypes
         for name in ("realspace_state", "ncl_realspace_state"):
             getattr(L, name).argtypes = [c_dbl_p, C.c_int, C.c_int, P, c_int_p, c_int_p, c_dbl_p]
         L.remove_phase.argtypes = [c_dbl_p, C.c_int, P, c_int_p]
@@ -340,17 +342,20 @@ class RefWavefunction:
 class RefProjector:
     """Reference-side analogue of pawpyc.CProjector (pawpyc.pyx:634-702)."""
 
-    def __init__(self, wf: RefWavefunction, basis: RefWavefunction, site_cat):
+    def __init__(self, wf: RefWavefunction, basis: RefWavefunction, site_cat, recip=False):
         self.wf, self.basis = wf, basis
         self.cat = [np.ascontiguousarray(x, dtype=np.int32) for x in site_cat]
         M_R, M_S, N_R, N_S, N_RS_R, N_RS_S = self.cat
-        lib().overlap_setup_real(basis.ptr, wf.ptr, _ip(basis.nums), _ip(wf.nums),
+        self.recip = recip
+        setup = lib().overlap_setup_recip if recip else lib().overlap_setup_real
+        setup(basis.ptr, wf.ptr, _ip(basis.nums), _ip(wf.nums),
                                  _dp(basis.coords), _dp(wf.coords), _ip(N_R), _ip(N_S),
                                  _ip(N_RS_R), _ip(N_RS_S), len(N_R), len(N_S), len(N_RS_R))
 
     def add_augmentation_terms(self, res, band_num, flip_spin=False):
         M_R, M_S, N_R, N_S, N_RS_R, N_RS_S = self.cat
-        lib().compensation_terms(res.ctypes.data_as(c_dbl_p), int(band_num), self.wf.ptr,
+        fn = lib().compensation_terms_recip if self.recip else lib().compensation_terms
+        fn(res.ctypes.data_as(c_dbl_p), int(band_num), self.wf.ptr,
                                  self.basis.ptr, len(M_R), len(N_R), len(N_S), len(N_RS_R),
                                  _ip(M_R), _ip(M_S), _ip(N_R), _ip(N_S), _ip(N_RS_R), _ip(N_RS_S),
                                  _ip(self.wf.nums), _dp(self.wf.coords), _ip(self.basis.nums),

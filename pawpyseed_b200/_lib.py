@@ -66,6 +66,12 @@ _SIGS = {
     "pawb200_compensation_terms": (None, [c_dbl_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                           C.c_int, C.c_int, C.c_int] + [c_int_p] * 6 +
                                    [c_int_p, c_dbl_p, c_int_p, c_dbl_p, c_int_p, C.c_int]),
+    "pawb200_overlap_setup_recip": (None, [C.c_void_p, C.c_void_p, c_int_p, c_int_p, c_dbl_p,
+                                           c_dbl_p, c_int_p, c_int_p, c_int_p, c_int_p,
+                                           C.c_int, C.c_int, C.c_int]),
+    "pawb200_compensation_terms_recip": (None, [c_dbl_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                                C.c_int, C.c_int, C.c_int] + [c_int_p] * 6 +
+                                         [c_int_p, c_dbl_p, c_int_p, c_dbl_p, c_int_p, C.c_int]),
     "pawb200_realspace_state": (None, [c_dbl_p, C.c_int, C.c_int, C.c_void_p, c_int_p, c_int_p, c_dbl_p]),
     "pawb200_ncl_realspace_state": (None, [c_dbl_p, C.c_int, C.c_int, C.c_void_p, c_int_p, c_int_p, c_dbl_p]),
     "pawb200_remove_phase": (None, [c_dbl_p, C.c_int, C.c_void_p, c_int_p]),

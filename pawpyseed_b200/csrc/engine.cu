@@ -519,6 +519,7 @@ namespace { struct PrunedPlan; }
 struct HostMatrixCache {
   uint64_t other_id = 0, other_gen = 0, self_gen = 0;
   int flip = -1;
+  int recip = 0;
   size_t list_hash = 0;
   std::vector<cdouble> data;   // [NK][nbS][nbR]
   bool valid = false;
@@ -559,6 +560,8 @@ struct pawb200_pswf {
   long ldw = 0;
   int wp_num = 0;
   std::vector<int> wp_nlm;             // channels per wave-projection site
+  std::vector<DevBuf> CA;              // (f3) per kappa: float2 [nband][ldc] augmentation part in the PW basis
+  bool recip_setup = false;            // off-site data came from overlap_setup_recip
   // as wf_S: off-site data
   std::vector<std::vector<cdouble>> omega;
   std::vector<double> dcoords;
@@ -1369,7 +1372,7 @@ struct AugPlan {
   long K = 0, Kpad = 0;
 };
 
-AugPlan plan_aug(const pawb200_pswf* S, const pawb200_pswf* R, const SiteLists& L) {
+AugPlan plan_aug(const pawb200_pswf* S, const pawb200_pswf* R, const SiteLists& L, bool recip = false) {
   HostSection hs_("plan_aug");
   if (!S->has_projections || !R->has_projections)
     throw std::runtime_error("setup_projections has not been run on both wavefunctions");
@@ -1406,7 +1409,7 @@ AugPlan plan_aug(const pawb200_pswf* S, const pawb200_pswf* R, const SiteLists& 
     col += r.nlm;
   }
   // O_R  (:915-924): W_S (S bands on R's N_R sites) against P_R
-  if (!L.N_R.empty()) {
+  if (!recip && !L.N_R.empty()) {
     if (S->wp_num != (int)L.N_R.size()) throw std::runtime_error("overlap_setup_real was not run for these site lists");
     int woff = 0;
     for (size_t q = 0; q < L.N_R.size(); q++) {
@@ -1419,7 +1422,7 @@ AugPlan plan_aug(const pawb200_pswf* S, const pawb200_pswf* R, const SiteLists& 
     }
   }
   // O_S  (:929-938): W_R (R bands on S's N_S sites) against P_S
-  if (!L.N_S.empty()) {
+  if (!recip && !L.N_S.empty()) {
     if (R->wp_num != (int)L.N_S.size()) throw std::runtime_error("overlap_setup_real was not run for these site lists");
     int woff = 0;
     for (size_t q = 0; q < L.N_S.size(); q++) {
@@ -1495,8 +1498,27 @@ void aug_block(pawb200_pswf* S, pawb200_pswf* R, AugPlan& A, int kap, int flip, 
 }
 
 // Full block(s) to host: out[kap - lo][bS][bR]
+// (f3) plane-wave part of the aug_recip correction  [projector.c:1016-1027]: out += <CA_R|C_S> + <C_R|CA_S>
+void recip_block(pawb200_pswf* S, pawb200_pswf* R, const SiteLists& L, int kap, int flip, double2* out, long ldo) {
+  const int kr = flipped(R, kap, flip);
+  if (S->kp[kap].nplane != R->kp[kr].nplane)
+    throw std::runtime_error("plane-wave bases differ between the two wavefunctions at kappa " + std::to_string(kap));
+  if (!L.N_R.empty()) {
+    if (R->CA.empty() || !R->CA[kr].p) throw std::runtime_error("overlap_setup_recip was not run for these site lists (N_R)");
+    wait_coeffs(S, kap, 0, S->nband);
+    run_zgemm<float2>(S->C[kap].as<float2>(), S->ldc[kap], R->CA[kr].as<float2>(), R->ldc[kr], S->nband, R->nband,
+                      S->ldc[kap], out, ldo, true, ST_GEMM_AUG);
+  }
+  if (!L.N_S.empty()) {
+    if (S->CA.empty() || !S->CA[kap].p) throw std::runtime_error("overlap_setup_recip was not run for these site lists (N_S)");
+    wait_coeffs(R, kr, 0, R->nband);
+    run_zgemm<float2>(S->CA[kap].as<float2>(), S->ldc[kap], R->C[kr].as<float2>(), R->ldc[kr], S->nband, R->nband,
+                      S->ldc[kap], out, ldo, true, ST_GEMM_AUG);
+  }
+}
+
 void overlap_matrix(pawb200_pswf* S, pawb200_pswf* R, const SiteLists* L, int flip, int lo, int hi,
-                    bool pseudo, bool aug, cdouble* out) {
+                    bool pseudo, bool aug, cdouble* out, bool recip = false) {
   HostSection hs_("overlap_matrix");
   check_pair(S, R);
   const int nS = S->nband, nR = R->nband;
@@ -1505,7 +1527,7 @@ void overlap_matrix(pawb200_pswf* S, pawb200_pswf* R, const SiteLists* L, int fl
   DevBuf blk;
   if (!side) blk.alloc(blk_bytes);
   AugPlan A;
-  if (aug) A = plan_aug(S, R, *L);
+  if (aug) A = plan_aug(S, R, *L, recip);
   int use = 0;
   for (int kap = lo; kap < hi; kap++) {
     cdouble* dst = out + (size_t)(kap - lo) * nS * nR;
@@ -1527,6 +1549,7 @@ void overlap_matrix(pawb200_pswf* S, pawb200_pswf* R, const SiteLists* L, int fl
       CUDA_OK(cudaEventRecord(g_pblk_done[slot], st2));
       CUDA_OK(cudaStreamWaitEvent(g_stream, g_pblk_done[slot], 0));
       if (aug) aug_block(S, R, A, kap, flip, b, nR, true);
+      if (aug && recip) recip_block(S, R, *L, kap, flip, b, nR);
       ScopedStage tm(ST_D2H);
       CUDA_OK(cudaMemcpyAsync(dst, b, blk_bytes, cudaMemcpyDeviceToHost, g_stream));
       CUDA_OK(cudaEventRecord(g_pblk_free[slot], g_stream));
@@ -1535,6 +1558,7 @@ void overlap_matrix(pawb200_pswf* S, pawb200_pswf* R, const SiteLists* L, int fl
     b = blk.as<double2>();
     if (pseudo) pseudo_block(S, R, kap, flip, b, nR);
     if (aug) aug_block(S, R, A, kap, flip, b, nR, pseudo);
+    if (aug && recip) recip_block(S, R, *L, kap, flip, b, nR);
     ScopedStage tm(ST_D2H);
     CUDA_OK(cudaMemcpyAsync(dst, b, blk_bytes, cudaMemcpyDeviceToHost, g_stream));
   }
@@ -1807,7 +1831,9 @@ void pawb200_projection_matrix(pawb200_c128* out, pawb200_pswf_t* wf_S, pawb200_
   check_pair(wf_S, wf_R);
   if (kappa_lo < 0 || kappa_hi > wf_S->nkappa() || kappa_lo > kappa_hi) throw std::runtime_error("bad kappa range");
   SiteLists L = make_lists(num_M, num_N_R, num_N_S, num_N_RS, M_R, M_S, N_R, N_S, N_RS_R, N_RS_S);
-  overlap_matrix(wf_S, wf_R, &L, flip_spin, kappa_lo, kappa_hi, true, !pseudo_only, (cdouble*)out);
+  // pseudo_only: 0 = pseudo + augmentation (aug_real), 1 = pseudo only, 2 = pseudo + aug_recip augmentation
+  overlap_matrix(wf_S, wf_R, &L, flip_spin, kappa_lo, kappa_hi, true, pseudo_only != 1, (cdouble*)out,
+                 pseudo_only == 2);
   API_END_VOID
 }
 
@@ -1830,6 +1856,108 @@ void pawb200_pseudoprojection(pawb200_c128* projections, pawb200_pswf_t* wf_ref,
   for (int k = 0; k < NK; k++)
     for (int b = 0; b < nR; b++) out[(size_t)b * NK + k] = c.data[((size_t)k * nS + BAND_NUM) * nR + b];
   API_END_VOID
+}
+
+// part 3 of overlap_setup_real / _recip (projector.c:682-719, 799-841): off-site partial-wave overlaps, host
+// side (O(pairs * channels^2) radial integrals)
+void setup_offsite(pawb200_pswf* wf_R, pawb200_pswf* wf_S, const int* labels_R, const int* labels_S,
+                   const double* coords_R, const double* coords_S, const int* N_RS_R, const int* N_RS_S,
+                   int num_N_RS) {
+  const auto& elsR = wf_R->pps->list.el;
+  const auto& elsS = wf_S->pps->list.el;
+  wf_S->omega.assign(num_N_RS, {});
+  wf_S->dcoords.assign(3 * (size_t)num_N_RS, 0.0);
+  wf_S->omega_n1.assign(num_N_RS, 0);
+  wf_S->omega_n2.assign(num_N_RS, 0);
+#pragma omp parallel for schedule(dynamic)
+  for (int i = 0; i < num_N_RS; i++) {
+    const int s1 = N_RS_R[i], s2 = N_RS_S[i];
+    const Element& p1 = elsR[labels_R[s1]];
+    const Element& p2 = elsS[labels_S[s2]];
+    double R = 0;
+    double* d = wf_S->dcoords.data() + 3 * i;
+    min_image_path(coords_S + 3 * s2, coords_R + 3 * s1, wf_R->lattice, d, &R);
+    auto& om = wf_S->omega[i];
+    om.resize((size_t)p1.total_projs * p2.total_projs);
+    for (int a = 0; a < p1.total_projs; a++)
+      for (int b = 0; b < p2.total_projs; b++) {
+        const Channel &ca = p1.chan[a], &cb = p2.chan[b];
+        const RadialFunc &fa = p1.funcs[ca.n], &fb = p2.funcs[cb.n];
+        om[(size_t)a * p2.total_projs + b] = std::conj(offsite_overlap_recip(
+            d, p1.kwave_grid.data(), fa.kwave.data(), fa.kwave_s, p1.wave_gridsize, p2.kwave_grid.data(),
+            fb.kwave.data(), fb.kwave_s, p2.wave_gridsize, ca.l, ca.m, cb.l, cb.m));
+      }
+    wf_S->omega_n1[i] = p1.total_projs;
+    wf_S->omega_n2[i] = p2.total_projs;
+  }
+}
+
+// (f3) get_aug_freqs for every band of `wf` (projector.c:420-453): the (phi - phit) augmentation of the listed
+// sites is accumulated on the FFT grid, transformed forward and gathered to complex64 plane-wave coefficients
+// CA[kappa][band][npw] stored like C (box order).  Unlike the reference, which keeps a band's CAs from an
+// earlier site list (the `CAs != NULL` early return at :424), the result is always recomputed.
+void compute_aug_freqs(pawb200_pswf* wf, const int* site_list, int nlist, const int* labels, const double* coords) {
+  HostSection hs_("compute_aug_freqs");
+  const int* fftg = wf->fftg;
+  const long ngrid = (long)fftg[0] * fftg[1] * fftg[2];
+  auto T = build_site_tables(wf->pps->list.el, site_list, nlist, labels, coords, wf->lattice, fftg, 1, false);
+  std::vector<int> full_off(nlist);
+  int maxpts = 0, maxlm = 0;
+  for (int s = 0; s < nlist; s++) {
+    if (site_list[s] < 0 || site_list[s] >= wf->num_sites) throw std::runtime_error("site index out of range");
+    const SiteDev& full = wf->proj_sites->host[site_list[s]];
+    if (full.nlm != T->host[s].nlm) throw std::runtime_error("labels differ from those given to setup_projections");
+    full_off[s] = full.lm_off;
+    maxpts = std::max(maxpts, T->host[s].npts);
+    maxlm = std::max(maxlm, T->host[s].nlm);
+  }
+  DevBuf doff = upload(full_off);
+  wf->CA.clear();
+  wf->CA.resize(wf->nkappa());
+  const double scale = std::pow(determinant3(wf->lattice), 0.5) / fftg[0] / fftg[1] / fftg[2];   // linalg.c:64-65
+  constexpr int NBMAX = 32;   // bands per augment launch (shared-memory P tile)
+  const long budget = (long)(fft_budget_bytes() / (ngrid * sizeof(double2)));
+  const int batch = (int)std::max<long>(1, std::min<long>(wf->nband, budget));
+  for (int kap = 0; kap < wf->nkappa(); kap++) {
+    if (!wf->resident[kap]) continue;
+    const int npw = wf->kp[kap].nplane;
+    std::vector<int> fwd;
+    build_inverse_map(wf, kap, fftg, &fwd);
+    std::vector<int> gsorted(npw);
+    for (int j = 0; j < npw; j++) gsorted[j] = fwd[wf->kp[kap].perm[j]];
+    DevBuf dg = upload(gsorted);
+    wf->CA[kap].alloc((size_t)wf->nband * wf->ldc[kap] * sizeof(float2));
+    wf->CA[kap].zero((size_t)wf->nband * wf->ldc[kap] * sizeof(float2));
+    double kc[3] = {wf->kp[kap].k[0], wf->kp[kap].k[1], wf->kp[kap].k[2]};
+    frac_to_cart(kc, wf->reclattice);                                           // projector.c:288-292
+    for (int b0 = 0; b0 < wf->nband; b0 += batch) {
+      const int nb = std::min(batch, wf->nband - b0);
+      g_grid.ensure((size_t)nb * ngrid * sizeof(double2));
+      double2* x = g_grid.as<double2>();
+      {
+        ScopedStage tm(ST_AUGMENT);
+        CUDA_OK(cudaMemsetAsync(x, 0, (size_t)nb * ngrid * sizeof(double2), g_stream));
+        for (int c0 = 0; c0 < nb && T->total_pts; c0 += NBMAX) {
+          const int nc = std::min(NBMAX, nb - c0);
+          dim3 grid(std::max(1, (maxpts + 255) / 256), nlist);
+          aug_freq_add_kernel<<<grid, 256, sizeof(double2) * nc * maxlm, g_stream>>>(
+              T->sites.as<SiteDev>(), doff.as<int>(), T->idx.as<int>(), T->path.as<double>(), T->total_pts,
+              T->table.as<double2>(), wf->P[kap].as<double2>() + (long)(b0 + c0) * wf->ldp, wf->ldp, nc,
+              x + (long)c0 * ngrid, ngrid, kc[0], kc[1], kc[2]);
+          count_launch();
+          check_launch();
+        }
+      }
+      launch_fft(x, fftg, nb, CUFFT_FORWARD);
+      ScopedStage tm(ST_SCATTER);
+      dim3 grid((npw + 255) / 256, nb);
+      gather_pw_batch_kernel<<<grid, 256, 0, g_stream>>>(x, ngrid, dg.as<int>(),
+                                                         wf->CA[kap].as<float2>() + (long)b0 * wf->ldc[kap],
+                                                         wf->ldc[kap], npw, scale);
+      count_launch();
+      check_launch();
+    }
+  }
 }
 
 void pawb200_overlap_setup_real(pawb200_pswf_t* wf_R, pawb200_pswf_t* wf_S, const int* labels_R,
@@ -1861,32 +1989,9 @@ void pawb200_overlap_setup_real(pawb200_pswf_t* wf_R, pawb200_pswf_t* wf_S, cons
     for (auto& sd : T->host) wf_R->wp_nlm.push_back(sd.nlm);
     project_all_bands(wf_R, *T, wf_R->fftg, wf_R->W, wf_R->ldw, false);
   }
-  // part 3 (:682-719): off-site partial-wave overlaps, host side (O(pairs * channels^2) radial integrals)
-  wf_S->omega.assign(num_N_RS, {});
-  wf_S->dcoords.assign(3 * (size_t)num_N_RS, 0.0);
-  wf_S->omega_n1.assign(num_N_RS, 0);
-  wf_S->omega_n2.assign(num_N_RS, 0);
-#pragma omp parallel for schedule(dynamic)
-  for (int i = 0; i < num_N_RS; i++) {
-    const int s1 = N_RS_R[i], s2 = N_RS_S[i];
-    const Element& p1 = elsR[labels_R[s1]];
-    const Element& p2 = elsS[labels_S[s2]];
-    double R = 0;
-    double* d = wf_S->dcoords.data() + 3 * i;
-    min_image_path(coords_S + 3 * s2, coords_R + 3 * s1, wf_R->lattice, d, &R);
-    auto& om = wf_S->omega[i];
-    om.resize((size_t)p1.total_projs * p2.total_projs);
-    for (int a = 0; a < p1.total_projs; a++)
-      for (int b = 0; b < p2.total_projs; b++) {
-        const Channel &ca = p1.chan[a], &cb = p2.chan[b];
-        const RadialFunc &fa = p1.funcs[ca.n], &fb = p2.funcs[cb.n];
-        om[(size_t)a * p2.total_projs + b] = std::conj(offsite_overlap_recip(
-            d, p1.kwave_grid.data(), fa.kwave.data(), fa.kwave_s, p1.wave_gridsize, p2.kwave_grid.data(),
-            fb.kwave.data(), fb.kwave_s, p2.wave_gridsize, ca.l, ca.m, cb.l, cb.m));
-      }
-    wf_S->omega_n1[i] = p1.total_projs;
-    wf_S->omega_n2[i] = p2.total_projs;
-  }
+  setup_offsite(wf_R, wf_S, labels_R, labels_S, coords_R, coords_S, N_RS_R, N_RS_S, num_N_RS);
+  wf_R->recip_setup = wf_S->recip_setup = false;
+  wf_R->CA.clear(); wf_S->CA.clear();
   wf_S->overlap_partner = wf_R->id;
   API_END_VOID
 }
@@ -1904,11 +2009,62 @@ void pawb200_compensation_terms(pawb200_c128* overlap, int BAND_NUM, pawb200_psw
   const int NK = wf_R->nkappa(), nS = wf_S->nband, nR = wf_R->nband;
   const size_t lh = L.hash();
   if (!c.valid || c.other_id != wf_R->id || c.other_gen != wf_R->gen || c.self_gen != wf_S->gen ||
-      c.flip != (spin_flip ? 1 : 0) || c.list_hash != lh) {
+      c.flip != (spin_flip ? 1 : 0) || c.list_hash != lh || c.recip != 0) {
     c.data.assign((size_t)NK * nS * nR, cdouble(0, 0));
     overlap_matrix(wf_S, wf_R, &L, spin_flip, 0, NK, false, true, c.data.data());
     c.other_id = wf_R->id; c.other_gen = wf_R->gen; c.self_gen = wf_S->gen;
-    c.flip = spin_flip ? 1 : 0; c.list_hash = lh; c.valid = true;
+    c.flip = spin_flip ? 1 : 0; c.list_hash = lh; c.recip = 0; c.valid = true;
+  }
+  cdouble* out = (cdouble*)overlap;
+  for (int k = 0; k < NK; k++)
+    for (int b = 0; b < nR; b++) out[(size_t)b * NK + k] += c.data[((size_t)k * nS + BAND_NUM) * nR + b];
+  API_END_VOID
+}
+
+// ---- (f3) method "aug_recip": projector.h:114-121, 130-137; projector.c:727-848, 965-1077 -------------------
+void pawb200_overlap_setup_recip(pawb200_pswf_t* wf_R, pawb200_pswf_t* wf_S, const int* labels_R,
+                                 const int* labels_S, const double* coords_R, const double* coords_S,
+                                 const int* N_R, const int* N_S, const int* N_RS_R, const int* N_RS_S,
+                                 int num_N_R, int num_N_S, int num_N_RS) {
+  API_BEGIN
+  HostSection hs_("overlap_setup_recip");
+  require_device();
+  check_pair(wf_S, wf_R);
+  if (!wf_R->has_projections || !wf_S->has_projections) throw std::runtime_error("setup_projections has not been run");
+  wf_R->gen++;
+  wf_S->gen++;
+  wf_R->aug_cache.valid = wf_S->aug_cache.valid = false;
+  wf_R->W.clear(); wf_S->W.clear();
+  wf_R->wp_nlm.clear(); wf_S->wp_nlm.clear();
+  wf_R->wp_num = num_N_S; wf_S->wp_num = num_N_R;    // projector.c:735-736
+  wf_R->CA.clear(); wf_S->CA.clear();
+  if (num_N_R > 0) compute_aug_freqs(wf_R, N_R, num_N_R, labels_R, coords_R);   // part 1 (:748-767)
+  if (num_N_S > 0) compute_aug_freqs(wf_S, N_S, num_N_S, labels_S, coords_S);   // part 2 (:770-792)
+  setup_offsite(wf_R, wf_S, labels_R, labels_S, coords_R, coords_S, N_RS_R, N_RS_S, num_N_RS);
+  wf_R->recip_setup = wf_S->recip_setup = true;
+  wf_S->overlap_partner = wf_R->id;
+  API_END_VOID
+}
+
+void pawb200_compensation_terms_recip(pawb200_c128* overlap, int BAND_NUM, pawb200_pswf_t* wf_S,
+                                      pawb200_pswf_t* wf_R, int num_M, int num_N_R, int num_N_S, int num_N_RS,
+                                      const int* M_R, const int* M_S, const int* N_R, const int* N_S,
+                                      const int* N_RS_R, const int* N_RS_S, const int*, const double*, const int*,
+                                      const double*, const int*, int spin_flip) {
+  API_BEGIN
+  require_device();
+  check_pair(wf_S, wf_R);
+  if (BAND_NUM < 0 || BAND_NUM >= wf_S->nband) throw std::runtime_error("band index out of range");
+  SiteLists L = make_lists(num_M, num_N_R, num_N_S, num_N_RS, M_R, M_S, N_R, N_S, N_RS_R, N_RS_S);
+  HostMatrixCache& c = wf_S->aug_cache;
+  const int NK = wf_R->nkappa(), nS = wf_S->nband, nR = wf_R->nband;
+  const size_t lh = L.hash();
+  if (!c.valid || c.other_id != wf_R->id || c.other_gen != wf_R->gen || c.self_gen != wf_S->gen ||
+      c.flip != (spin_flip ? 1 : 0) || c.list_hash != lh || c.recip != 1) {
+    c.data.assign((size_t)NK * nS * nR, cdouble(0, 0));
+    overlap_matrix(wf_S, wf_R, &L, spin_flip, 0, NK, false, true, c.data.data(), true);
+    c.other_id = wf_R->id; c.other_gen = wf_R->gen; c.self_gen = wf_S->gen;
+    c.flip = spin_flip ? 1 : 0; c.list_hash = lh; c.recip = 1; c.valid = true;
   }
   cdouble* out = (cdouble*)overlap;
   for (int k = 0; k < NK; k++)

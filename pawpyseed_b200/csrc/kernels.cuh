@@ -555,6 +555,51 @@ augment_add_kernel(const SiteDev* __restrict__ sites, const int* __restrict__ id
   }
 }
 
+// (f3) augmentation part of a band on the FFT grid  [projector.c:276-331, get_aug_freqs_helper]:
+//   x[b][idx[pt]] += e^{-i k_cart.path[pt]} * sum_ch T[ch][pt] * P[b][full_off[site] + ch]
+// T = filtered (phi - phit) tables of the listed sites, P = the band's projector overlaps (full channel axis).
+__global__ void __launch_bounds__(256)
+aug_freq_add_kernel(const SiteDev* __restrict__ sites, const int* __restrict__ full_off,
+                    const int* __restrict__ idx, const double* __restrict__ path, long path_ld,
+                    const double2* __restrict__ table, const double2* __restrict__ P, long ldp, int nbox,
+                    double2* __restrict__ x, long ngrid, double kx, double ky, double kz) {
+  const SiteDev sd = sites[blockIdx.y];
+  const int off = full_off[blockIdx.y];
+  extern __shared__ double2 sP[];    // [nbox][nlm]
+  for (int e = threadIdx.x; e < nbox * sd.nlm; e += blockDim.x)
+    sP[e] = P[(long)(e / sd.nlm) * ldp + off + (e % sd.nlm)];
+  __syncthreads();
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < sd.npts; p += gridDim.x * blockDim.x) {
+    const long q = sd.pt_off + p;
+    const double kr = -(kx * path[q] + ky * path[path_ld + q] + kz * path[2 * path_ld + q]);
+    double s, c;
+    sincos(kr, &s, &c);
+    const int g = idx[q];
+    for (int b = 0; b < nbox; b++) {
+      double2 acc = make_double2(0, 0);
+      for (int ch = 0; ch < sd.nlm; ch++) {
+        const double2 t = cmul(sP[b * sd.nlm + ch], table[sd.tab_off + (long)ch * sd.npts_pad + p]);
+        acc.x += t.x;
+        acc.y += t.y;
+      }
+      double* dst = reinterpret_cast<double*>(x + (long)b * ngrid + g);
+      atomicAdd(dst, acc.x * c - acc.y * s);
+      atomicAdd(dst + 1, acc.x * s + acc.y * c);
+    }
+  }
+}
+
+// batched (a3): Cout[b][w] = (complex64) scale * x[b][gidx[w]]
+__global__ void __launch_bounds__(256)
+gather_pw_batch_kernel(const double2* __restrict__ x, long ngrid, const int* __restrict__ gidx,
+                       float2* __restrict__ Cout, long ldc, int npw, double scale) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= npw) return;
+  const int g = gidx[w];
+  const double2 v = x[(long)blockIdx.y * ngrid + g];
+  Cout[(long)blockIdx.y * ldc + w] = make_float2((float)(v.x * scale), (float)(v.y * scale));
+}
+
 // (a13) density accumulation  [density.c:170-173, 193-196]:  rho[g] += sum_box w[box] |x_box[g]|^2
 __global__ void __launch_bounds__(256)
 density_accum_kernel(const double2* __restrict__ x, long ngrid, int nbox,

@@ -455,20 +455,21 @@ class CNCLWavefunction(CWavefunction):
 
 
 class CProjector:
-    """pawpyc.pyx:634-736 (aug_real / pseudo paths)."""
+    """pawpyc.pyx:634-736."""
 
     def __init__(self, wf, basis):
         self.wf = wf
         self.basis = basis
 
     def _setup_overlap(self, site_cat, recip):
-        if recip:
-            raise PAWpyError("method 'aug_recip' is not part of the B200 hot path (SURVEY 8f3); use 'aug_real'")
+        """pawpyc.pyx:642-683."""
         names = ("M_R", "M_S", "N_R", "N_S", "N_RS_R", "N_RS_S")
         for n, lst in zip(names, site_cat):
             setattr(self, n, np.array(lst, dtype=np.int32, order="C"))
             setattr(self, "num_" + n, len(lst))
-        _lib.lib().pawb200_overlap_setup_real(
+        self._recip = bool(recip)
+        fn = _lib.lib().pawb200_overlap_setup_recip if recip else _lib.lib().pawb200_overlap_setup_real
+        fn(
             self.basis.wf_ptr, self.wf.wf_ptr, ip(self.basis.nums), ip(self.wf.nums),
             dp(self.basis.coords), dp(self.wf.coords), ip(self.N_R), ip(self.N_S), ip(self.N_RS_R),
             ip(self.N_RS_S), self.num_N_R, self.num_N_S, self.num_N_RS_R)
@@ -486,7 +487,16 @@ class CProjector:
         check()
 
     def _projection_recip(self, res, band_num, flip_spin):
-        raise PAWpyError("method 'aug_recip' is not part of the B200 hot path (SURVEY 8f3)")
+        """pawpyc.pyx:704-721."""
+        if res.dtype != np.complex128 or not res.flags["C_CONTIGUOUS"]:
+            raise ValueError("res must be a contiguous complex128 array")
+        _lib.lib().pawb200_compensation_terms_recip(
+            res.ctypes.data_as(_lib.c_dbl_p), int(band_num), self.wf.wf_ptr, self.basis.wf_ptr,
+            self.num_M_R, self.num_N_R, self.num_N_S, self.num_N_RS_R, ip(self.M_R), ip(self.M_S),
+            ip(self.N_R), ip(self.N_S), ip(self.N_RS_R), ip(self.N_RS_S), ip(self.wf.nums),
+            dp(self.wf.coords), ip(self.basis.nums), dp(self.basis.coords), ip(self.wf.dimv),
+            int(bool(flip_spin)))
+        check()
 
     def _realspace_projection(self, band_num, dim):
         """pawpyc.pyx:723-736 -> project_realspace_state (density.c:205-230)."""
@@ -511,6 +521,7 @@ class CProjector:
         _lib.lib().pawb200_projection_matrix(
             out.ctypes.data_as(_lib.c_dbl_p), self.wf.wf_ptr, self.basis.wf_ptr, len(lists[0]),
             len(lists[2]), len(lists[3]), len(lists[4]), *[ip(a) for a in lists],
-            int(bool(flip_spin)), int(lo), int(hi), int(bool(pseudo_only) or not have))
+            int(bool(flip_spin)), int(lo), int(hi),
+            1 if (pseudo_only or not have) else (2 if getattr(self, "_recip", False) else 0))
         check()
         return out

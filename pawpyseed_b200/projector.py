@@ -24,14 +24,25 @@ class Projector(pawpyc.CProjector):
         elif self.method == "realspace":
             self._single_band_projection = self._single_band_projection_realspace
         elif self.method == "aug_recip":
-            raise PAWpyError("method 'aug_recip' is outside the B200 hot path (SURVEY 8f3); use 'aug_real', "
-                             "'realspace' or 'pseudo'")
+            self._single_band_projection = self._single_band_projection_aug_recip
         else:
             raise PAWpyError("method not recognized for Projector")
         if wf.ncl or basis.ncl:
             raise PAWpyError("Projection not supported for noncollinear case!")
-        if unsym_basis or unsym_wf:
-            raise PAWpyError("desymmetrisation is outside the B200 hot path (SURVEY 8f2)")
+        # projector.py:77-95: bring both onto one unreduced mesh (GPU remap, pawb200_expand_symm_wf)
+        if unsym_basis and unsym_wf:
+            basis = basis.desymmetrized_copy()
+            wf = wf.desymmetrized_copy(basis.kpts, basis.kws)
+        elif unsym_wf:
+            if basis.kpts.shape[0] < wf.kpts.shape[0]:
+                raise PAWpyError("Basis doesn't have enough kpoints, needs to be desymmetrized!")
+            wf = wf.desymmetrized_copy(basis.kpts, basis.kws)
+        elif unsym_basis:
+            if wf.kpts.shape[0] < basis.kpts.shape[0]:
+                raise PAWpyError("Defect doesn't have enough kpoints, needs to be desymmetrized!")
+            basis = basis.desymmetrized_copy(wf.kpts, wf.kws)
+        if basis.kpts.shape != wf.kpts.shape:
+            raise PAWpyError("k-point grids for projection are not matched.")
         if np.linalg.norm(basis.kpts - wf.kpts) > 1e-10:
             raise PAWpyError("k-point grids for projection are not matched.")
         if np.linalg.norm(basis.kws - wf.kws) > 1e-10:
@@ -80,7 +91,9 @@ class Projector(pawpyc.CProjector):
             site_cat = [M_R, M_S, N_R, N_S, N_RS_R, N_RS_S]
         self.site_cat = [list(x) for x in site_cat]
         start = time.monotonic()
-        self._setup_overlap(self.site_cat, False)
+        if self.method not in ("aug_recip", "aug_real"):
+            raise PAWpyError("method must be aug type for setup_overlap call")
+        self._setup_overlap(self.site_cat, self.method == "aug_recip")
         Timer.overlap_time(time.monotonic() - start)
 
     def _single_band_projection_pseudo(self, band_num):
@@ -98,6 +111,13 @@ class Projector(pawpyc.CProjector):
         start = time.monotonic()
         self._add_augmentation_terms(res, band_num, flip_spin)
         Timer.augmentation_time(time.monotonic() - start)
+        return res
+
+    def _single_band_projection_aug_recip(self, band_num, flip_spin=False):
+        """projector.py:225-236: augmentation carried through the plane-wave basis (low-pass filtered partial
+        waves -> FFT grid -> forward FFT), then plane-wave dot products."""
+        res = self.wf.pseudoprojection(band_num, self.basis, flip_spin)
+        self._projection_recip(res, band_num, flip_spin)
         return res
 
     def single_band_projection(self, band_num, **kwargs):

@@ -1,7 +1,7 @@
 """Generates tests/golden/*.npz from the UNMODIFIED reference C (oracle/_ref/libpawpy_ref.so).
 
 Run in the build container (needs /root/reference for the bundled WAVECARs):
-    python tests/golden/make_golden.py [base] [realspace_proj] [volumetric] [desymm]    (default: all)
+    python tests/golden/make_golden.py [base] [realspace_proj] [volumetric] [desymm] [aug_recip]    (default: all)
 Inputs are (a) the first bands of the reference's own fixtures test_files/WAVECAR,
 WAVECAR2.gz and noncollinear/WAVECAR re-packed into small WAVECAR images, and (b) seeded
 synthetic cells from tests/cases.py.  Every stored output comes from the reference library
@@ -166,8 +166,26 @@ def make_desymm():
     R.free()
 
 
+def make_recip():
+    """method "aug_recip" (overlap_setup_recip + compensation_terms_recip, projector.c:727-848, 965-1077) on the
+    synthetic two-element pair of synth_gan.npz: all three unmatched-site mechanisms (N_R, N_S, N_RS)."""
+    cR, cS = cases.small_case(seed=7, nband=6), cases.small_case(seed=11, nband=6, perturb=0.03)
+    cat = [[0, 1], [0, 1], [2, 3], [2, 3], [2, 3, 2], [2, 3, 3]]
+    R, S = rd.RefWavefunction(cR["image"], cR["kws"]), rd.RefWavefunction(cS["image"], cS["kws"])
+    for w, c in ((R, cR), (S, cS)):
+        w.setup_projections(c["pps"], c["labels"], c["coords"], cR["dim"], cR["grid_encut"])
+    pr = rd.RefProjector(S, R, cat, recip=True)
+    NK = R.nwk * R.nspin
+    out = {}
+    for flip in (0, 1):
+        out["aug_f%d" % flip] = np.array([pr.add_augmentation_terms(np.zeros(R.nband * NK, complex), b, bool(flip))
+                                          for b in range(S.nband)])
+    R.free(); S.free()
+    np.savez_compressed(os.path.join(HERE, "aug_recip.npz"), cat=np.array(cat, dtype=object), **out)
+
+
 MAKERS = {"base": make_base, "realspace_proj": make_realspace_proj, "volumetric": make_volumetric,
-          "desymm": make_desymm}
+          "desymm": make_desymm, "aug_recip": make_recip}
 
 
 def main():

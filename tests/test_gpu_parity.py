@@ -275,3 +275,58 @@ def test_desymmetrisation_vs_reference_and_oracle():
                                         _lib.dp(pw.weights), _lib.ip(c["trs"]))
     with pytest.raises(_lib.PAWpyError):
         _lib.check()
+
+
+def test_aug_recip_vs_reference_and_oracle(gan):
+    # overlap_setup_recip + compensation_terms_recip (projector.c:727-848, 965-1077).
+    # The reference stores CAs as complex64 and accumulates both dot products in single precision; the GPU
+    # keeps complex64 storage (same layout as the plane-wave coefficients) and accumulates in FP64.  Bars:
+    # FP32 round-off of the correction against the reference C, 1e-7 of it against the FP64-accumulating oracle
+    # (the only difference left is which way a CA coefficient rounds to float).
+    g = np.load(os.path.join(G, "aug_recip.npz"), allow_pickle=True)
+    cat = [list(x) for x in g["cat"]]
+    cR, cS = cases.small_case(seed=7, nband=6), cases.small_case(seed=11, nband=6, perturb=0.03)
+    R, S = from_case(cR), from_case(cS)
+    oR, oS = oracle_wf(cR), oracle_wf(cS)
+    pr = pawpyc.CProjector(S, R)
+    pr._setup_overlap(cat, True)
+    opr = pn.Projector(oS, oR, cat, recip=True)
+    scale = np.abs(g["aug_f0"]).max()
+    for flip in (0, 1):
+        for b in range(6):
+            res = np.zeros(6 * 4, complex)
+            pr._projection_recip(res, b, bool(flip))
+            assert np.abs(res - g["aug_f%d" % flip][b]).max() < 5e-6 * scale
+            assert np.abs(res - opr.compensation_terms_recip(b, bool(flip))).max() < 1e-7 * scale
+        # batched call: pseudo + recip augmentation for every band pair
+        want = np.array([opr.single_band_projection(b, bool(flip)) for b in range(6)]).reshape(6, 6, 4)
+        got = pr._projection_matrix(bool(flip))
+        assert np.abs(got - want.transpose(2, 0, 1)).max() < 1e-7 * scale
+    # switching the same pair back to the real-space method drops the recip state
+    pr2 = pawpyc.CProjector(S, R)
+    pr2._setup_overlap(cat, False)
+    g2 = np.load(os.path.join(G, "synth_gan.npz"), allow_pickle=True)
+    res = np.zeros(6 * 4, complex)
+    pr2._add_augmentation_terms(res, 0, False)
+    assert rel(res, g2["aug_c0_f0"][0]) < TOL
+    with pytest.raises(_lib.PAWpyError):
+        pr._projection_recip(np.zeros(24, complex), 0, False)      # recip data was replaced by the real setup
+
+
+@pytest.mark.parametrize("cat", [
+    [[0], [0], [1, 2, 3], [], [], []],                                   # N_R only
+    [[0, 1, 2], [0, 1, 2], [], [3], [], []],                             # N_S only
+    [[], [], [0, 1, 2, 3], [0, 1, 2, 3], [0, 1, 2, 3], [0, 1, 2, 3]],    # everything unmatched
+])
+def test_aug_recip_site_categories_vs_oracle(gan, cat):
+    cR, cS, R, S, oR, oS = gan
+    pr = pawpyc.CProjector(S, R)
+    pr._setup_overlap(cat, True)
+    opr = pn.Projector(oS, oR, cat, recip=True)
+    nb = cR["nband"]
+    want = np.array([opr.compensation_terms_recip(b, False) for b in range(nb)])
+    scale = max(np.abs(want).max(), 1e-30)
+    for b in (0, nb - 1):
+        res = np.zeros(nb * 4, complex)
+        pr._projection_recip(res, b, False)
+        assert np.abs(res - want[b]).max() < 1e-7 * scale

@@ -87,7 +87,7 @@ def test_pseudo_method_and_errors(pair):
     with pytest.raises(PAWpyError):
         Projector(wf, basis, method="nonsense")
     with pytest.raises(PAWpyError):
-        Projector(wf, basis, method="aug_recip")                # outside the hot path, named in the error
+        pr.setup_overlap()                                      # projector.py:180-181: aug methods only
 
 
 def test_wavefunction_realspace_and_files(pair, tmp_path):
@@ -149,3 +149,16 @@ def test_desymmetrized_copy_matches_oracle():
     # mapping onto a given mesh
     sub = wf.desymmetrized_copy(allkpts=allk[[2, 7]], weights=np.array([0.5, 0.5]), symmops=ops)
     assert sub.nwk == 2 and np.allclose(sub.kpts, allk[[2, 7]])
+
+
+def test_projector_method_aug_recip(pair):
+    # projector.py:225-236 through the public class; site lists come from make_site_lists
+    cR, cS, basis, wf = pair[:4]
+    pr = Projector(wf, basis, method="aug_recip")
+    oR, oS = oracle(cR), oracle(cS)
+    opr = pn.Projector(oS, oR, pr.site_cat, recip=True)
+    want = opr.single_band_projection(2)
+    got = pr.single_band_projection(2)
+    assert np.abs(got - want).max() < 1e-7 * np.abs(want).max()
+    M = pr.projection_matrix()
+    assert np.abs(M[:, 2, :].T.reshape(-1) - got).max() < 1e-12

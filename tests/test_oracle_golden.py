@@ -147,3 +147,20 @@ def test_symmetry_kpoint_generation_round_trip():
     assert len(full) == 8 + 12 + 1
     with pytest.raises(Exception):
         symmetry.get_kpt_mapping(np.array([[0.1, 0.2, 0.3]]), kpts, symmops=ops)
+
+
+def test_aug_recip_restatement_vs_reference():
+    # overlap_setup_recip + compensation_terms_recip; golden from the reference C.
+    # The reference keeps the augmentation coefficients and both dot products in single precision, so the
+    # comparison is absolute at FP32 round-off of the (small) correction.
+    g = np.load(os.path.join(G, "aug_recip.npz"), allow_pickle=True)
+    cR, cS = cases.small_case(seed=7, nband=6), cases.small_case(seed=11, nband=6, perturb=0.03)
+    R, S = pn.Wavefunction.from_image(cR["image"], cR["kws"]), pn.Wavefunction.from_image(cS["image"], cS["kws"])
+    for w, c in ((R, cR), (S, cS)):
+        w.setup_projections(c["pps"], c["labels"], c["coords"], cR["dim"], cR["grid_encut"])
+    pr = pn.Projector(S, R, list(g["cat"]), recip=True)
+    scale = np.abs(g["aug_f0"]).max()
+    for b in (0, 5):
+        for flip in (0, 1):
+            got = pr.compensation_terms_recip(b, bool(flip))
+            assert np.abs(got - g["aug_f%d" % flip][b]).max() < 5e-6 * scale
