@@ -538,6 +538,8 @@ struct pawb200_pswf {
   std::vector<double> weight;          // per kappa
   std::vector<DevBuf> C;               // per kappa: float2 [nband][ldc]
   std::vector<long> ldc;
+  std::vector<DevBuf> Cil;             // per kappa: float2 [ceil(nslot/16)][ldil][16], 16-slot interleaved copy (pass Z)
+  std::vector<long> ldil;
   std::vector<char> resident;          // per kappa: this process holds the block
   std::vector<DevBuf> perm_dev;        // per kappa: device copy of the box-order permutation
   struct Chunk { int kap, band_lo, band_hi; cudaEvent_t ready; };
@@ -671,6 +673,9 @@ void box_order(KPointInfo& kp) {
   for (int j = 0; j < ng; j++) kp.pos[kp.perm[j]] = j;
 }
 
+void interleave_rows(pawb200_pswf* wf, int kap, int band_lo, int band_hi, cudaStream_t st);
+void alloc_interleaved(pawb200_pswf* wf, int kap);
+
 pawb200_pswf* ingest(ByteSource src, const double* kws) {
   HostSection hs_("ingest");
   require_device();
@@ -752,6 +757,7 @@ pawb200_pswf* ingest(ByteSource src, const double* kws) {
     // box order; consumers wait on the per-chunk events (wait_coeffs)
     {
       wf->perm_dev[kap] = upload(kp.perm);
+      alloc_interleaved(wf.get(), kap);
       cudaEvent_t alloc_ev;   // the pool block / permutation upload are ordered on the main stream
       CUDA_OK(cudaEventCreateWithFlags(&alloc_ev, cudaEventDisableTiming));
       CUDA_OK(cudaEventRecord(alloc_ev, g_stream));
@@ -759,7 +765,7 @@ pawb200_pswf* ingest(ByteSource src, const double* kws) {
       CUDA_OK(cudaEventDestroy(alloc_ev));
       const int half_len = kp.nplane / (wf->ncl ? 2 : 1);
       const int nchunk = std::max(1, std::min(8, hd.nband / 16));
-      const int per = (hd.nband + nchunk - 1) / nchunk;
+      const int per = ((hd.nband + nchunk - 1) / nchunk + 15) / 16 * 16;   // whole interleave groups per chunk
       for (int b0 = 0; b0 < hd.nband; b0 += per) {
         const int nb = std::min(per, hd.nband - b0);
         IngestRing::Slot& sl = ring.slots[ring.next++ % 3];
@@ -781,6 +787,7 @@ pawb200_pswf* ingest(ByteSource src, const double* kws) {
                                                          wf->perm_dev[kap].as<int>());
         count_launch();
         check_launch();
+        interleave_rows(wf.get(), kap, b0, b0 + nb, ring.copy);
         pawb200_pswf::Chunk ck{kap, b0, b0 + nb, nullptr};
         CUDA_OK(cudaEventCreateWithFlags(&ck.ready, cudaEventDisableTiming));
         CUDA_OK(cudaEventRecord(ck.ready, ring.copy));
@@ -800,6 +807,29 @@ void wait_coeffs(const pawb200_pswf* wf, int kap, int band_lo, int band_hi, cuda
   for (auto& c : wf->chunks)
     if (c.kap == kap && c.band_lo < band_hi && c.band_hi > band_lo)
       CUDA_OK(cudaStreamWaitEvent(st ? st : g_stream, c.ready, 0));
+}
+
+// Build / refresh the 16-slot interleaved coefficient copy for bands [band_lo, band_hi) of kappa on `st`.
+void interleave_rows(pawb200_pswf* wf, int kap, int band_lo, int band_hi, cudaStream_t st) {
+  const int h = wf->halves(), half_len = wf->npw_half(kap);
+  if (half_len == 0 || band_hi <= band_lo) return;
+  const int slot_lo = band_lo * h, slot_hi = band_hi * h;
+  dim3 grid((half_len + 127) / 128, ((slot_hi + 15) >> 4) - (slot_lo >> 4));
+  interleave_coeff_kernel<<<grid, 256, 0, st>>>(wf->C[kap].as<float2>(), wf->ldc[kap], h, half_len, slot_lo, slot_hi,
+                                                wf->Cil[kap].as<float2>(), wf->ldil[kap]);
+  count_launch();
+  check_launch();
+}
+
+// allocate (zeroed, on the main stream) the interleaved copy of kappa
+void alloc_interleaved(pawb200_pswf* wf, int kap) {
+  const int NK = wf->nkappa();
+  if ((int)wf->Cil.size() != NK) { wf->Cil.resize(NK); wf->ldil.assign(NK, 0); }
+  const long ldil = ((long)wf->npw_half(kap) + 1) / 2 * 2;
+  const size_t bytes = (size_t)((wf->nslot() + 15) / 16) * ldil * 16 * sizeof(float2);
+  wf->ldil[kap] = ldil;
+  wf->Cil[kap].alloc(std::max<size_t>(bytes, 16));
+  wf->Cil[kap].zero(std::max<size_t>(bytes, 16));
 }
 
 // ---- inverse scatter map -------------------------------------------------------------------
@@ -899,7 +929,7 @@ DevBuf g_grid;   // FFT box batch, reused across calls
 struct PrunedPlan {
   bool ok = false;
   FftGeom g;
-  DevBuf col_start, col_cnt, zpos, ysrc, xsrc, tw[3];
+  DevBuf col_start, col_cnt, zpos, col_run, ysrc, xsrc, tw[3];
 };
 
 bool factor_pair(int n, int& r1, int& r2) {
@@ -979,6 +1009,23 @@ std::shared_ptr<PrunedPlan> build_pruned_plan(const pawb200_pswf* wf, int kap, c
     xsrc[plane_xpos[p]] = p;
     for (int c = plane_col0[p]; c < plane_col0[p] + plane_ncol[p]; c++) ysrc[(size_t)p * fftg[1] + col_ypos[c]] = c;
   }
+  // cyclic z-run of each column (always one run for a cutoff sphere; checked, with a staged fallback)
+  std::vector<int4> col_run(g.ncol);
+  bool runs_ok = getenv("PAWB200_FFT_STAGED_Z") == nullptr;
+  for (int c = 0; c < g.ncol && runs_ok; c++) {
+    const int s0 = col_start[c], cnt = col_cnt[c];
+    int gap = -1;
+    for (int j = 0; j + 1 < cnt; j++)
+      if (zpos[s0 + j + 1] != zpos[s0 + j] + 1) {
+        if (gap >= 0) runs_ok = false;
+        gap = j;
+      }
+    if (gap >= 0 && !(zpos[s0] == 0 && zpos[s0 + cnt - 1] == fftg[2] - 1)) runs_ok = false;
+    // sorted list = [wrapped-around tail of the run (z = 0..), head of the run (z = zlo..n3-1)]
+    col_run[c] = gap < 0 ? make_int4(s0, cnt, zpos[s0], cnt) : make_int4(s0, cnt, zpos[s0 + gap + 1], cnt - (gap + 1));
+  }
+  if (runs_ok) P->col_run = upload(col_run);
+  g.col_run = runs_ok ? P->col_run.as<int4>() : nullptr;
   P->col_start = upload(col_start); P->col_cnt = upload(col_cnt); P->zpos = upload(zpos);
   P->ysrc = upload(ysrc); P->xsrc = upload(xsrc);
   g.col_start = P->col_start.as<int>(); g.col_cnt = P->col_cnt.as<int>(); g.zpos = P->zpos.as<int>();
@@ -1017,17 +1064,22 @@ void pruned_fft_r(const pawb200_pswf* wf, int kap, const PrunedPlan& P, int slot
   static bool configured = false;
   int occ[3] = {1, 1, 1};
   const size_t smem_z = (size_t)(2 * g.n3 * FFT_B + g.n3) * sizeof(double2);
+  const bool runs = g.col_run != nullptr && !wf->Cil.empty() && wf->Cil[kap].p;
   const size_t smem_y = (size_t)(2 * g.n2 * FFT_B + g.n2) * sizeof(double2) + g.n2 * sizeof(int);
   const size_t smem_x = (size_t)(2 * g.n1 * FFT_B + g.n1) * sizeof(double2) + g.n1 * sizeof(int);
   if (!configured) {
     const int big = 200 * 1024;
     CUDA_OK(cudaFuncSetAttribute(fft_pass_z_kernel<RMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CUDA_OK(cudaFuncSetAttribute(fft_pass_z_staged_kernel<RMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CUDA_OK(cudaFuncSetAttribute(fft_pass_y_kernel<RMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CUDA_OK(cudaFuncSetAttribute(fft_pass_x_kernel<RMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     configured = true;
   }
   auto threads = [&](int d) { return std::max(g.r1[d], g.r2[d]) * FFT_B; };
-  CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[0], fft_pass_z_kernel<RMAX>, threads(2), smem_z));
+  if (runs)
+    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[0], fft_pass_z_kernel<RMAX>, threads(2), smem_z));
+  else
+    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[0], fft_pass_z_staged_kernel<RMAX>, threads(2), smem_z));
   CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], fft_pass_y_kernel<RMAX>, threads(1), smem_y));
   CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[2], fft_pass_x_kernel<RMAX>, threads(0), smem_x));
   const int ngroups = (nslot + FFT_B - 1) / FFT_B;
@@ -1050,8 +1102,12 @@ void pruned_fft_r(const pawb200_pswf* wf, int kap, const PrunedPlan& P, int slot
     const int s0 = slot0 + g0 * FFT_B;
     const int ns = std::min(nslot - g0 * FFT_B, ng * FFT_B);
     wait_coeffs(wf, kap, s0 / h, (s0 + ns + h - 1) / h);
-    fft_pass_z_kernel<RMAX><<<grid((long)ng * g.ncol, occ[0]), threads(2), smem_z, g_stream>>>(
-        g, wf->C[kap].as<float2>(), wf->ldc[kap], h, wf->npw_half(kap), s0, ns, scale, g_fft_t1.as<double2>(), ng);
+    if (runs)
+      fft_pass_z_kernel<RMAX><<<grid((long)ng * g.ncol, occ[0]), threads(2), smem_z, g_stream>>>(
+          g, wf->Cil[kap].as<float2>(), wf->ldil[kap], s0, ns, scale, g_fft_t1.as<double2>(), ng);
+    else
+      fft_pass_z_staged_kernel<RMAX><<<grid((long)ng * g.ncol, occ[0]), threads(2), smem_z, g_stream>>>(
+          g, wf->C[kap].as<float2>(), wf->ldc[kap], h, wf->npw_half(kap), s0, ns, scale, g_fft_t1.as<double2>(), ng);
     fft_pass_y_kernel<RMAX><<<grid((long)ng * g.nplane * ((g.n3 + FFT_ZC - 1) / FFT_ZC), occ[1]), threads(1), smem_y, g_stream>>>(
         g, g_fft_t1.as<double2>(), g_fft_t2.as<double2>(), ng);
     fft_pass_x_kernel<RMAX><<<grid((long)ng * g.n2 * g.n3, occ[2]), threads(0), smem_x, g_stream>>>(
@@ -2176,6 +2232,8 @@ pawb200_pswf_t* pawb200_expand_symm_wf(pawb200_pswf_t* rwf, int num_kpts, const 
                                                 wf->nband, npw, dsrc.as<int>(), dfac.as<float2>(), tr == 1 ? 1 : 0);
     count_launch();
     check_launch();
+    alloc_interleaved(wf.get(), knum);
+    interleave_rows(wf.get(), knum, 0, wf->nband, g_stream);
   }
   return wf.release();
   API_END(nullptr)

@@ -159,6 +159,9 @@ struct FftGeom {            // device-side description of one (k-point, grid) pr
   const int* col_start;     // [ncol] first sorted plane-wave index of the column
   const int* col_cnt;       // [ncol]
   const int* zpos;          // [npw]  wrapped g3 of each sorted plane wave
+  const int4* col_run;      // [ncol] {start, cnt, zlo, nfirst}: the column's plane waves occupy the cyclic z-run
+                            //        zlo .. zlo+cnt-1 (mod n3); the first nfirst of the run sit at the END of the
+                            //        sorted list (they wrap), see fft_pass_z_kernel.  Null if some column is not a run.
   const int* ysrc;          // [nplane][n2] column index holding (plane, y) or -1
   const int* xsrc;          // [n1] plane index holding x or -1
   const double2* tw[3];     // exp(+2 pi i m / n_d), m < n_d
@@ -170,11 +173,63 @@ template <int RMAX> struct FftLaunch {
 };
 
 // ---- pass Z: coefficients -> T1[group][col][z][FFT_B] ---------------------------------------------
+// Reads the 16-slot interleaved coefficient copy (interleave_coeff_kernel): thread (q, b) pulls the plane waves
+// of slot b that phase 1 needs straight into registers, 16 threads per 128-byte row.  A column's plane waves
+// cover one cyclic run of z (the cutoff sphere is convex), so "is z present, and where" is arithmetic on four
+// integers per column instead of a staged, zero-filled shared-memory column.
+template <int RMAX>
+__global__ void __launch_bounds__(FftLaunch<RMAX>::THREADS, FftLaunch<RMAX>::MINB)
+fft_pass_z_kernel(FftGeom g, const float2* __restrict__ Cil, long ldil, int slot0, int nslot, double scale,
+                  double2* __restrict__ T1, int ngroups) {
+  extern __shared__ __align__(16) unsigned char fft_smem[];
+  double2* bufs = reinterpret_cast<double2*>(fft_smem);      // [2][n3][FFT_B] exchange buffers
+  double2* tw = bufs + 2 * g.n3 * FFT_B;                     // [n3]
+  const int tid = threadIdx.x, q = tid / FFT_B, b = tid % FFT_B;
+  const int R1 = g.r1[2], R2 = g.r2[2], n3 = g.n3;
+  for (int i = tid; i < n3; i += blockDim.x) tw[i] = g.tw[2][i];
+  const long nlines = (long)ngroups * g.ncol;
+  long line = blockIdx.x;
+  int4 run = line < nlines ? __ldg(g.col_run + (int)(line % g.ncol)) : make_int4(0, 0, 0, 0);
+  __syncthreads();
+  for (int it = 0; line < nlines; line += gridDim.x, it++) {
+    const int grp = (int)(line / g.ncol), col = (int)(line % g.ncol);
+    const int4 cur = run;
+    const long nxt = line + gridDim.x;
+    if (nxt < nlines) run = __ldg(g.col_run + (int)(nxt % g.ncol));     // next column's run, off the critical path
+    double2* buf = bufs + (it & 1) * n3 * FFT_B;
+    if (q < R2) {
+      const int slot = slot0 + grp * FFT_B + b;
+      const int cnt = slot < slot0 + nslot ? cur.y : 0;                  // pad slots of the last group stay zero
+      const float2* base = Cil + ((long)(slot >> 4) * ldil + cur.x) * FFT_B + (slot & 15);
+      auto load = [&](int row) {
+        int d = row - cur.z;
+        if (d < 0) d += n3;
+        if (d >= cnt) return make_double2(0, 0);
+        const int j = d < cur.w ? cur.y - cur.w + d : d - cur.w;
+        const float2 c = __ldg(base + j * FFT_B);
+        return make_double2(scale * (double)c.x, scale * (double)c.y);
+      };
+#define P1(R) line_phase1<R>(buf, tw, R2, q, b, load)
+      PAWB200_RADIX_SWITCH(R1, P1)
+#undef P1
+    }
+    __syncthreads();
+    if (q < R1) {
+      double2* out = T1 + (((long)grp * g.ncol + col) * n3) * FFT_B + b;
+      auto store = [&](int row, double2 v) { out[(long)row * FFT_B] = v; };
+#define P2(R) line_phase2<R>(buf, R1, q, b, store)
+      PAWB200_RADIX_SWITCH(R2, P2)
+#undef P2
+    }
+  }
+}
+
+// ---- pass Z, staged variant (fallback when a column's plane waves are not one cyclic z-run) --------------
 // slot -> coefficient row like scatter_pw_kernel: band = slot / halves, half = slot % halves.
 // The sparse column (z-run of plane waves) is staged through shared memory with coalesced reads.
 template <int RMAX>
 __global__ void __launch_bounds__(FftLaunch<RMAX>::THREADS, FftLaunch<RMAX>::MINB)
-fft_pass_z_kernel(FftGeom g, const float2* __restrict__ C, long ldc, int halves, int half_len, int slot0,
+fft_pass_z_staged_kernel(FftGeom g, const float2* __restrict__ C, long ldc, int halves, int half_len, int slot0,
                   int nslot, double scale, double2* __restrict__ T1, int ngroups) {
   extern __shared__ __align__(16) unsigned char fft_smem[];
   double2* in = reinterpret_cast<double2*>(fft_smem);        // [n3][FFT_B] sparse input column

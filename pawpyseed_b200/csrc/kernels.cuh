@@ -71,6 +71,32 @@ permute_coeff_kernel(const float2* __restrict__ raw, float2* __restrict__ C, lon
       C[(long)b * ld + (long)h * half_len + j] = raw[(long)b * ld + (long)h * half_len + src];
 }
 
+// Second coefficient layout for the pruned FFT: slots (band, spinor half) interleaved in groups of 16,
+//   Cil[((slot >> 4) * ldil + j) * 16 + (slot & 15)] = C[slot / halves][(slot % halves) * half_len + j]
+// so that pass Z reads 128-byte rows (16 slots of one plane wave) straight into registers.
+// Tiled transpose: CTA = one 16-slot group x 128 plane waves; only slots in [slot_lo, slot_hi) are written.
+__global__ void __launch_bounds__(256)
+interleave_coeff_kernel(const float2* __restrict__ C, long ldc, int halves, int half_len, int slot_lo,
+                        int slot_hi, float2* __restrict__ Cil, long ldil) {
+  __shared__ float2 tile[16][129];
+  const int grp = (slot_lo >> 4) + blockIdx.y;
+  const int j0 = blockIdx.x * 128;
+  for (int e = threadIdx.x; e < 16 * 128; e += 256) {
+    const int r = e >> 7, jj = e & 127;
+    const int slot = grp * 16 + r, j = j0 + jj;
+    float2 v = make_float2(0.f, 0.f);
+    if (slot >= slot_lo && slot < slot_hi && j < half_len)
+      v = C[(long)(slot / halves) * ldc + (long)(slot % halves) * half_len + j];
+    tile[r][jj] = v;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < 16 * 128; e += 256) {
+    const int jj = e >> 4, r = e & 15;
+    const int slot = grp * 16 + r, j = j0 + jj;
+    if (slot >= slot_lo && slot < slot_hi && j < half_len) Cil[((long)grp * ldil + j) * 16 + r] = tile[r][jj];
+  }
+}
+
 // (f2) k-point desymmetrisation  [utils.c:1070-1081]: Cnew[b][j] = fac[j] * Cold[b][src[j]] (conjugated under
 // time reversal), in single precision without FMA contraction so it rounds like the reference's complex float
 // multiply.
