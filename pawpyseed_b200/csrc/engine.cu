@@ -105,6 +105,8 @@ void require_device() {
   if (state < 0) throw std::runtime_error(why);
 }
 
+void trim_all_pools();
+
 // Stream-ordered caching allocator: all work runs on one stream, so a block returned to the pool
 // can be handed out again without a device synchronisation (later kernels are ordered after the
 // earlier users).  Avoids cudaMalloc/cudaFree (and their implicit syncs) on the per-step path.
@@ -133,7 +135,7 @@ struct DevPool {
     cudaError_t e = cudaMalloc(&p, n);
     if (e != cudaSuccess) {
       cudaGetLastError();
-      trim();
+      trim_all_pools();
       e = cudaMalloc(&p, n);
       if (e != cudaSuccess)
         throw std::runtime_error(std::string("CUDA: out of device memory allocating ") + std::to_string(n >> 20) + " MiB");
@@ -153,49 +155,68 @@ struct DevPool {
   }
 };
 DevPool g_pool;
+// Second pool for buffers that are written on the ingest streams (coefficients, their interleaved copy, the
+// box-order permutation).  Blocks only come back through pawb200_free_pswf, which waits for every stream first,
+// so a block taken from it is quiescent and may be used on any stream without ordering it behind the main one.
+DevPool g_xpool;
+void trim_all_pools() { g_pool.trim(); g_xpool.trim(); }
 
 struct DevBuf {
   void* p = nullptr;
   size_t bytes = 0;
+  bool x = false;   // block belongs to g_xpool
   DevBuf() = default;
   explicit DevBuf(size_t n) { alloc(n); }
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
-  DevBuf(DevBuf&& o) noexcept : p(o.p), bytes(o.bytes) { o.p = nullptr; o.bytes = 0; }
+  DevBuf(DevBuf&& o) noexcept : p(o.p), bytes(o.bytes), x(o.x) { o.p = nullptr; o.bytes = 0; }
   DevBuf& operator=(DevBuf&& o) noexcept {
-    if (this != &o) { release(); p = o.p; bytes = o.bytes; o.p = nullptr; o.bytes = 0; }
+    if (this != &o) { release(); p = o.p; bytes = o.bytes; x = o.x; o.p = nullptr; o.bytes = 0; }
     return *this;
   }
   ~DevBuf() { release(); }
   void alloc(size_t n) {
     release();
     if (n == 0) return;
+    x = false;
     p = g_pool.get(n);
     bytes = n;
   }
+  void alloc_x(size_t n) {   // cross-stream buffer, see g_xpool
+    release();
+    if (n == 0) return;
+    x = true;
+    p = g_xpool.get(n);
+    bytes = n;
+  }
   void ensure(size_t n) { if (n > bytes) alloc(n); }
-  void release() { if (p) g_pool.put(p, bytes); p = nullptr; bytes = 0; }
-  void zero() { if (p) CUDA_OK(cudaMemsetAsync(p, 0, bytes, g_stream)); }
-  void zero(size_t n) { if (p) CUDA_OK(cudaMemsetAsync(p, 0, std::min(n, bytes), g_stream)); }
+  void release() { if (p) (x ? g_xpool : g_pool).put(p, bytes); p = nullptr; bytes = 0; }
+  void zero(cudaStream_t st = g_stream) { if (p) CUDA_OK(cudaMemsetAsync(p, 0, bytes, st)); }
+  void zero(size_t n, cudaStream_t st = g_stream) { if (p) CUDA_OK(cudaMemsetAsync(p, 0, std::min(n, bytes), st)); }
   template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
 // Pinned staging arena for host->device uploads of setup data: bump allocation, recycled at the
 // synchronisation points the API already has (or when full).
+cudaStream_t g_unpack_stream = nullptr;   // ingest unpack stream (also reads the arena), set by ingest_ring()
+void sync_arena_users() {
+  CUDA_OK(cudaStreamSynchronize(g_stream));
+  if (g_unpack_stream) CUDA_OK(cudaStreamSynchronize(g_unpack_stream));
+}
 struct PinnedArena {
   unsigned char* base = nullptr;
   size_t cap = 0, used = 0;
   void* take(size_t n) {
     n = (n + 255) / 256 * 256;
     if (n > cap) {   // grow: everything in flight must land first
-      CUDA_OK(cudaStreamSynchronize(g_stream));
+      sync_arena_users();
       if (base) cudaFreeHost(base);
       cap = std::max<size_t>(n * 2, (size_t)64 << 20);
       CUDA_OK(cudaMallocHost((void**)&base, cap));
       used = 0;
     }
     if (used + n > cap) {
-      CUDA_OK(cudaStreamSynchronize(g_stream));
+      sync_arena_users();
       used = 0;
     }
     void* p = base + used;
@@ -207,22 +228,33 @@ struct PinnedArena {
 PinnedArena g_arena;
 
 void stream_sync() {
-  CUDA_OK(cudaStreamSynchronize(g_stream));
+  sync_arena_users();
   g_arena.reset_after_sync();
 }
 
+// pinned arena block -> device, by kernel (see pinned_fetch_kernel)
+void fetch_pinned(void* dst, const void* pinned_src, size_t bytes, cudaStream_t st) {
+  if (!bytes) return;
+  const unsigned blocks = (unsigned)std::min<size_t>(64, (bytes / 16 + 255) / 256 + 1);
+  pinned_fetch_kernel<<<blocks, 256, 0, st>>>((const unsigned char*)pinned_src, (unsigned char*)dst, bytes);
+  CUDA_OK(cudaGetLastError());
+}
+
 template <typename T>
-DevBuf upload(const T* v, size_t n) {
-  DevBuf b(std::max<size_t>(n, 1) * sizeof(T));
+DevBuf upload(const T* v, size_t n, cudaStream_t st = g_stream, bool xpool = false) {
+  DevBuf b;
+  if (xpool) b.alloc_x(std::max<size_t>(n, 1) * sizeof(T)); else b.alloc(std::max<size_t>(n, 1) * sizeof(T));
   if (n) {
-    void* st = g_arena.take(n * sizeof(T));
-    memcpy(st, v, n * sizeof(T));
-    CUDA_OK(cudaMemcpyAsync(b.p, st, n * sizeof(T), cudaMemcpyHostToDevice, g_stream));
+    void* stg = g_arena.take(n * sizeof(T));
+    memcpy(stg, v, n * sizeof(T));
+    fetch_pinned(b.p, stg, n * sizeof(T), st);
   }
   return b;
 }
 template <typename T>
-DevBuf upload(const std::vector<T>& v) { return upload(v.data(), v.size()); }
+DevBuf upload(const std::vector<T>& v, cudaStream_t st = g_stream, bool xpool = false) {
+  return upload(v.data(), v.size(), st, xpool);
+}
 
 // ---- stage timers (CUDA events on the launch stream) ---------------------------------------
 enum Stage { ST_H2D, ST_SCATTER, ST_FFT, ST_PROJECT, ST_TABLE, ST_GEMM_PS, ST_GEMM_AUG, ST_AUGMENT,
@@ -287,6 +319,33 @@ struct HostSection {
     g_hostprof.calls[name] += 1;
   }
 };
+
+// Device-side trace for debugging overlap (PAWB200_TRACE=1): trace_mark records an event on a stream; the marks
+// are printed, relative to the first one, when pawb200_get_timers is called.
+struct TraceMark { std::string name; cudaEvent_t ev; };
+std::vector<TraceMark> g_trace;
+bool trace_on() {
+  static const bool on = getenv("PAWB200_TRACE") != nullptr;
+  return on;
+}
+void trace_mark(const std::string& name, cudaStream_t st) {
+  if (!trace_on()) return;
+  TraceMark m{name, nullptr};
+  cudaEventCreate(&m.ev);
+  cudaEventRecord(m.ev, st);
+  g_trace.push_back(m);
+}
+void trace_dump() {
+  if (g_trace.empty()) return;
+  cudaDeviceSynchronize();
+  for (auto& m : g_trace) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, g_trace[0].ev, m.ev);
+    fprintf(stderr, "[trace] %8.3f ms  %s\n", ms, m.name.c_str());
+  }
+  for (auto& m : g_trace) cudaEventDestroy(m.ev);
+  g_trace.clear();
+}
 
 inline void count_launch(int n = 1) { g_launches += n; }
 inline void check_launch() { CUDA_OK(cudaGetLastError()); }
@@ -474,12 +533,12 @@ std::unique_ptr<SiteTables> build_site_tables(const std::vector<Element>& els, c
   }
   T->sites = upload(T->host);
   T->idx.alloc(npt * sizeof(int32_t));
-  CUDA_OK(cudaMemcpyAsync(T->idx.p, idx, npt * sizeof(int32_t), cudaMemcpyHostToDevice, g_stream));
+  fetch_pinned(T->idx.p, idx, npt * sizeof(int32_t), g_stream);
   T->path.alloc(3 * npt * sizeof(double));
-  CUDA_OK(cudaMemcpyAsync(T->path.p, path, 3 * npt * sizeof(double), cudaMemcpyHostToDevice, g_stream));
+  fetch_pinned(T->path.p, path, 3 * npt * sizeof(double), g_stream);
   if (wrap) {
     T->wrap.alloc(3 * npt * sizeof(int32_t));
-    CUDA_OK(cudaMemcpyAsync(T->wrap.p, wrap, 3 * npt * sizeof(int32_t), cudaMemcpyHostToDevice, g_stream));
+    fetch_pinned(T->wrap.p, wrap, 3 * npt * sizeof(int32_t), g_stream);
   }
   T->table.alloc(std::max<size_t>(1, tab) * sizeof(double2));
   T->by_mt.assign(4, {});
@@ -614,14 +673,27 @@ struct IngestRing {
   struct Slot {
     void* p = nullptr;
     size_t bytes = 0;
+    cudaEvent_t filled = nullptr, free = nullptr;   // copy landed / unpack kernels have consumed it
   };
-  cudaStream_t copy = nullptr;
+  // `copy` carries only the H2D transfers, `unpack` (high priority) the permutation / interleave kernels, so a
+  // transfer never queues behind a kernel that is waiting for SMs held by the persistent FFT / GEMM kernels.
+  cudaStream_t copy = nullptr, unpack = nullptr;
   Slot slots[3];
   unsigned next = 0;
 };
 IngestRing& ingest_ring() {
   static IngestRing r;
-  if (!r.copy) CUDA_OK(cudaStreamCreateWithFlags(&r.copy, cudaStreamNonBlocking));
+  if (!r.copy) {
+    int lo = 0, hi = 0;
+    CUDA_OK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CUDA_OK(cudaStreamCreateWithFlags(&r.copy, cudaStreamNonBlocking));
+    CUDA_OK(cudaStreamCreateWithPriority(&r.unpack, cudaStreamNonBlocking, hi));
+    g_unpack_stream = r.unpack;
+    for (auto& sl : r.slots) {
+      CUDA_OK(cudaEventCreateWithFlags(&sl.filled, cudaEventDisableTiming));
+      CUDA_OK(cudaEventCreateWithFlags(&sl.free, cudaEventDisableTiming));
+    }
+  }
   return r;
 }
 bool g_async_ingest = false;
@@ -674,7 +746,7 @@ void box_order(KPointInfo& kp) {
 }
 
 void interleave_rows(pawb200_pswf* wf, int kap, int band_lo, int band_hi, cudaStream_t st);
-void alloc_interleaved(pawb200_pswf* wf, int kap);
+void alloc_interleaved(pawb200_pswf* wf, int kap, cudaStream_t st);
 
 pawb200_pswf* ingest(ByteSource src, const double* kws) {
   HostSection hs_("ingest");
@@ -737,8 +809,10 @@ pawb200_pswf* ingest(ByteSource src, const double* kws) {
     wf->resident[kap] = 1;
     const long ld = ((long)kp.nplane + 31) / 32 * 32;
     wf->ldc[kap] = ld;
-    wf->C[kap].alloc((size_t)hd.nband * ld * sizeof(float2));
-    wf->C[kap].zero((size_t)hd.nband * ld * sizeof(float2));
+    // cross-stream buffers from the quiescent pool: the unpack stream fills them without being ordered behind
+    // whatever the main stream still has queued (e.g. the previous structure's transforms)
+    wf->C[kap].alloc_x((size_t)hd.nband * ld * sizeof(float2));
+    wf->C[kap].zero((size_t)hd.nband * ld * sizeof(float2), ring.unpack);
     const unsigned char* from;
     if (src.mem) {
       from = src.mem + (base + 1) * hd.nrecl;
@@ -756,41 +830,46 @@ pawb200_pswf* ingest(ByteSource src, const double* kws) {
     // raw records -> HBM in band chunks on the copy stream, each followed by its column permutation into
     // box order; consumers wait on the per-chunk events (wait_coeffs)
     {
-      wf->perm_dev[kap] = upload(kp.perm);
-      alloc_interleaved(wf.get(), kap);
-      cudaEvent_t alloc_ev;   // the pool block / permutation upload are ordered on the main stream
-      CUDA_OK(cudaEventCreateWithFlags(&alloc_ev, cudaEventDisableTiming));
-      CUDA_OK(cudaEventRecord(alloc_ev, g_stream));
-      CUDA_OK(cudaStreamWaitEvent(ring.copy, alloc_ev, 0));
-      CUDA_OK(cudaEventDestroy(alloc_ev));
+      wf->perm_dev[kap] = upload(kp.perm, ring.unpack, true);
+      alloc_interleaved(wf.get(), kap, ring.unpack);
       const int half_len = kp.nplane / (wf->ncl ? 2 : 1);
       const int nchunk = std::max(1, std::min(8, hd.nband / 16));
-      const int per = ((hd.nband + nchunk - 1) / nchunk + 15) / 16 * 16;   // whole interleave groups per chunk
+      // whole GEMM row tiles (64) per chunk when there are enough bands, else whole interleave groups (16)
+      const int gran = hd.nband >= 256 ? 64 : 16;
+      const int per = ((hd.nband + nchunk - 1) / nchunk + gran - 1) / gran * gran;
       for (int b0 = 0; b0 < hd.nband; b0 += per) {
         const int nb = std::min(per, hd.nband - b0);
         IngestRing::Slot& sl = ring.slots[ring.next++ % 3];
         const size_t raw_bytes = (size_t)per * ld * sizeof(float2);
         if (raw_bytes > sl.bytes) {
           CUDA_OK(cudaStreamSynchronize(ring.copy));
+          CUDA_OK(cudaStreamSynchronize(ring.unpack));
           if (sl.p) cudaFree(sl.p);
           CUDA_OK(cudaMalloc(&sl.p, raw_bytes));
           sl.bytes = raw_bytes;
         }
+        CUDA_OK(cudaStreamWaitEvent(ring.copy, sl.free, 0));     // the slot's previous contents were unpacked
+        trace_mark("h2d chunk start b0=" + std::to_string(b0), ring.copy);
         {
           ScopedStage tm(ST_H2D, ring.copy);
           CUDA_OK(cudaMemcpy2DAsync(sl.p, ld * sizeof(float2), from + (size_t)b0 * hd.nrecl, hd.nrecl,
                                     (size_t)kp.nplane * sizeof(float2), nb, cudaMemcpyHostToDevice, ring.copy));
         }
+        CUDA_OK(cudaEventRecord(sl.filled, ring.copy));
+        trace_mark("h2d chunk done b0=" + std::to_string(b0), ring.copy);
+        CUDA_OK(cudaStreamWaitEvent(ring.unpack, sl.filled, 0));
         dim3 grid((half_len + 255) / 256, std::min(nb, 64));
-        permute_coeff_kernel<<<grid, 256, 0, ring.copy>>>((const float2*)sl.p, wf->C[kap].as<float2>() + (long)b0 * ld,
+        permute_coeff_kernel<<<grid, 256, 0, ring.unpack>>>((const float2*)sl.p, wf->C[kap].as<float2>() + (long)b0 * ld,
                                                          ld, nb, wf->ncl ? 2 : 1, half_len,
                                                          wf->perm_dev[kap].as<int>());
         count_launch();
         check_launch();
-        interleave_rows(wf.get(), kap, b0, b0 + nb, ring.copy);
+        interleave_rows(wf.get(), kap, b0, b0 + nb, ring.unpack);
+        CUDA_OK(cudaEventRecord(sl.free, ring.unpack));
+        trace_mark("unpack done b0=" + std::to_string(b0), ring.unpack);
         pawb200_pswf::Chunk ck{kap, b0, b0 + nb, nullptr};
         CUDA_OK(cudaEventCreateWithFlags(&ck.ready, cudaEventDisableTiming));
-        CUDA_OK(cudaEventRecord(ck.ready, ring.copy));
+        CUDA_OK(cudaEventRecord(ck.ready, ring.unpack));
         wf->chunks.push_back(ck);
       }
     }
@@ -822,14 +901,14 @@ void interleave_rows(pawb200_pswf* wf, int kap, int band_lo, int band_hi, cudaSt
 }
 
 // allocate (zeroed, on the main stream) the interleaved copy of kappa
-void alloc_interleaved(pawb200_pswf* wf, int kap) {
+void alloc_interleaved(pawb200_pswf* wf, int kap, cudaStream_t st) {
   const int NK = wf->nkappa();
   if ((int)wf->Cil.size() != NK) { wf->Cil.resize(NK); wf->ldil.assign(NK, 0); }
   const long ldil = ((long)wf->npw_half(kap) + 1) / 2 * 2;
   const size_t bytes = (size_t)((wf->nslot() + 15) / 16) * ldil * 16 * sizeof(float2);
   wf->ldil[kap] = ldil;
-  wf->Cil[kap].alloc(std::max<size_t>(bytes, 16));
-  wf->Cil[kap].zero(std::max<size_t>(bytes, 16));
+  wf->Cil[kap].alloc_x(std::max<size_t>(bytes, 16));
+  wf->Cil[kap].zero(std::max<size_t>(bytes, 16), st);
 }
 
 // ---- inverse scatter map -------------------------------------------------------------------
@@ -1113,6 +1192,7 @@ void pruned_fft_r(const pawb200_pswf* wf, int kap, const PrunedPlan& P, int slot
     fft_pass_x_kernel<RMAX><<<grid((long)ng * g.n2 * g.n3, occ[2]), threads(0), smem_x, g_stream>>>(
         g, g_fft_t2.as<double2>(), X + (long)g0 * ngrid * FFT_B, ng);
     count_launch(3);
+    trace_mark("fft done slots " + std::to_string(s0) + "+" + std::to_string(ns), g_stream);
   }
   check_launch();
 }
@@ -1155,6 +1235,7 @@ void launch_project_il(const SiteTables& T, const double2* X, long ngrid, int ns
   launch_project_il_mt<1>(T, X, ngrid, nslot, P, ldp, slot0);
   launch_project_il_mt<2>(T, X, ngrid, nslot, P, ldp, slot0);
   launch_project_il_mt<3>(T, X, ngrid, nslot, P, ldp, slot0);
+  trace_mark("project_il done slots " + std::to_string(slot0) + "+" + std::to_string(nslot), g_stream);
 }
 
 size_t keep_boxes_budget() {
@@ -1289,8 +1370,10 @@ struct RawBuf {            // plain cudaMalloc buffer (not from the stream-order
   size_t bytes = 0;
   void ensure(size_t n) {
     if (n <= bytes) return;
-    CUDA_OK(cudaDeviceSynchronize());
-    if (p) cudaFree(p);
+    if (p) {   // growing: nothing may still be using the old block
+      CUDA_OK(cudaDeviceSynchronize());
+      cudaFree(p);
+    }
     CUDA_OK(cudaMalloc(&p, n));
     bytes = n;
   }
@@ -1338,7 +1421,7 @@ void run_zgemm_variant(const T* A, long lda, const T* B, long ldb, int M, int N,
   }
   plan.total = (long)plan.tiles_m * plan.tiles_n * plan.kiters;
   // side stream: one CTA per SM so the transforms on the main stream keep most of the register file / smem
-  plan.G = (int)std::min<long>((side_stream ? 1L : 2L) * g_num_sms, plan.total);
+  plan.G = (int)std::min<long>(2L * g_num_sms, plan.total);
   const size_t ws_bytes = (size_t)plan.G * 2 * ZG_BM * BN * sizeof(double2);
   double2* ws;
   if (side_stream) {
@@ -1348,6 +1431,7 @@ void run_zgemm_variant(const T* A, long lda, const T* B, long ldb, int M, int N,
     g_zg_ws.ensure(ws_bytes);
     ws = g_zg_ws.as<double2>();
   }
+  trace_mark(std::string(side_stream ? "side " : "main ") + "zgemm start M=" + std::to_string(M), st);
   ScopedStage tm(stage, st);
   zgemm_abh_kernel<T, K3M><<<plan.G, ZG_THREADS, smem, st>>>(A, lda, B, ldb, plan, out, ldo, accumulate ? 1 : 0, ws);
   count_launch();
@@ -1355,6 +1439,7 @@ void run_zgemm_variant(const T* A, long lda, const T* B, long ldb, int M, int N,
   zgemm_fixup_kernel<<<plan.tiles_m * plan.tiles_n, 256, 0, st>>>(plan, ws, out, ldo, accumulate ? 1 : 0);
   count_launch();
   check_launch();
+  trace_mark(std::string(side_stream ? "side " : "main ") + "zgemm done M=" + std::to_string(M) + " K=" + std::to_string(Kpad), st);
 }
 
 // PAWB200_GEMM_4M=1 selects the 4-real-product variant (default: 3M, 25 % fewer DMMA instructions)
@@ -1383,6 +1468,13 @@ void check_pair(const pawb200_pswf* S, const pawb200_pswf* R) {
                                                  "(projector.py:74-75)");
 }
 
+// true while some ingest chunk of (wf, kap) is still being copied to the device
+bool coeffs_in_flight(const pawb200_pswf* wf, int kap) {
+  for (auto& c : wf->chunks)
+    if (c.kap == kap && cudaEventQuery(c.ready) == cudaErrorNotReady) return true;
+  return false;
+}
+
 // pseudo overlap block for one kappa into dev [nbS][nbR]
 void pseudo_block(pawb200_pswf* S, pawb200_pswf* R, int kap, int flip, double2* out, long ldo,
                   cudaStream_t st = nullptr, bool side_stream = false) {
@@ -1391,8 +1483,21 @@ void pseudo_block(pawb200_pswf* S, pawb200_pswf* R, int kap, int flip, double2* 
   // the reference takes num_waves from wf_ref->kpts[kpt_num] (pseudoprojector.c:84) for both vectors
   if (S->kp[kap].nplane != R->kp[kr].nplane)
     throw std::runtime_error("plane-wave bases differ between the two wavefunctions at kappa " + std::to_string(kap));
-  wait_coeffs(S, kap, 0, S->nband, st);
   wait_coeffs(R, kr, 0, R->nband, st);
+  if (side_stream && coeffs_in_flight(S, kap)) {
+    // rows of S are multiplied ingest chunk by ingest chunk as their H2D copies land, so the GEMM runs under
+    // the rest of the transfer instead of after it
+    cudaStream_t s2 = st ? st : g_stream;
+    for (auto& c : S->chunks) {
+      if (c.kap != kap) continue;
+      CUDA_OK(cudaStreamWaitEvent(s2, c.ready, 0));
+      run_zgemm<float2>(S->C[kap].as<float2>() + (long)c.band_lo * S->ldc[kap], S->ldc[kap], R->C[kr].as<float2>(),
+                        R->ldc[kr], c.band_hi - c.band_lo, R->nband, S->ldc[kap], out + (long)c.band_lo * ldo, ldo,
+                        false, ST_GEMM_PS, st, side_stream);
+    }
+    return;
+  }
+  wait_coeffs(S, kap, 0, S->nband, st);
   run_zgemm<float2>(S->C[kap].as<float2>(), S->ldc[kap], R->C[kr].as<float2>(), R->ldc[kr], S->nband,
                     R->nband, S->ldc[kap], out, ldo, false, ST_GEMM_PS, st, side_stream);
 }
@@ -1579,7 +1684,11 @@ void overlap_matrix(pawb200_pswf* S, pawb200_pswf* R, const SiteLists* L, int fl
   check_pair(S, R);
   const int nS = S->nband, nR = R->nband;
   const size_t blk_bytes = (size_t)nS * nR * sizeof(double2);
-  const bool side = pseudo && gemm_overlap_enabled();
+  // the pseudo GEMM goes to its own stream when asked to (PAWB200_GEMM_OVERLAP) or while wf coefficients are still
+  // arriving (async ingest): it then starts per ingest chunk, ahead of the transforms queued on the main stream
+  bool side = pseudo && gemm_overlap_enabled();
+  for (int kap = lo; kap < hi && pseudo && !side; kap++)
+    if (S->resident[kap] && coeffs_in_flight(S, kap)) side = true;
   DevBuf blk;
   if (!side) blk.alloc(blk_bytes);
   AugPlan A;
@@ -1608,6 +1717,7 @@ void overlap_matrix(pawb200_pswf* S, pawb200_pswf* R, const SiteLists* L, int fl
       if (aug && recip) recip_block(S, R, *L, kap, flip, b, nR);
       ScopedStage tm(ST_D2H);
       CUDA_OK(cudaMemcpyAsync(dst, b, blk_bytes, cudaMemcpyDeviceToHost, g_stream));
+      trace_mark("d2h block done", g_stream);
       CUDA_OK(cudaEventRecord(g_pblk_free[slot], g_stream));
       continue;
     }
@@ -1803,6 +1913,7 @@ pawb200_pswf_t* pawb200_read_wavefunctions_from_str(const char* start, const dou
 void pawb200_free_pswf(pawb200_pswf_t* wf) {
   if (!wf) return;
   cudaStreamSynchronize(ingest_ring().copy);
+  cudaStreamSynchronize(ingest_ring().unpack);
   if (g_stream2) cudaStreamSynchronize(g_stream2);
   cudaStreamSynchronize(g_stream);
   delete wf;
@@ -2232,7 +2343,7 @@ pawb200_pswf_t* pawb200_expand_symm_wf(pawb200_pswf_t* rwf, int num_kpts, const 
                                                 wf->nband, npw, dsrc.as<int>(), dfac.as<float2>(), tr == 1 ? 1 : 0);
     count_launch();
     check_launch();
-    alloc_interleaved(wf.get(), knum);
+    alloc_interleaved(wf.get(), knum, g_stream);
     interleave_rows(wf.get(), knum, 0, wf->nband, g_stream);
   }
   return wf.release();
@@ -2538,6 +2649,7 @@ int pawb200_get_site_indices(pawb200_pswf_t* wf, int site, int* out, int capacit
 }
 void pawb200_get_timers(pawb200_timers* t) {
   drain_timers();
+  trace_dump();
   if (getenv("PAWB200_PROFILE")) {
     for (auto& kv : g_hostprof.ms)
       fprintf(stderr, "[pawb200 host] %-22s %9.2f ms  (%ld calls)\n", kv.first.c_str(), kv.second,

@@ -116,6 +116,17 @@ symm_map_kernel(const float2* __restrict__ Cold, long ldo, float2* __restrict__ 
   }
 }
 
+// Small host->device uploads (tables, index lists, plans) read pinned host memory from a kernel instead of using
+// the copy engine, so they never queue behind the bulk coefficient transfers the ingest stream has in flight.
+__global__ void __launch_bounds__(256)
+pinned_fetch_kernel(const unsigned char* __restrict__ src, unsigned char* __restrict__ dst, size_t n) {
+  const size_t n16 = n / 16;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride)
+    reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(src)[i];
+  for (size_t i = n16 * 16 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = src[i];
+}
+
 // (a3) gather back after a forward FFT  [linalg.c:72-77]; narrow to complex64
 __global__ void gather_pw_kernel(const double2* __restrict__ x, const int* __restrict__ gidx,
                                  float2* __restrict__ Cout, int npw, double scale) {
