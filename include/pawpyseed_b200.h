@@ -27,6 +27,8 @@
 #ifndef PAWPYSEED_B200_H
 #define PAWPYSEED_B200_H
 
+#include <stddef.h>
+
 #ifdef __cplusplus
 extern "C" {
 typedef struct { double re, im; } pawb200_c128;   /* layout of C99 `double complex` */
@@ -181,6 +183,10 @@ void pawb200_projection_matrix(pawb200_c128 *out, pawb200_pswf_t *wf_S, pawb200_
                                const int *M_R, const int *M_S, const int *N_R, const int *N_S,
                                const int *N_RS_R, const int *N_RS_S, int flip_spin,
                                int kappa_lo, int kappa_hi, int pseudo_only);
+/* Page-locked host memory for result buffers (e.g. the `out` of pawb200_projection_matrix): the device->host
+ * copy into it runs at full PCIe rate.  Any host pointer is accepted everywhere; this is only faster. */
+void *pawb200_alloc_pinned(size_t bytes);
+void pawb200_free_pinned(void *p);
 /* Multi-GPU sharding (one process per GPU): subsequent pawb200_read_wavefunctions* calls keep
  * only the (k,spin) blocks with kappa % world == rank in HBM; blocks of other ranks come back
  * as zeros from pawb200_projection_matrix and are summed/gathered by the caller (NCCL). */

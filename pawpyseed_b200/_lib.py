@@ -106,6 +106,8 @@ _SIGS = {
     "pawb200_num_projections": (C.c_int, [C.c_void_p, C.c_int]),
     "pawb200_get_channel_index": (C.c_int, [C.c_void_p, c_int_p]),
     "pawb200_get_site_indices": (C.c_int, [C.c_void_p, C.c_int, c_int_p, C.c_int]),
+    "pawb200_alloc_pinned": (C.c_void_p, [C.c_size_t]),
+    "pawb200_free_pinned": (None, [C.c_void_p]),
     "pawb200_get_timers": (None, [C.POINTER(Timers)]),
     "pawb200_reset_timers": (None, []),
 }
@@ -154,6 +156,33 @@ def i32(a):
 
 def f64(a):
     return np.ascontiguousarray(a, dtype=np.float64)
+
+
+_pinned_free = {}   # nbytes -> [ptr]: page-locked blocks are recycled (cudaMallocHost / cudaFreeHost synchronise)
+
+
+def _pinned_release(nbytes, ptr):
+    _pinned_free.setdefault(nbytes, []).append(ptr)
+
+
+def pinned_empty(shape, dtype):
+    """Uninitialised numpy array in page-locked host memory; the block returns to a free list with the array."""
+    import weakref
+    dtype = np.dtype(dtype)
+    count = int(np.prod(shape))
+    n = max(count * dtype.itemsize, 1)
+    cached = _pinned_free.get(n)
+    if cached:
+        ptr = cached.pop()
+    else:
+        ptr = lib().pawb200_alloc_pinned(n)
+        check()
+        if not ptr:
+            raise PAWpyError("pinned allocation of %d bytes failed" % n)
+    buf = (C.c_char * n).from_address(ptr)
+    arr = np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
+    weakref.finalize(buf, _pinned_release, n, ptr)
+    return arr
 
 
 def timers() -> dict:

@@ -2647,6 +2647,19 @@ int pawb200_get_site_indices(pawb200_pswf_t* wf, int site, int* out, int capacit
   if (out) std::copy(v.begin(), v.begin() + std::min<size_t>(capacity, v.size()), out);
   return (int)v.size();
 }
+// Page-locked host buffers for results: device->host copies into them run at full PCIe rate and asynchronously
+void* pawb200_alloc_pinned(size_t bytes) {
+  API_BEGIN
+  require_device();
+  void* p = nullptr;
+  CUDA_OK(cudaMallocHost(&p, std::max<size_t>(bytes, 1)));
+  return p;
+  API_END(nullptr)
+}
+void pawb200_free_pinned(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
 void pawb200_get_timers(pawb200_timers* t) {
   drain_timers();
   trace_dump();

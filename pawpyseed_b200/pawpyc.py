@@ -514,7 +514,7 @@ class CProjector:
         single_band_projection(b_wf)[b_basis*NK + kappa]."""
         NK = self.basis.nwk * self.basis.nspin
         lo, hi = (0, NK) if kappa_range is None else kappa_range
-        out = np.zeros((hi - lo, self.wf.nband, self.basis.nband), dtype=np.complex128)
+        out = _lib.pinned_empty((hi - lo, self.wf.nband, self.basis.nband), np.complex128)   # fully overwritten
         have = hasattr(self, "M_R")
         z = np.zeros(0, np.int32)
         lists = [getattr(self, n) if have else z for n in ("M_R", "M_S", "N_R", "N_S", "N_RS_R", "N_RS_S")]
