@@ -1137,30 +1137,80 @@ std::shared_ptr<PrunedPlan> get_pruned_plan(pawb200_pswf* wf, int kap, const int
 DevBuf g_fft_t1, g_fft_t2;
 
 // Inverse transform of slots [slot0, slot0 + nslot) of kappa into X (interleaved groups of FFT_B slots).
+// One launcher per pass, templated on the largest radix of ITS axis (10 / 12 / 14 / 16): thread count, register
+// budget and resident CTAs follow the axis, not the worst axis of the grid.
+constexpr int kFftSmemOptIn = 200 * 1024;
+inline unsigned fft_grid_dim(long lines, int occ) {
+  return (unsigned)std::min<long>(lines, (long)g_num_sms * std::max(occ, 1));
+}
+
 template <int RMAX>
-void pruned_fft_r(const pawb200_pswf* wf, int kap, const PrunedPlan& P, int slot0, int nslot, double2* X) {
-  const FftGeom& g = P.g;
-  static bool configured = false;
-  int occ[3] = {1, 1, 1};
-  const size_t smem_z = (size_t)(2 * g.n3 * FFT_B + g.n3) * sizeof(double2);
+void launch_pass_z(const pawb200_pswf* wf, int kap, const FftGeom& g, int s0, int ns, int ng, double scale) {
+  static int occ_run = 0, occ_staged = 0;
+  const int threads = std::max(g.r1[2], g.r2[2]) * FFT_B;
+  const size_t smem = (size_t)(2 * g.n3 * FFT_B + g.n3) * sizeof(double2);
   const bool runs = g.col_run != nullptr && !wf->Cil.empty() && wf->Cil[kap].p;
-  const size_t smem_y = (size_t)(2 * g.n2 * FFT_B + g.n2) * sizeof(double2) + g.n2 * sizeof(int);
-  const size_t smem_x = (size_t)(2 * g.n1 * FFT_B + g.n1) * sizeof(double2) + g.n1 * sizeof(int);
-  if (!configured) {
-    const int big = 200 * 1024;
-    CUDA_OK(cudaFuncSetAttribute(fft_pass_z_kernel<RMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    CUDA_OK(cudaFuncSetAttribute(fft_pass_z_staged_kernel<RMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    CUDA_OK(cudaFuncSetAttribute(fft_pass_y_kernel<RMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    CUDA_OK(cudaFuncSetAttribute(fft_pass_x_kernel<RMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    configured = true;
+  int& occ = runs ? occ_run : occ_staged;
+  if (!occ) {
+    if (runs) {
+      CUDA_OK(cudaFuncSetAttribute(fft_pass_z_kernel<RMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFftSmemOptIn));
+      CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fft_pass_z_kernel<RMAX>, threads, smem));
+    } else {
+      CUDA_OK(cudaFuncSetAttribute(fft_pass_z_staged_kernel<RMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFftSmemOptIn));
+      CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fft_pass_z_staged_kernel<RMAX>, threads, smem));
+    }
+    occ = std::max(occ, 1);
   }
-  auto threads = [&](int d) { return std::max(g.r1[d], g.r2[d]) * FFT_B; };
   if (runs)
-    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[0], fft_pass_z_kernel<RMAX>, threads(2), smem_z));
+    fft_pass_z_kernel<RMAX><<<fft_grid_dim((long)ng * g.ncol, occ), threads, smem, g_stream>>>(
+        g, wf->Cil[kap].as<float2>(), wf->ldil[kap], s0, ns, scale, g_fft_t1.as<double2>(), ng);
   else
-    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[0], fft_pass_z_staged_kernel<RMAX>, threads(2), smem_z));
-  CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], fft_pass_y_kernel<RMAX>, threads(1), smem_y));
-  CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[2], fft_pass_x_kernel<RMAX>, threads(0), smem_x));
+    fft_pass_z_staged_kernel<RMAX><<<fft_grid_dim((long)ng * g.ncol, occ), threads, smem, g_stream>>>(
+        g, wf->C[kap].as<float2>(), wf->ldc[kap], wf->halves(), wf->npw_half(kap), s0, ns, scale,
+        g_fft_t1.as<double2>(), ng);
+}
+
+template <int RMAX>
+void launch_pass_y(const FftGeom& g, int ng) {
+  static int occ = 0;
+  const int threads = std::max(g.r1[1], g.r2[1]) * FFT_B;
+  const size_t smem = (size_t)(2 * g.n2 * FFT_B + g.n2) * sizeof(double2) + g.n2 * sizeof(int);
+  if (!occ) {
+    CUDA_OK(cudaFuncSetAttribute(fft_pass_y_kernel<RMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFftSmemOptIn));
+    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fft_pass_y_kernel<RMAX>, threads, smem));
+    occ = std::max(occ, 1);
+  }
+  fft_pass_y_kernel<RMAX><<<fft_grid_dim((long)ng * g.nplane * ((g.n3 + FFT_ZC - 1) / FFT_ZC), occ), threads, smem,
+                            g_stream>>>(g, g_fft_t1.as<double2>(), g_fft_t2.as<double2>(), ng);
+}
+
+template <int RMAX>
+void launch_pass_x(const FftGeom& g, double2* X, int ng) {
+  static int occ = 0;
+  const int threads = std::max(g.r1[0], g.r2[0]) * FFT_B;
+  const size_t smem = (size_t)(2 * g.n1 * FFT_B + g.n1) * sizeof(double2) + g.n1 * sizeof(int);
+  if (!occ) {
+    CUDA_OK(cudaFuncSetAttribute(fft_pass_x_kernel<RMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFftSmemOptIn));
+    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fft_pass_x_kernel<RMAX>, threads, smem));
+    occ = std::max(occ, 1);
+  }
+  fft_pass_x_kernel<RMAX><<<fft_grid_dim((long)ng * g.n2 * g.n3, occ), threads, smem, g_stream>>>(
+      g, g_fft_t2.as<double2>(), X, ng);
+}
+
+#define PAWB200_AXIS_SWITCH(r, CALL) \
+  do {                               \
+    if ((r) <= 10) { CALL(10); }     \
+    else if ((r) <= 12) { CALL(12); } \
+    else if ((r) <= 14) { CALL(14); } \
+    else { CALL(16); }               \
+  } while (0)
+
+// Inverse transform of slots [slot0, slot0 + nslot) of kappa into X (interleaved groups of FFT_B slots).
+// NOTE: the cached occupancies assume one grid shape per process and axis class; they only size the persistent
+// grids, so a stale value costs efficiency, never correctness.
+void pruned_fft(const pawb200_pswf* wf, int kap, const PrunedPlan& P, int slot0, int nslot, double2* X) {
+  const FftGeom& g = P.g;
   const int ngroups = (nslot + FFT_B - 1) / FFT_B;
   const long ngrid = (long)g.n1 * g.n2 * g.n3;
   const size_t t1_grp = (size_t)g.ncol * g.n3 * FFT_B * sizeof(double2);
@@ -1173,7 +1223,7 @@ void pruned_fft_r(const pawb200_pswf* wf, int kap, const PrunedPlan& P, int slot
   g_fft_t2.ensure(t2_grp * gc);
   const double scale = std::pow(determinant3(wf->lattice), -0.5);
   const int h = wf->halves();
-  auto grid = [&](long lines, int o) { return (unsigned)std::min<long>(lines, (long)g_num_sms * std::max(o, 1)); };
+  const int rz = std::max(g.r1[2], g.r2[2]), ry = std::max(g.r1[1], g.r2[1]), rx = std::max(g.r1[0], g.r2[0]);
   ScopedStage tm(ST_FFT);
   g_boxes_fft += nslot;
   for (int g0 = 0; g0 < ngroups; g0 += gc) {
@@ -1181,29 +1231,19 @@ void pruned_fft_r(const pawb200_pswf* wf, int kap, const PrunedPlan& P, int slot
     const int s0 = slot0 + g0 * FFT_B;
     const int ns = std::min(nslot - g0 * FFT_B, ng * FFT_B);
     wait_coeffs(wf, kap, s0 / h, (s0 + ns + h - 1) / h);
-    if (runs)
-      fft_pass_z_kernel<RMAX><<<grid((long)ng * g.ncol, occ[0]), threads(2), smem_z, g_stream>>>(
-          g, wf->Cil[kap].as<float2>(), wf->ldil[kap], s0, ns, scale, g_fft_t1.as<double2>(), ng);
-    else
-      fft_pass_z_staged_kernel<RMAX><<<grid((long)ng * g.ncol, occ[0]), threads(2), smem_z, g_stream>>>(
-          g, wf->C[kap].as<float2>(), wf->ldc[kap], h, wf->npw_half(kap), s0, ns, scale, g_fft_t1.as<double2>(), ng);
-    fft_pass_y_kernel<RMAX><<<grid((long)ng * g.nplane * ((g.n3 + FFT_ZC - 1) / FFT_ZC), occ[1]), threads(1), smem_y, g_stream>>>(
-        g, g_fft_t1.as<double2>(), g_fft_t2.as<double2>(), ng);
-    fft_pass_x_kernel<RMAX><<<grid((long)ng * g.n2 * g.n3, occ[2]), threads(0), smem_x, g_stream>>>(
-        g, g_fft_t2.as<double2>(), X + (long)g0 * ngrid * FFT_B, ng);
+#define PASS_Z(R) launch_pass_z<R>(wf, kap, g, s0, ns, ng, scale)
+#define PASS_Y(R) launch_pass_y<R>(g, ng)
+#define PASS_X(R) launch_pass_x<R>(g, X + (long)g0 * ngrid * FFT_B, ng)
+    PAWB200_AXIS_SWITCH(rz, PASS_Z);
+    PAWB200_AXIS_SWITCH(ry, PASS_Y);
+    PAWB200_AXIS_SWITCH(rx, PASS_X);
+#undef PASS_Z
+#undef PASS_Y
+#undef PASS_X
     count_launch(3);
     trace_mark("fft done slots " + std::to_string(s0) + "+" + std::to_string(ns), g_stream);
   }
   check_launch();
-}
-
-void pruned_fft(const pawb200_pswf* wf, int kap, const PrunedPlan& P, int slot0, int nslot, double2* X) {
-  int rmax = 0;
-  for (int d = 0; d < 3; d++) rmax = std::max({rmax, P.g.r1[d], P.g.r2[d]});
-  if (rmax <= 10)
-    pruned_fft_r<10>(wf, kap, P, slot0, nslot, X);
-  else
-    pruned_fft_r<16>(wf, kap, P, slot0, nslot, X);
 }
 
 template <int MT>
@@ -1241,7 +1281,15 @@ void launch_project_il(const SiteTables& T, const double2* X, long ngrid, int ns
 size_t keep_boxes_budget() {
   const char* e = getenv("PAWB200_KEEP_BOXES_BYTES");
   if (e) return (size_t)atoll(e);
-  return (size_t)32 << 30;
+  // per wavefunction: a quarter of the device (45 GB on a 180 GB B200), so a basis/wf pair leaves half of HBM
+  // for coefficients, tables and scratch
+  static size_t quarter = 0;
+  if (!quarter) {
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) total_b = (size_t)128 << 30;
+    quarter = total_b / 4;
+  }
+  return quarter;
 }
 
 // setup_projections, step 1: transform every band of every resident (k,spin) block into resident interleaved

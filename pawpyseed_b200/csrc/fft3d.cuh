@@ -169,7 +169,8 @@ struct FftGeom {            // device-side description of one (k-point, grid) pr
 
 template <int RMAX> struct FftLaunch {
   static constexpr int THREADS = RMAX * FFT_B;          // q-slots x 16 bands
-  static constexpr int MINB = RMAX <= 10 ? 5 : 2;       // resident CTAs per SM the register budget is tuned for
+  // resident CTAs per SM the register budget is tuned for (10: 160 thr x 5, 12: 192 x 3, 14: 224 x 2, 16: 256 x 2)
+  static constexpr int MINB = RMAX <= 10 ? 5 : RMAX <= 12 ? 3 : 2;
 };
 
 // ---- pass Z: coefficients -> T1[group][col][z][FFT_B] ---------------------------------------------

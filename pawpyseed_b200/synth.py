@@ -120,8 +120,8 @@ def wavecar_image(lattice, encut, kpts, nspin, nband, coeffs, occs=None,
     """Build an in-memory WAVECAR (uint8 array) that `read_wavefunctions_from_str`
     parses (layout: SURVEY App. D / reader.c:129-228).
 
-    coeffs: callable (kappa, npw_file) -> complex64 [nband, npw_file], or a list
-            indexed by kappa = s*nwk + k.  For ncl, npw_file = 2*npw.
+    coeffs: callable (kappa, npw_file) -> complex64 [nband, npw_file] (or None to leave the
+            block as zero pages), or a list indexed by kappa = s*nwk + k.  For ncl, npw_file = 2*npw.
     """
     lattice = np.asarray(lattice, dtype=np.float64).reshape(3, 3)
     kpts = np.asarray(kpts, dtype=np.float64).reshape(-1, 3)
@@ -161,6 +161,8 @@ def wavecar_image(lattice, encut, kpts, nspin, nband, coeffs, occs=None,
             h[6::3] = occs[kap]
             rec(base)[:8 * len(h)].view(np.float64)[:] = h
             c = coeffs(kap, npw_file[k]) if callable(coeffs) else coeffs[kap]
+            if c is None:       # block left as untouched zero pages (another rank's shard)
+                continue
             c = np.ascontiguousarray(c, dtype=np.complex64)
             assert c.shape == (nband, npw_file[k]), (c.shape, nband, npw_file[k])
             view = img[(base + 1) * nrecl:(base + 1 + nband) * nrecl].reshape(nband, nrecl)
