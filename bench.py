@@ -248,7 +248,8 @@ def run_b200(args):
     nband, NK = w["nband"], w["nk"] * w["nspin"]
     own = {k for k in range(NK) if k % world == rank}
     L.pawb200_set_read_shard(rank, world)
-    L.pawb200_set_host_threads(max(1, (os.cpu_count() or 1) // world))   # torchrun exports OMP_NUM_THREADS=1
+    host_threads = int(os.environ.get("PAWB200_BENCH_THREADS", max(1, (os.cpu_count() or 1) // world)))
+    L.pawb200_set_host_threads(host_threads)   # torchrun exports OMP_NUM_THREADS=1
     imgs = make_images(w, own=own, pinned=True)
     h2d_bytes = sum(2 * 8 * nband * len(w["gvecs"][k % w["nk"]]) for k in own)   # both structures
     d2h_bytes = 16 * nband * nband * len(own)
@@ -276,8 +277,9 @@ def run_b200(args):
             return pr._projection_matrix()     # [NK][nbS][nbR] on host
         # one process per GPU: compute only the owned (k,spin) blocks, then all-gather the per-k matrices over NCCL
         ks = sorted(own)
-        mine = np.concatenate([pr._projection_matrix(kappa_range=(k, k + 1)) for k in ks]) if ks else \
-            np.zeros((0, nband, nband), np.complex128)
+        blocks = [pr._projection_matrix(kappa_range=(k, k + 1)) for k in ks]
+        mine = blocks[0] if len(blocks) == 1 else (np.concatenate(blocks) if blocks else
+                                                   np.zeros((0, nband, nband), np.complex128))
         return pdist.all_gather_own_blocks(mine, ks, NK, pinned_out=gather_pin, want_host=(rank == 0))
 
     def barrier():

@@ -63,17 +63,18 @@ def all_gather_own_blocks(own: np.ndarray, own_kappas, nkappa: int, group=None, 
     dist.all_gather_into_tensor(recv, send, group=group)
     if not want_host:
         return recv          # every rank holds all blocks in HBM; only callers that ask pay the D2H
+    # rank-major [world][per] -> kappa-major (kappa = j*world + r) on the device, then ONE copy of the nkappa valid
+    # blocks to the host; with a pinned buffer the returned array is a view of it (no host-side repacking)
+    if per > 1:
+        recv = recv.view(world, per, blk * 2).transpose(0, 1).contiguous().view(-1)
+    valid = recv[: nkappa * blk * 2]
     if pinned_out is not None:
-        pinned_out.copy_(recv, non_blocking=False)
-        host = pinned_out.numpy()
+        dst = pinned_out[: valid.numel()]
+        dst.copy_(valid, non_blocking=False)
+        host = dst.numpy()
     else:
-        host = recv.cpu().numpy()
-    host = host.view(np.complex128).reshape(world, per, *own.shape[1:])
-    full = np.zeros((nkappa,) + own.shape[1:], dtype=np.complex128)
-    for r in range(world):
-        ks = shard_kappas(nkappa, r, world)
-        full[ks] = host[r, : len(ks)]
-    return full
+        host = valid.cpu().numpy()
+    return host.view(np.complex128).reshape((nkappa,) + own.shape[1:])
 
 
 def max_over_ranks(value: float, group=None) -> float:
