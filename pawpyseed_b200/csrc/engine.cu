@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <unordered_map>
 #include <map>
 #include <memory>
 #include <stdexcept>
@@ -917,18 +918,44 @@ DevBuf build_inverse_map(const pawb200_pswf* wf, int kap, const int* fftg, std::
   const KPointInfo& kp = wf->kp[kap];
   const int npw = wf->npw_half(kap);
   const long ngrid = (long)fftg[0] * fftg[1] * fftg[2];
-  std::vector<int> inv(ngrid, -1);
-  if (fwd) fwd->resize(npw);
+  // host work is O(npw): grid position of every plane wave; the O(N_grid) map itself is filled on the device
+  std::vector<int> lin(npw), val(npw);
+  int lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
   for (int w = 0; w < npw; w++) {
     const int g1 = (kp.G[3 * w] + fftg[0]) % fftg[0];
     const int g2 = (kp.G[3 * w + 1] + fftg[1]) % fftg[1];
     const int g3 = (kp.G[3 * w + 2] + fftg[2]) % fftg[2];
     if (g1 < 0 || g2 < 0 || g3 < 0) throw std::runtime_error("FFT grid smaller than the G range");
-    const long lin = ((long)g1 * fftg[1] + g2) * fftg[2] + g3;
-    inv[lin] = kp.pos[w];   // later plane waves overwrite earlier ones, like linalg.c:31
-    if (fwd) (*fwd)[w] = (int)lin;
+    lin[w] = (int)(((long)g1 * fftg[1] + g2) * fftg[2] + g3);
+    val[w] = kp.pos[w];
+    for (int d = 0; d < 3; d++) {
+      lo[d] = std::min(lo[d], (int)kp.G[3 * w + d]);
+      hi[d] = std::max(hi[d], (int)kp.G[3 * w + d]);
+    }
   }
-  return upload(inv);
+  if (fwd) *fwd = lin;
+  // On an aliased grid several plane waves share a position; the reference's loop lets the last one win
+  // (linalg.c:31).  Keep only those winners so the device scatter has no write conflicts.
+  if (hi[0] - lo[0] >= fftg[0] || hi[1] - lo[1] >= fftg[1] || hi[2] - lo[2] >= fftg[2]) {
+    std::unordered_map<int, int> last;
+    for (int w = 0; w < npw; w++) last[lin[w]] = w;
+    std::vector<int> l2, v2;
+    l2.reserve(last.size()); v2.reserve(last.size());
+    for (int w = 0; w < npw; w++)
+      if (last[lin[w]] == w) { l2.push_back(lin[w]); v2.push_back(val[w]); }
+    lin.swap(l2);
+    val.swap(v2);
+  }
+  DevBuf inv((size_t)ngrid * sizeof(int));
+  CUDA_OK(cudaMemsetAsync(inv.p, 0xFF, (size_t)ngrid * sizeof(int), g_stream));    // -1 everywhere
+  const int n = (int)lin.size();
+  if (n) {
+    DevBuf dl = upload(lin), dv = upload(val);
+    fill_inverse_map_kernel<<<(n + 255) / 256, 256, 0, g_stream>>>(dl.as<int>(), dv.as<int>(), n, inv.as<int>());
+    count_launch();
+    check_launch();
+  }
+  return inv;
 }
 
 void launch_scatter(const pawb200_pswf* wf, int kap, int slot0, int nslot, const DevBuf& inv,
@@ -1833,6 +1860,52 @@ void check_kpoint(const pawb200_pswf* wf, int band, int kap) {
   if (!wf->resident[kap]) throw std::runtime_error("(k,spin) block not resident on this rank");
 }
 
+// Device -> arbitrary (pageable or pinned) host memory through two page-locked staging buffers: the copy of
+// chunk i+1 overlaps the host-side store (or += for accumulate) of chunk i, so large grids leave at PCIe rate instead
+// of the pageable-memcpy rate.  Synchronises the main stream.
+void d2h_pipelined(void* dst, const void* src_dev, size_t bytes, bool accumulate_f64) {
+  static unsigned char* stage[2] = {nullptr, nullptr};
+  static cudaEvent_t done[2];
+  const size_t chunk = (size_t)32 << 20;
+  if (!stage[0]) {
+    for (int i = 0; i < 2; i++) {
+      CUDA_OK(cudaMallocHost((void**)&stage[i], chunk));
+      CUDA_OK(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
+    }
+  }
+  const size_t nchunk = (bytes + chunk - 1) / chunk;
+  auto issue = [&](size_t c) {
+    const size_t off = c * chunk, n = std::min(chunk, bytes - off);
+    CUDA_OK(cudaMemcpyAsync(stage[c & 1], (const unsigned char*)src_dev + off, n, cudaMemcpyDeviceToHost, g_stream));
+    CUDA_OK(cudaEventRecord(done[c & 1], g_stream));
+  };
+  if (nchunk) issue(0);
+  for (size_t c = 0; c < nchunk; c++) {
+    CUDA_OK(cudaEventSynchronize(done[c & 1]));
+    const size_t off = c * chunk, n = std::min(chunk, bytes - off);
+    if (accumulate_f64) {
+      double* d = (double*)((unsigned char*)dst + off);
+      const double* s8 = (const double*)stage[c & 1];
+      const long cnt = (long)(n / sizeof(double));
+      // chunk c+1 may not be issued into the other buffer before chunk c-1's host pass is over: it is (sequential)
+      if (c + 1 < nchunk) issue(c + 1);
+#pragma omp parallel for schedule(static)
+      for (long i = 0; i < cnt; i++) d[i] += s8[i];
+    } else {
+      if (c + 1 < nchunk) issue(c + 1);
+      unsigned char* d = (unsigned char*)dst + off;
+      const unsigned char* s1 = stage[c & 1];
+      const long parts = 16, per = (long)((n + parts - 1) / parts);
+#pragma omp parallel for schedule(static)
+      for (long q = 0; q < parts; q++) {
+        const long o = q * per;
+        if (o < (long)n) memcpy(d + o, s1 + o, (size_t)std::min<long>(per, (long)n - o));
+      }
+    }
+  }
+  CUDA_OK(cudaStreamSynchronize(g_stream));
+}
+
 void state_to_host(pawb200_c128* out, int band, int kap, pawb200_pswf* wf, const int* fftg, const int* labels,
                    const double* coords) {
   require_device();
@@ -1842,9 +1915,7 @@ void state_to_host(pawb200_c128* out, int band, int kap, pawb200_pswf* wf, const
   const int h = wf->halves();
   realspace_boxes(wf, kap, band * h, h, fftg, T, inv);
   const long ngrid = (long)fftg[0] * fftg[1] * fftg[2];
-  ScopedStage tm(ST_D2H);
-  CUDA_OK(cudaMemcpyAsync(out, g_grid.p, (size_t)h * ngrid * sizeof(double2), cudaMemcpyDeviceToHost, g_stream));
-  CUDA_OK(cudaStreamSynchronize(g_stream));
+  d2h_pipelined(out, g_grid.p, (size_t)h * ngrid * sizeof(double2), false);
 }
 
 void density_to_host(double* Pout, pawb200_pswf* wf, const int* fftg, const int* labels, const double* coords,
@@ -1893,13 +1964,10 @@ void density_to_host(double* Pout, pawb200_pswf* wf, const int* fftg, const int*
                                                                    dw.as<double>(), rho.as<double>());
       count_launch();
       check_launch();
-      CUDA_OK(cudaStreamSynchronize(g_stream));
       i = j;
     }
   }
-  std::vector<double> hrho(ngrid);
-  CUDA_OK(cudaMemcpy(hrho.data(), rho.p, ngrid * sizeof(double), cudaMemcpyDeviceToHost));
-  for (long g = 0; g < ngrid; g++) Pout[g] += hrho[g];     // the reference accumulates into P
+  d2h_pipelined(Pout, rho.p, (size_t)ngrid * sizeof(double), true);     // the reference accumulates into P
 }
 
 }  // namespace

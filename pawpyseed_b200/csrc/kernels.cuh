@@ -127,6 +127,13 @@ pinned_fetch_kernel(const unsigned char* __restrict__ src, unsigned char* __rest
   for (size_t i = n16 * 16 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = src[i];
 }
 
+// inverse scatter map: inv[lin[w]] = val[w]  (lin holds distinct grid positions)
+__global__ void fill_inverse_map_kernel(const int* __restrict__ lin, const int* __restrict__ val, int n,
+                                        int* __restrict__ inv) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w < n) inv[lin[w]] = val[w];
+}
+
 // (a3) gather back after a forward FFT  [linalg.c:72-77]; narrow to complex64
 __global__ void gather_pw_kernel(const double2* __restrict__ x, const int* __restrict__ gidx,
                                  float2* __restrict__ Cout, int npw, double scale) {
