@@ -183,6 +183,10 @@ void pawb200_projection_matrix(pawb200_c128 *out, pawb200_pswf_t *wf_S, pawb200_
                                const int *M_R, const int *M_S, const int *N_R, const int *N_S,
                                const int *N_RS_R, const int *N_RS_S, int flip_spin,
                                int kappa_lo, int kappa_hi, int pseudo_only);
+/* Band shard of pawb200_ae_chg_density: occupied bands in [band_lo, band_hi) only, same weights; += into P.
+ * Ranks that hold the same wavefunction split the bands and all-reduce their grids (distributed.py). */
+void pawb200_ae_chg_density_bands(double *P, pawb200_pswf_t *wf, const int *fftg, const int *labels,
+                                  const double *coords, int band_lo, int band_hi);
 /* Page-locked host memory for result buffers (e.g. the `out` of pawb200_projection_matrix): the device->host
  * copy into it runs at full PCIe rate.  Any host pointer is accepted everywhere; this is only faster. */
 void *pawb200_alloc_pinned(size_t bytes);

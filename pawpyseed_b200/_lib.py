@@ -77,6 +77,7 @@ _SIGS = {
     "pawb200_remove_phase": (None, [c_dbl_p, C.c_int, C.c_void_p, c_int_p]),
     "pawb200_ae_state_density": (None, [c_dbl_p, C.c_int, C.c_int, C.c_void_p, c_int_p, c_int_p, c_dbl_p]),
     "pawb200_ae_chg_density": (None, [c_dbl_p, C.c_void_p, c_int_p, c_int_p, c_dbl_p]),
+    "pawb200_ae_chg_density_bands": (None, [c_dbl_p, C.c_void_p, c_int_p, c_int_p, c_dbl_p, C.c_int, C.c_int]),
     "pawb200_ncl_ae_chg_density": (None, [c_dbl_p, C.c_void_p, c_int_p, c_int_p, c_dbl_p]),
     "pawb200_write_volumetric": (None, [C.c_char_p, c_dbl_p, c_int_p, C.c_double]),
     "pawb200_project_realspace_state": (None, [c_dbl_p, C.c_int, C.c_void_p, C.c_void_p, c_int_p, c_int_p, c_dbl_p,

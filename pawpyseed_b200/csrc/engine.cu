@@ -1919,7 +1919,7 @@ void state_to_host(pawb200_c128* out, int band, int kap, pawb200_pswf* wf, const
 }
 
 void density_to_host(double* Pout, pawb200_pswf* wf, const int* fftg, const int* labels, const double* coords,
-                     int only_band, int only_kap) {
+                     int only_band, int only_kap, int band_lo = 0, int band_hi = 1 << 30) {
   require_device();
   if (!wf) throw std::runtime_error("NULL wavefunction pointer");
   SiteTables& T = ae_tables(wf, fftg, labels, coords);
@@ -1939,7 +1939,7 @@ void density_to_host(double* Pout, pawb200_pswf* wf, const int* fftg, const int*
       bands.push_back(only_band);
       wts.push_back(1.0);                                    // ae_state_density, density.c:35-37
     } else {
-      for (int b = 0; b < wf->nband; b++)
+      for (int b = std::max(0, band_lo); b < std::min(wf->nband, band_hi); b++)
         if (wf->kp[kap].occ[b] > 0) {                        // density.c:168
           bands.push_back(b);
           wts.push_back(wf->weight[kap] * wf->kp[kap].occ[b] * spin_mult);
@@ -2533,6 +2533,16 @@ void pawb200_ae_state_density(double* P, int BAND_NUM, int KPOINT_NUM, pawb200_p
 void pawb200_ae_chg_density(double* P, pawb200_pswf_t* wf, const int* fftg, const int* labels, const double* coords) {
   API_BEGIN
   density_to_host(P, wf, fftg, labels, coords, -1, -1);
+  API_END_VOID
+}
+
+// Band shard of ae_chg_density: only the occupied bands in [band_lo, band_hi) contribute (same weights), so that
+// ranks holding the same wavefunction can split the bands and sum their grids (one all-reduce).
+void pawb200_ae_chg_density_bands(double* P, pawb200_pswf_t* wf, const int* fftg, const int* labels,
+                                  const double* coords, int band_lo, int band_hi) {
+  API_BEGIN
+  if (wf && wf->ncl) throw std::runtime_error("band-sharded density is implemented for collinear wavefunctions");
+  density_to_host(P, wf, fftg, labels, coords, -1, -1, band_lo, band_hi);
   API_END_VOID
 }
 void pawb200_ncl_ae_chg_density(double* P, pawb200_pswf_t* wf, const int* fftg, const int* labels,

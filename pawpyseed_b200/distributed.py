@@ -77,6 +77,30 @@ def all_gather_own_blocks(own: np.ndarray, own_kappas, nkappa: int, group=None, 
     return host.view(np.complex128).reshape((nkappa,) + own.shape[1:])
 
 
+def band_block(nband: int, rank: int, world: int):
+    """Contiguous band range [lo, hi) of `rank` when the bands of one (k,spin) block are split over ranks."""
+    per = -(-nband // world)
+    return min(nband, rank * per), min(nband, (rank + 1) * per)
+
+
+def sharded_chg_density(wf, group=None, device=None):
+    """AE charge density with the bands split over ranks (the one reduction on the path).
+    Every rank holds the same wavefunction `wf` (a CWavefunction with projectors set up), accumulates the
+    |psi|^2 of its band block on its own GPU, and the f64 grids are summed with one all-reduce (NCCL on GPUs)."""
+    import torch
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return wf._get_realspace_density()
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    lo, hi = band_block(wf.nband, rank, world)
+    part = wf._get_realspace_density_shard(lo, hi)
+    if device is None:
+        device = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    t = torch.from_numpy(part.reshape(-1)).to(device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t.cpu().numpy().reshape(part.shape)
+
+
 def max_over_ranks(value: float, group=None) -> float:
     import torch
     import torch.distributed as dist

@@ -341,6 +341,15 @@ class CWavefunction(PseudoWavefunction):
         res.shape = tuple(self.fdimv)
         return res
 
+    def _get_realspace_density_shard(self, band_lo, band_hi):
+        """Extension: ae_chg_density restricted to the occupied bands in [band_lo, band_hi) (a rank's band shard)."""
+        res = np.zeros(self.fgridsize, dtype=np.float64, order="C")
+        _lib.lib().pawb200_ae_chg_density_bands(dp(res), self.wf_ptr, ip(self.fdimv), ip(self.nums), dp(self.coords),
+                                                int(band_lo), int(band_hi))
+        check()
+        res.shape = tuple(self.fdimv)
+        return res
+
     def _write_realspace_state(self, filename1, filename2, scale, b, k, s, remove_phase=False):
         self._check_bks(b, k, s)
         L = _lib.lib()

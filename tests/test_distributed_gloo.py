@@ -41,6 +41,14 @@ def test_shard_assignment_is_a_partition():
             assert seen == list(range(nk))
 
 
+def test_band_blocks_partition_the_bands():
+    for nband in (1, 7, 600, 2000):
+        for world in (1, 2, 3, 8):
+            blocks = [pd.band_block(nband, r, world) for r in range(world)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == nband
+            assert all(blocks[i][1] == blocks[i + 1][0] for i in range(world - 1))
+
+
 def test_block_exchange_world2_gloo():
     world, nk = 2, 5
     ctx = mp.get_context("spawn")

@@ -162,3 +162,15 @@ def test_projector_method_aug_recip(pair):
     assert np.abs(got - want).max() < 1e-7 * np.abs(want).max()
     M = pr.projection_matrix()
     assert np.abs(M[:, 2, :].T.reshape(-1) - got).max() < 1e-12
+
+
+def test_density_band_shards_sum_to_full_density(pair):
+    # band-split density = one all-reduce of the shard grids; here the two shards are summed in-process
+    from pawpyseed_b200 import distributed as pdist
+    basis = pair[2]
+    full = basis._get_realspace_density()
+    nb = basis.nband
+    parts = [basis._get_realspace_density_shard(*pdist.band_block(nb, r, 4)) for r in range(4)]
+    assert rel(sum(parts), full) < 1e-13
+    assert np.abs(parts[0]).max() > 0 and np.abs(parts[1]).max() > 0       # the occupied half is split over two shards
+    assert pdist.sharded_chg_density(basis).shape == full.shape            # no process group: plain call
