@@ -1039,7 +1039,7 @@ struct PrunedPlan {
 };
 
 bool factor_pair(int n, int& r1, int& r2) {
-  static const int ok[] = {2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 14, 15, 16};
+  static const int ok[] = {2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 14, 15, 16, 18, 20};
   int best = 1 << 30;
   bool found = false;
   for (int a : ok)
@@ -1166,7 +1166,7 @@ DevBuf g_fft_t1, g_fft_t2;
 // Inverse transform of slots [slot0, slot0 + nslot) of kappa into X (interleaved groups of FFT_B slots).
 // One launcher per pass, templated on the largest radix of ITS axis (10 / 12 / 14 / 16): thread count, register
 // budget and resident CTAs follow the axis, not the worst axis of the grid.
-constexpr int kFftSmemOptIn = 200 * 1024;
+constexpr int kFftSmemOptIn = 227 * 1024;
 inline unsigned fft_grid_dim(long lines, int occ) {
   return (unsigned)std::min<long>(lines, (long)g_num_sms * std::max(occ, 1));
 }
@@ -1230,7 +1230,8 @@ void launch_pass_x(const FftGeom& g, double2* X, int ng) {
     if ((r) <= 10) { CALL(10); }     \
     else if ((r) <= 12) { CALL(12); } \
     else if ((r) <= 14) { CALL(14); } \
-    else { CALL(16); }               \
+    else if ((r) <= 16) { CALL(16); } \
+    else { CALL(20); }               \
   } while (0)
 
 // Inverse transform of slots [slot0, slot0 + nslot) of kappa into X (interleaved groups of FFT_B slots).
@@ -1832,9 +1833,11 @@ void realspace_boxes(pawb200_pswf* wf, int kap, int slot0, int nslot, const int*
   const double* k = wf->kp[kap].k;
   ScopedStage tm(ST_AUGMENT);
   const long blocks = std::min<long>((ngrid + 255) / 256, (long)g_num_sms * 16);
-  bloch_phase_kernel<<<(unsigned)blocks, 256, 0, g_stream>>>(x, fftg[0], fftg[1], fftg[2], k[0], k[1], k[2], 1.0, nslot);
-  count_launch();
-  check_launch();
+  if (k[0] != 0 || k[1] != 0 || k[2] != 0) {   // exp(0) = 1 exactly: nothing to do at Gamma
+    bloch_phase_kernel<<<(unsigned)blocks, 256, 0, g_stream>>>(x, fftg[0], fftg[1], fftg[2], k[0], k[1], k[2], 1.0, nslot);
+    count_launch();
+    check_launch();
+  }
   if (T.nsites && T.total_pts) {
     int maxpts = 0, maxlm = 0;
     for (auto& sd : T.host) { maxpts = std::max(maxpts, sd.npts); maxlm = std::max(maxlm, sd.nlm); }
@@ -1847,6 +1850,39 @@ void realspace_boxes(pawb200_pswf* wf, int kap, int slot0, int nslot, const int*
           T.sites.as<SiteDev>(), T.idx.as<int>(), T.wrap.as<int>(), T.total_pts, T.table.as<double2>(),
           wf->P[kap].as<double2>() + (long)(slot0 + b0) * wf->ldp, wf->ldp, nb, x + (long)b0 * ngrid, ngrid,
           k[0], k[1], k[2]);
+      count_launch();
+      check_launch();
+    }
+  }
+}
+
+// Same, through the pruned transform: boxes in its band-interleaved layout X[group][g][16] (left in g_grid).
+// Used by the density accumulation, which never needs a box in the caller's layout.
+void realspace_boxes_il(pawb200_pswf* wf, int kap, const PrunedPlan& plan, int slot0, int nslot, const int* fftg,
+                        SiteTables& T) {
+  const long ngrid = (long)fftg[0] * fftg[1] * fftg[2];
+  const int ng = (nslot + FFT_B - 1) / FFT_B;
+  g_grid.ensure((size_t)ng * FFT_B * ngrid * sizeof(double2));
+  double2* x = g_grid.as<double2>();
+  pruned_fft(wf, kap, plan, slot0, nslot, x);
+  const double* k = wf->kp[kap].k;
+  ScopedStage tm(ST_AUGMENT);
+  if (k[0] != 0 || k[1] != 0 || k[2] != 0) {
+    const long blocks = std::min<long>((ngrid + 255) / 256, (long)g_num_sms * 16);
+    bloch_phase_il_kernel<<<(unsigned)blocks, 256, 0, g_stream>>>(x, fftg[0], fftg[1], fftg[2], k[0], k[1], k[2], 1.0, ng);
+    count_launch();
+    check_launch();
+  }
+  if (T.nsites && T.total_pts) {
+    int maxpts = 0, maxlm = 0;
+    for (auto& sd : T.host) { maxpts = std::max(maxpts, sd.npts); maxlm = std::max(maxlm, sd.nlm); }
+    constexpr int NBMAX = 32;
+    for (int b0 = 0; b0 < nslot; b0 += NBMAX) {
+      const int nb = std::min(NBMAX, nslot - b0);
+      dim3 grid(std::max(1, (maxpts + 255) / 256), T.nsites);
+      augment_add_il_kernel<<<grid, 256, sizeof(double2) * nb * maxlm, g_stream>>>(
+          T.sites.as<SiteDev>(), T.idx.as<int>(), T.wrap.as<int>(), T.total_pts, T.table.as<double2>(),
+          wf->P[kap].as<double2>() + (long)slot0 * wf->ldp, wf->ldp, b0, nb, x, ngrid, k[0], k[1], k[2]);
       count_launch();
       check_launch();
     }
@@ -1946,6 +1982,32 @@ void density_to_host(double* Pout, pawb200_pswf* wf, const int* fftg, const int*
         }
     }
     if (bands.empty()) continue;
+    // pruned transform + interleaved boxes when the grid factors and one 16-slot group fits the box budget
+    std::shared_ptr<PrunedPlan> plan = get_pruned_plan(wf, kap, fftg);
+    const size_t grp_bytes = (size_t)FFT_B * ngrid * sizeof(double2);
+    const long il_groups = std::min<long>(4, (long)(keep_boxes_budget() / grp_bytes));
+    if (plan->ok && il_groups >= 1 && !getenv("PAWB200_DENSITY_GENERIC")) {
+      const long il_batch = il_groups * FFT_B / h;          // bands per batch
+      size_t i = 0;
+      while (i < bands.size()) {
+        size_t j = i + 1;
+        while (j < bands.size() && bands[j] == bands[j - 1] + 1 && (long)(j - i) < il_batch) j++;
+        const int nb = (int)(j - i), nslot = nb * h, ng = (nslot + FFT_B - 1) / FFT_B;
+        realspace_boxes_il(wf, kap, *plan, bands[i] * h, nslot, fftg, T);
+        std::vector<double> w((size_t)ng * FFT_B, 0.0);     // pad slots of the last group weigh nothing
+        for (int q = 0; q < nb; q++)
+          for (int hh = 0; hh < h; hh++) w[q * h + hh] = wts[i + q];
+        DevBuf dw = upload(w);
+        const long blocks = std::min<long>((ngrid * 16 + 255) / 256, (long)g_num_sms * 16);
+        ScopedStage tm(ST_AUGMENT);
+        density_accum_il_kernel<<<(unsigned)blocks, 256, 0, g_stream>>>(g_grid.as<double2>(), ngrid, ng,
+                                                                        dw.as<double>(), rho.as<double>());
+        count_launch();
+        check_launch();
+        i = j;
+      }
+      continue;
+    }
     DevBuf inv = build_inverse_map(wf, kap, fftg);
     // occupied bands are contiguous in practice; process maximal runs in batches
     size_t i = 0;

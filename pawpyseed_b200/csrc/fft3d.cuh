@@ -9,8 +9,8 @@
 // full passes).  Boxes are stored band-interleaved, X[group][x][y][z][FFT_B], FFT_B = 16 bands = 256 B per grid
 // point, so every pass - whatever its direction - and the sphere gather of the projection kernel move whole
 // 256-B segments.  Each CTA transforms NB = 16 bands x LPC adjacent lines held in shared memory as [n][NB]
-// (batch fastest -> conflict-free), with a two-factor Cooley-Tukey n = R1*R2 (R <= 16, radices 2,3,5,7 and
-// their products <= 16 evaluated in registers).
+// (batch fastest -> conflict-free), with a two-factor Cooley-Tukey n = R1*R2 (R <= 20, radices 2,3,5,7 and
+// their products <= 20 evaluated in registers; n <= 400).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -18,9 +18,9 @@
 namespace pawb200 {
 
 constexpr int FFT_B = 16;          // interleaved bands per group
-constexpr int FFT_MAXR = 16;
+constexpr int FFT_MAXR = 20;
 
-// exp(+2 pi i m / R) for R <= 16 (filled by the host at start-up)
+// exp(+2 pi i m / R) for R <= FFT_MAXR (filled by the host at start-up)
 __constant__ double2 c_small_tw[FFT_MAXR + 1][FFT_MAXR];
 
 __device__ __forceinline__ double2 cmulf(double2 a, double2 b) {
@@ -116,7 +116,14 @@ struct SmallDFT {
       if constexpr (RMAX > 10) {                                                                  \
         switch (R) {                                                                              \
           case 12: CALL(12); break; case 14: CALL(14); break; case 15: CALL(15); break;           \
-          case 16: CALL(16); break; default: break;                                               \
+          case 16: CALL(16); break;                                                               \
+          default:                                                                                \
+            if constexpr (RMAX > 16) {                                                            \
+              switch (R) {                                                                        \
+                case 18: CALL(18); break; case 20: CALL(20); break; default: break;               \
+              }                                                                                   \
+            }                                                                                     \
+            break;                                                                                \
         }                                                                                         \
       }                                                                                           \
       break;                                                                                      \
@@ -169,8 +176,9 @@ struct FftGeom {            // device-side description of one (k-point, grid) pr
 
 template <int RMAX> struct FftLaunch {
   static constexpr int THREADS = RMAX * FFT_B;          // q-slots x 16 bands
-  // resident CTAs per SM the register budget is tuned for (10: 160 thr x 5, 12: 192 x 3, 14: 224 x 2, 16: 256 x 2)
-  static constexpr int MINB = RMAX <= 10 ? 5 : RMAX <= 12 ? 3 : 2;
+  // resident CTAs per SM the register budget is tuned for (10: 160 thr x 5, 12: 192 x 3, 14: 224 x 2, 16: 256 x 2,
+  // 20: 320 x 1 - lines up to 400 points fill the shared memory of an SM on their own)
+  static constexpr int MINB = RMAX <= 10 ? 5 : RMAX <= 12 ? 3 : RMAX <= 16 ? 2 : 1;
 };
 
 // ---- pass Z: coefficients -> T1[group][col][z][FFT_B] ---------------------------------------------

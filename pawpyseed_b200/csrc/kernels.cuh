@@ -644,6 +644,97 @@ gather_pw_batch_kernel(const double2* __restrict__ x, long ngrid, const int* __r
   Cout[(long)blockIdx.y * ldc + w] = make_float2((float)(v.x * scale), (float)(v.y * scale));
 }
 
+// ---- band-interleaved variants (boxes from the pruned transform: X[group][g][16]) of the real-space kernels ----
+// x *= exp(sign 2 pi i k.r_frac): a warp takes 32 consecutive grid points, each lane evaluates one phase, and the
+// 16 slots of two points are processed per step (512 contiguous bytes per warp access).
+__global__ void __launch_bounds__(256)
+bloch_phase_il_kernel(double2* __restrict__ x, int n0, int n1, int n2, double kx, double ky, double kz,
+                      double sign, int ngroups) {
+  const double PI = 3.14159265359;   // density.c:13
+  const long ngrid = (long)n0 * n1 * n2;
+  const int lane = threadIdx.x & 31;
+  const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+  for (long g0 = warp * 32; g0 < ngrid; g0 += nwarps * 32) {
+    const long g = g0 + lane;
+    double s = 0, c = 1;
+    if (g < ngrid) {
+      const int i = (int)(g / ((long)n1 * n2));
+      const int rem = (int)(g % ((long)n1 * n2));
+      const double kr = kx * ((double)i / n0) + ky * ((double)(rem / n2) / n1) + kz * ((double)(rem % n2) / n2);
+      sincos(sign * 2 * PI * kr, &s, &c);
+    }
+    for (int it = 0; it < 16; it++) {
+      const int src = 2 * it + (lane >> 4);
+      const double ss = __shfl_sync(0xffffffffu, s, src), cc = __shfl_sync(0xffffffffu, c, src);
+      const long gg = g0 + src;
+      if (gg >= ngrid) continue;
+      for (int grp = 0; grp < ngroups; grp++) {
+        double2* p = x + ((long)grp * ngrid + gg) * 16 + (lane & 15);
+        const double2 v = *p;
+        *p = make_double2(v.x * cc - v.y * ss, v.x * ss + v.y * cc);
+      }
+    }
+  }
+}
+
+// augment_add_kernel on interleaved boxes: slot b of the batch lives at x[((b >> 4) * ngrid + g) * 16 + (b & 15)]
+__global__ void __launch_bounds__(256)
+augment_add_il_kernel(const SiteDev* __restrict__ sites, const int* __restrict__ idx,
+                      const int* __restrict__ wrap, long wrap_ld, const double2* __restrict__ table,
+                      const double2* __restrict__ P, long ldp, int b0, int nbox, double2* __restrict__ x,
+                      long ngrid, double kx, double ky, double kz) {
+  const double PI = 3.14159265359;   // density.c:13
+  const SiteDev sd = sites[blockIdx.y];
+  extern __shared__ double2 sP[];    // [nbox][nlm]
+  for (int e = threadIdx.x; e < nbox * sd.nlm; e += blockDim.x)
+    sP[e] = P[(long)(b0 + e / sd.nlm) * ldp + sd.lm_off + (e % sd.nlm)];
+  __syncthreads();
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < sd.npts; p += gridDim.x * blockDim.x) {
+    const long q = sd.pt_off + p;
+    const double ph = (sd.coord[0] + wrap[q]) * kx + (sd.coord[1] + wrap[wrap_ld + q]) * ky +
+                      (sd.coord[2] + wrap[2 * wrap_ld + q]) * kz;
+    double s, c;
+    sincos(2 * PI * ph, &s, &c);
+    const int g = idx[q];
+    for (int b = 0; b < nbox; b++) {
+      double2 acc = make_double2(0, 0);
+      for (int ch = 0; ch < sd.nlm; ch++) {
+        const double2 t = cmul(table[sd.tab_off + (long)ch * sd.npts_pad + p], sP[b * sd.nlm + ch]);
+        acc.x += t.x;
+        acc.y += t.y;
+      }
+      const int slot = b0 + b;
+      double* dst = reinterpret_cast<double*>(x + ((long)(slot >> 4) * ngrid + g) * 16 + (slot & 15));
+      atomicAdd(dst, acc.x * c - acc.y * s);
+      atomicAdd(dst + 1, acc.x * s + acc.y * c);
+    }
+  }
+}
+
+// rho[g] += sum_slot w[slot] |x_slot[g]|^2 on interleaved boxes: half a warp per grid point, one lane per slot
+__global__ void __launch_bounds__(256)
+density_accum_il_kernel(const double2* __restrict__ x, long ngrid, int ngroups, const double* __restrict__ w,
+                        double* __restrict__ rho) {
+  const int lane = threadIdx.x & 31, b = lane & 15;
+  const long half = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+  const long nhalf = ((long)gridDim.x * blockDim.x) >> 4;
+  for (long g0 = 0; g0 < ngrid; g0 += nhalf) {          // uniform trip count per warp (shuffles inside)
+    const long g = g0 + half;
+    double a = 0;
+    if (g < ngrid)
+      for (int grp = 0; grp < ngroups; grp++) {
+        const double2 v = x[((long)grp * ngrid + g) * 16 + b];
+        a += (v.x * v.x + v.y * v.y) * w[grp * 16 + b];
+      }
+    a += __shfl_xor_sync(0xffffffffu, a, 8);
+    a += __shfl_xor_sync(0xffffffffu, a, 4);
+    a += __shfl_xor_sync(0xffffffffu, a, 2);
+    a += __shfl_xor_sync(0xffffffffu, a, 1);
+    if (b == 0 && g < ngrid) rho[g] += a;
+  }
+}
+
 // (a13) density accumulation  [density.c:170-173, 193-196]:  rho[g] += sum_box w[box] |x_box[g]|^2
 __global__ void __launch_bounds__(256)
 density_accum_kernel(const double2* __restrict__ x, long ngrid, int nbox,

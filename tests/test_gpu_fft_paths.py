@@ -39,6 +39,8 @@ def oracle(c):
     (28, 30, 32),    # 4x7, 5x6, 4x8            (radix 7, 8)
     (45, 48, 56),    # 5x9, 3x16|6x8, 7x8       (radix 9, 16)
     (60, 42, 75),    # 6x10, 6x7, 5x15          (radix 10, 15) - non-cubic
+    (162, 20, 36),   # 9x18, 4x5, 6x6           (radix 18: the 320-thread class)
+    (20, 200, 18),   # 4x5, 10x20, 3x6          (radix 20)
     (22, 26, 20),    # 2x11 / 2x13: unsupported radices -> generic cuFFT path
     (19, 20, 20),    # prime size -> generic path
 ])
@@ -48,6 +50,10 @@ def test_projections_on_awkward_grids(dim):
     got = np.array([[wf._get_projections(b, k) for b in range(5)] for k in range(4)])
     assert rel(got, np.array(o.P)) < TOL
     assert rel(wf._get_realspace_state(2, 1, 0), o.realspace_state(2, 1)) < TOL
+    # density on the same grid: pruned transform + interleaved accumulation where the grid factors, cuFFT otherwise
+    wf.fdimv = np.array(dim, np.int32)
+    wf.fgridsize = int(np.prod(dim))
+    assert rel(wf._get_realspace_density(), o.chg_density(np.array(dim))) < TOL
 
 
 def test_17_bands_group_tail_and_offsite_reuse_of_resident_boxes():
