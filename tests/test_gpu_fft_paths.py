@@ -121,3 +121,33 @@ def test_sharded_and_async_ingest():
     opr = pn.Projector(o, o, [[0, 1, 2, 3], [0, 1, 2, 3], [], [], [], []])
     want = np.array([opr.single_band_projection(b) for b in range(6)]).reshape(6, 6, 4).transpose(2, 0, 1)
     assert rel(full, want) < TOL
+
+
+def test_chunked_side_stream_gemm_matches_single_gemm(tmp_path):
+    """While wf coefficients are still arriving the pseudo-overlap GEMM runs per ingest chunk on its own stream
+    (PAWB200_GEMM_CHUNKED=1 forces that path): 300 bands = five 64-band chunks; same matrix as the one-shot GEMM."""
+    code = (
+        "import sys, numpy as np; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import cases; from pawpyseed_b200 import pawpyc, _lib\n"
+        "_lib.lib().pawb200_set_async_ingest(1)\n"
+        "cR, cS = cases.small_case(seed=41, nband=300, nspin=1), cases.small_case(seed=42, nband=300, nspin=1, perturb=0.02)\n"
+        "ws = []\n"
+        "for c in (cR, cS):\n"
+        "    w = pawpyc.CWavefunction(pawpyc.PWFPointer.from_arrays(c['image'], c['kpts'], c['kws']))\n"
+        "    w._c_projector_setup(len(c['pps']), len(c['labels']), c['grid_encut'], c['labels'], c['coords'], c['dim'], c['pps'])\n"
+        "    ws.append(w)\n"
+        "pr = pawpyc.CProjector(ws[1], ws[0])\n"
+        "pr._setup_overlap([[0, 1, 2], [0, 1, 2], [3], [3], [3], [3]], False)\n"
+        "np.save(sys.argv[1], pr._projection_matrix())\n"
+    ) % (ROOT, os.path.join(ROOT, "tests"))
+    outs = []
+    for mode in ("single", "chunked"):
+        env = dict(os.environ)
+        env.pop("PAWB200_GEMM_CHUNKED", None)
+        if mode == "chunked":
+            env["PAWB200_GEMM_CHUNKED"] = "1"
+        out = str(tmp_path / (mode + ".npy"))
+        subprocess.run([sys.executable, "-c", code, out], check=True, env=env, timeout=600)
+        outs.append(np.load(out))
+    assert outs[0].shape == (2, 300, 300)
+    assert rel(outs[1], outs[0]) < 1e-13
