@@ -40,6 +40,7 @@ typedef float complex pawb200_c64;
 #endif
 
 typedef struct pawb200_pswf pawb200_pswf_t;   /* replaces pswf_t  (utils.h:117-141) */
+typedef struct pawb200_density_ft pawb200_density_ft_t;   /* replaces density_ft_elem_t* (momentum.h:29-33) */
 typedef struct pawb200_ppot pawb200_ppot_t;   /* replaces ppot_t* (utils.h:49-70), a whole element list */
 
 /* ---- status ------------------------------------------------------------------------- */
@@ -172,6 +173,30 @@ void pawb200_reciprocal_offsite_wave_overlap(const double *dcoord, const double 
                                              const double *k2, const double *f2,
                                              const double *s2_3N, int size2, int l1, int m1,
                                              int l2, int m2, double *re_im);   /* radial.h:30-35 */
+
+/* ---- MomentumMatrix (momentum.h:56-92; pawpyc.pyx:738-807), SURVEY 8 row f4 -------------------------
+ * < b1,k1,s1 | exp(i (G + k1 - k2).r) | b2,k2,s2 > for every G of a cutoff sphere, and the plane-wave expansion
+ * of an all-electron band.  Grid helpers and quick_overlap run on the host like the reference's; the per-G sums run
+ * on the GPU (one warp per G for the plane-wave correlation, one CTA per G for the one-centre terms). */
+void pawb200_momentum_grid_size(pawb200_pswf_t *wf, double *nb1max, double *nb2max, double *nb3max,
+                                int *npmax, double encut);
+int pawb200_get_momentum_grid(int *igall, pawb200_pswf_t *wf, double nb1max, double nb2max,
+                              double nb3max, double encut);
+void pawb200_grid_bounds(int *G_bounds, int *gdim, const int *igall, int num_waves);
+void pawb200_list_to_grid_map(int *grid, const int *G_bounds, const int *gdim, const int *igall,
+                              int num_waves);
+pawb200_density_ft_t *pawb200_get_all_transforms(pawb200_pswf_t *wf, double encut);
+void pawb200_free_density_ft_elem_list(pawb200_density_ft_t *elems, int num_elems);
+void pawb200_get_momentum_matrix(pawb200_c128 *matrix, int numg, const int *igall, pawb200_pswf_t *wf,
+                                 const int *labels, const double *coords, int band1, int kpt1,
+                                 int spin1, int band2, int kpt2, int spin2,
+                                 pawb200_density_ft_t *transforms_list, double encut);
+void pawb200_fullwf_reciprocal(pawb200_c128 *Cs, const int *igall, pawb200_pswf_t *wf, int numg,
+                               int band_num, int kpt_num, const int *labels, const double *coords);
+/* returns the complex value through re_im[2] (the reference returns double complex by value) */
+void pawb200_quick_overlap(const int *dG, const pawb200_c128 *C1s, const pawb200_c128 *C2s, int numg,
+                           const int *Gs, const int *gmap, const int *G_bounds, const int *gdim,
+                           double *re_im);
 
 /* ---- extensions (no reference counterpart; used by bench.py / batched callers) -------- */
 /* Whole PAW-corrected overlap block in one call: out[kappa][b_S][b_R] (complex128,

@@ -906,6 +906,160 @@ def project_realspace_state(band_num, wf: Wavefunction, wf_R: Wavefunction, fftg
     return out
 
 
+# --------------------------------------------------------------------------- #
+# MomentumMatrix (momentum.c; pawpyc.pyx:738-807)
+# --------------------------------------------------------------------------- #
+def _dir_angles(v):
+    """theta, phi of a Cartesian vector with the reference's branch choices (momentum.c:190-202, 533-545)."""
+    r = mag(v)
+    theta = math.acos(v[2] / r)
+    if r - abs(v[2]) == 0:
+        phi = 0.0
+    else:
+        phi = math.acos(v[0] / math.pow(v[0] * v[0] + v[1] * v[1], 0.5))
+    if v[1] < 0:
+        phi = 2 * PI - phi
+    return theta, phi
+
+
+class MomentumMatrix:
+    def __init__(self, wf: Wavefunction, encut):
+        from pawpyseed_b200.synth import enumerate_gvectors
+        self.wf, self.encut = wf, float(encut)
+        # momentum_grid_size + get_momentum_grid (momentum.c:359-363, 402-445): the reader's enumeration at k = 0
+        self.ggrid = enumerate_gvectors(wf.lattice, self.encut, np.zeros(3)).astype(np.int32)
+        lo, hi = self.ggrid.min(axis=0), self.ggrid.max(axis=0)
+        self.gbounds = np.array([min(lo[0], 0), max(hi[0], 0), min(lo[1], 0), max(hi[1], 0), min(lo[2], 0), max(hi[2], 0)])
+        self.gdim = np.array([self.gbounds[1] - self.gbounds[0] + 1, self.gbounds[3] - self.gbounds[2] + 1,
+                              self.gbounds[5] - self.gbounds[4] + 1])
+        # get_all_transforms (momentum.c:225-276): SBT of (phi_i phi_j - phit_i phit_j)/r for every L
+        self.trans = []
+        for pp in wf.ppots:
+            t = {}
+            for n1, l1 in enumerate(pp.ls):
+                for n2, l2 in enumerate(pp.ls):
+                    rho = (pp.aewave[n1] * pp.aewave[n2] - pp.pswave[n1] * pp.pswave[n2]) / pp.wave_grid
+                    sbt = SBT(1e7, 0.0, l1 + l2, pp.wave_grid)
+                    for L in range(abs(l1 - l2), l1 + l2 + 1, 2):
+                        f = sbt.forward(rho, L)
+                        t[(n1, n2, L)] = (sbt.kgrid, f, spline_coeff(sbt.kgrid, f))
+            self.trans.append(t)
+
+    def spher_momentum(self, elem, n1, l1, m1, n2, l2, m2, G):
+        """momentum.c:156-223."""
+        if l1 < l2:
+            lx, ly, mx, my = l2, l1, m2, m1
+        else:
+            lx, ly, mx, my = l1, l2, m1, m2
+        if my < 0:
+            mx, my = -mx, -my
+        total = 0j
+        magG = mag(G)
+        for L in range(abs(l1 - l2), l1 + l2 + 1, 2):
+            k, f, sp = self.trans[elem][(n1, n2, L)]
+            if magG == 0:
+                sph = complex(Ylm(L, m2 - m1, 0.0, 0.0)) if (L == 0 and m1 == m2) else 0j
+            else:
+                th, ph = _dir_angles(G)
+                sph = complex(Ylm(L, m2 - m1, th, ph)) if abs(m2 - m1) <= L else 0j
+            total += sbtfac(lx, ly, (L - abs(l1 - l2)) // 2, lx + mx, my) * sph * 4 * PI * (1j) ** L \
+                * (-1.0) ** m2 * float(wave_interpolate(np.array([magG]), k, f, sp)[0])
+        return total
+
+    def pseudo_momentum(self, GP, kap1, b1, kap2, b2):
+        """momentum.c:47-107 (accumulated in FP64 here; the reference uses float complex)."""
+        wf = self.wf
+        G1, G2 = wf.Gs[kap1 % wf.nwk], wf.Gs[kap2 % wf.nwk]
+        look = {tuple(g): w for w, g in enumerate(G1.tolist())}
+        c1, c2 = wf.Cs[kap1][b1].astype(np.complex128), wf.Cs[kap2][b2].astype(np.complex128)
+        total = 0j
+        for w, g in enumerate(G2.tolist()):
+            j = look.get((g[0] + GP[0], g[1] + GP[1], g[2] + GP[2]))
+            if j is not None:
+                total += c2[w] * np.conj(c1[j])
+        return total
+
+    def momentum_matrix_elems(self, b1, k1, s1, b2, k2, s2):
+        """get_momentum_matrix (momentum.c:278-357)."""
+        wf = self.wf
+        kap1, kap2 = k1 + s1 * wf.nwk, k2 + s2 * wf.nwk
+        P1, P2 = wf.P[kap1][b1], wf.P[kap2][b2]
+        out = np.zeros(len(self.ggrid), dtype=np.complex128)
+        for gi, GP in enumerate(self.ggrid.tolist()):
+            total = self.pseudo_momentum(GP, kap1, b1, kap2, b2)
+            Gc = frac_to_cartesian(wf.kpts[k1] - wf.kpts[k2] + np.array(GP, dtype=np.float64), wf.reclattice)
+            cache = {}
+            for s in range(wf.num_sites):
+                e = int(wf.labels[s])
+                if e not in cache:
+                    ch = wf.ppots[e].chan
+                    cache[e] = np.array([[self.spher_momentum(e, n1, l1, m1, n2, l2, m2, Gc)
+                                          for (n2, l2, m2) in ch] for (n1, l1, m1) in ch])
+                phase = np.exp(2j * PI * np.dot(np.array(GP, dtype=np.float64), wf.coords[s]))
+                a = P1[wf.site_off[s]:wf.site_off[s + 1]]
+                b = P2[wf.site_off[s]:wf.site_off[s + 1]]
+                total += (np.conj(a) @ cache[e] @ b) * phase
+            out[gi] = total
+        return out
+
+    def reciprocal_fullfw(self, b, k, s):
+        """fullwf_reciprocal (momentum.c:465-543)."""
+        wf = self.wf
+        kap = k + s * wf.nwk
+        G = wf.Gs[k]
+        look = {tuple(g): w for w, g in enumerate(G.tolist())}
+        # fill_grid wraps with the G_bounds extents: later plane waves overwrite aliased earlier ones
+        lo = G.min(axis=0) if len(G) else np.zeros(3, int)
+        c = wf.Cs[kap][b]
+        inv_sqrt_vol = math.pow(determinant(wf.lattice), -0.5)
+        out = np.zeros(len(self.ggrid), dtype=np.complex128)
+        gb = self._wf_gbounds()
+        fd = np.array([gb[1] - gb[0] + 1, gb[3] - gb[2] + 1, gb[5] - gb[4] + 1])
+        grid = {}
+        for w, g in enumerate(G.tolist()):
+            grid[tuple(np.mod(np.mod(g, fd) + fd, fd))] = np.complex64(c[w])
+        for gi, GP in enumerate(self.ggrid.tolist()):
+            val = 0j
+            if gb[0] <= GP[0] <= gb[1] and gb[2] <= GP[1] <= gb[3] and gb[4] <= GP[2] <= gb[5]:
+                val += complex(grid.get(tuple(np.mod(np.array(GP) + fd, fd)), 0))
+            Gc = frac_to_cartesian(-np.array(GP, dtype=np.float64) - wf.kpts[k], wf.reclattice)
+            r = mag(Gc)
+            for site in range(wf.num_sites):
+                pp = wf.ppots[wf.labels[site]]
+                phase = np.exp(-2j * PI * np.dot(np.array(GP, dtype=np.float64), wf.coords[site]))
+                pr = wf.P[kap][b][wf.site_off[site]:wf.site_off[site + 1]]
+                for p, (n, l, m) in enumerate(pp.chan):
+                    rad = float(wave_interpolate(np.array([r]), pp.kwave_grid, pp.kwave[n], pp.kwave_spline[n])[0])
+                    if r == 0:
+                        sph = complex(Ylm(l, m, 0.0, 0.0))
+                    else:
+                        th, ph = _dir_angles(Gc)
+                        sph = complex(Ylm(l, m, th, ph))
+                    val += pr[p] * rad * sph * (1j) ** l * phase * 4 * PI * inv_sqrt_vol
+            out[gi] = val
+        return out
+
+    def _wf_gbounds(self):
+        """wf->G_bounds as the reader accumulates it over all k-points (reader.c:262-268), starting from 0."""
+        allg = np.concatenate(self.wf.Gs)
+        lo, hi = np.minimum(allg.min(axis=0), 0), np.maximum(allg.max(axis=0), 0)
+        return [lo[0], hi[0], lo[1], hi[1], lo[2], hi[2]]
+
+    def g_from_fullfw(self, b1, k1, s1, b2, k2, s2, dG):
+        """quick_overlap (momentum.c:547-574)."""
+        v1, v2 = self.reciprocal_fullfw(b1, k1, s1), self.reciprocal_fullfw(b2, k2, s2)
+        look = {tuple(g): w for w, g in enumerate(self.ggrid.tolist())}
+        gb = self.gbounds
+        total = 0j
+        for w, g in enumerate(self.ggrid.tolist()):
+            q = (g[0] + dG[0], g[1] + dG[1], g[2] + dG[2])
+            if gb[0] <= q[0] <= gb[1] and gb[2] <= q[1] <= gb[3] and gb[4] <= q[2] <= gb[5]:
+                wp = look.get(q)
+                if wp is not None:
+                    total += np.conj(v1[wp]) * v2[w]
+        return total
+
+
 def make_site_lists(coords_R, labels_R, coords_S, labels_S, lattice, rmax_R, rmax_S, tol=0.02):
     """projector.py:115-160 with pymatgen's periodic distance restated through
     min_cart_path; element identity is label equality.  rmax_* : per-label list."""

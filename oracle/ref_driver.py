@@ -163,6 +163,20 @@ def lib():
                                        C.POINTER(c_dbl_p)]
         L.wave_interpolate.restype = C.c_double
         L.wave_interpolate.argtypes = [C.c_double, C.c_int, c_dbl_p, c_dbl_p, C.POINTER(c_dbl_p)]
+        # momentum.h:56-92 (MomentumMatrix)
+        L.momentum_grid_size.argtypes = [P, c_dbl_p, c_dbl_p, c_dbl_p, c_int_p, C.c_double]
+        L.get_momentum_grid.restype = C.c_int
+        L.get_momentum_grid.argtypes = [c_int_p, P, C.c_double, C.c_double, C.c_double, C.c_double]
+        L.grid_bounds.argtypes = [c_int_p, c_int_p, c_int_p, C.c_int]
+        L.list_to_grid_map.argtypes = [c_int_p, c_int_p, c_int_p, c_int_p, C.c_int]
+        L.get_all_transforms.restype = C.c_void_p
+        L.get_all_transforms.argtypes = [P, C.c_double]
+        L.free_density_ft_elem_list.argtypes = [C.c_void_p, C.c_int]
+        L.get_momentum_matrix.argtypes = [c_dbl_p, C.c_int, c_int_p, P, c_int_p, c_dbl_p] + [C.c_int] * 6 + \
+            [C.c_void_p, C.c_double]
+        L.fullwf_reciprocal.argtypes = [c_dbl_p, c_int_p, P, C.c_int, C.c_int, C.c_int, c_int_p, c_dbl_p]
+        L.quick_overlap.restype = cdouble
+        L.quick_overlap.argtypes = [c_int_p, c_dbl_p, c_dbl_p, C.c_int, c_int_p, c_int_p, c_int_p, c_int_p]
         _lib = L
     return _lib
 
@@ -375,3 +389,45 @@ class RefProjector:
         """projector.py:210-223 (`aug_real`)."""
         res = self.wf.pseudoprojection(band_num, self.basis, flip_spin)
         return self.add_augmentation_terms(res, band_num, flip_spin)
+
+
+class RefMomentumMatrix:
+    """Reference-side analogue of pawpyc.CMomentumMatrix (pawpyc.pyx:738-807)."""
+
+    def __init__(self, wf: RefWavefunction, encut):
+        L = lib()
+        self.wf, self.encut = wf, float(encut)
+        nb = [C.c_double(0) for _ in range(3)]
+        npmax = C.c_int(0)
+        L.momentum_grid_size(wf.ptr, C.byref(nb[0]), C.byref(nb[1]), C.byref(nb[2]), C.byref(npmax), self.encut)
+        self.nbmax = [v.value for v in nb]
+        grid = np.zeros(3 * npmax.value, dtype=np.int32)
+        n = L.get_momentum_grid(_ip(grid), wf.ptr, nb[0].value, nb[1].value, nb[2].value, self.encut)
+        self.ggrid = np.ascontiguousarray(grid[:3 * n])
+        self.gbounds = np.zeros(6, dtype=np.int32)
+        self.gdim = np.zeros(3, dtype=np.int32)
+        L.grid_bounds(_ip(self.gbounds), _ip(self.gdim), _ip(self.ggrid), n)
+        self.grid3d = -np.ones(int(np.prod(self.gdim)), dtype=np.int32)
+        L.list_to_grid_map(_ip(self.grid3d), _ip(self.gbounds), _ip(self.gdim), _ip(self.ggrid), n)
+        self.transforms = L.get_all_transforms(wf.ptr, self.encut)
+
+    def momentum_matrix_elems(self, b1, k1, s1, b2, k2, s2):
+        numg = len(self.ggrid) // 3
+        res = np.zeros(numg, dtype=np.complex128)
+        lib().get_momentum_matrix(res.ctypes.data_as(c_dbl_p), numg, _ip(self.ggrid), self.wf.ptr, _ip(self.wf.nums),
+                                  _dp(self.wf.coords), b1, k1, s1, b2, k2, s2, self.transforms, self.encut)
+        return res
+
+    def reciprocal_fullfw(self, b, k, s):
+        numg = len(self.ggrid) // 3
+        res = np.zeros(numg, dtype=np.complex128)
+        lib().fullwf_reciprocal(res.ctypes.data_as(c_dbl_p), _ip(self.ggrid), self.wf.ptr, numg, b,
+                                k + s * self.wf.nwk, _ip(self.wf.nums), _dp(self.wf.coords))
+        return res
+
+    def g_from_fullfw(self, b1, k1, s1, b2, k2, s2, G):
+        v1, v2 = self.reciprocal_fullfw(b1, k1, s1), self.reciprocal_fullfw(b2, k2, s2)
+        GP = np.ascontiguousarray(G, dtype=np.int32)
+        r = lib().quick_overlap(_ip(GP), v1.ctypes.data_as(c_dbl_p), v2.ctypes.data_as(c_dbl_p), len(self.ggrid) // 3,
+                                _ip(self.ggrid), _ip(self.grid3d), _ip(self.gbounds), _ip(self.gdim))
+        return complex(r.re, r.im)

@@ -7,7 +7,8 @@ this package is the host-side mirror of the reference's Python / Cython interfac
 """
 from ._lib import PAWpyError  # noqa: F401
 
-__all__ = ["Wavefunction", "CoreRegion", "Pseudopotential", "Projector", "NCLWavefunction", "PAWpyError"]
+__all__ = ["Wavefunction", "CoreRegion", "Pseudopotential", "Projector", "NCLWavefunction", "MomentumMatrix",
+           "PAWpyError"]
 
 
 def __getattr__(name):
@@ -20,4 +21,7 @@ def __getattr__(name):
     if name == "NCLWavefunction":
         from .noncollinear import NCLWavefunction
         return NCLWavefunction
+    if name == "MomentumMatrix":
+        from .momentum import MomentumMatrix
+        return MomentumMatrix
     raise AttributeError(name)

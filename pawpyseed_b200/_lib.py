@@ -97,6 +97,16 @@ _SIGS = {
     "pawb200_reciprocal_offsite_wave_overlap": (None, [c_dbl_p, c_dbl_p, c_dbl_p, c_dbl_p, C.c_int,
                                                        c_dbl_p, c_dbl_p, c_dbl_p, C.c_int,
                                                        C.c_int, C.c_int, C.c_int, C.c_int, c_dbl_p]),
+    "pawb200_momentum_grid_size": (None, [C.c_void_p, c_dbl_p, c_dbl_p, c_dbl_p, c_int_p, C.c_double]),
+    "pawb200_get_momentum_grid": (C.c_int, [c_int_p, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double]),
+    "pawb200_grid_bounds": (None, [c_int_p, c_int_p, c_int_p, C.c_int]),
+    "pawb200_list_to_grid_map": (None, [c_int_p, c_int_p, c_int_p, c_int_p, C.c_int]),
+    "pawb200_get_all_transforms": (C.c_void_p, [C.c_void_p, C.c_double]),
+    "pawb200_free_density_ft_elem_list": (None, [C.c_void_p, C.c_int]),
+    "pawb200_get_momentum_matrix": (None, [c_dbl_p, C.c_int, c_int_p, C.c_void_p, c_int_p, c_dbl_p] + [C.c_int] * 6 +
+                                    [C.c_void_p, C.c_double]),
+    "pawb200_fullwf_reciprocal": (None, [c_dbl_p, c_int_p, C.c_void_p, C.c_int, C.c_int, C.c_int, c_int_p, c_dbl_p]),
+    "pawb200_quick_overlap": (None, [c_int_p, c_dbl_p, c_dbl_p, C.c_int, c_int_p, c_int_p, c_int_p, c_int_p, c_dbl_p]),
     "pawb200_projection_matrix": (None, [c_dbl_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                          C.c_int] + [c_int_p] * 6 + [C.c_int, C.c_int, C.c_int, C.c_int]),
     "pawb200_set_kappa_range": (None, [C.c_void_p, C.c_int, C.c_int]),

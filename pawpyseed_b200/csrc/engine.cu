@@ -2875,3 +2875,366 @@ void pawb200_reset_timers(void) {
 }
 
 }  // extern "C"
+
+// =======================================================================================
+// (f4) MomentumMatrix: momentum.h:56-92, momentum.c; pawpyc.pyx:738-807
+// =======================================================================================
+struct pawb200_density_ft {
+  // per element: SBT of (phi_n1 phi_n2 - phit_n1 phit_n2)/r for L = |l1-l2| .. l1+l2 step 2 (momentum.c:116-140,
+  // 225-276), as spline tables on the transform's k grid
+  struct Elem {
+    int N = 0;
+    std::vector<double> ks;
+    std::map<std::tuple<int, int, int>, int> slot;     // (n1, n2, L) -> slot
+    std::vector<std::vector<double>> tab;              // per slot: f[N] + 3N spline coefficients
+  };
+  std::vector<Elem> el;
+};
+
+namespace {
+
+Spline make_spline_v(const std::vector<double>& x, const std::vector<double>& f) {
+  return make_spline(x.data(), f.data(), (int)x.size());
+}
+
+std::vector<double> pack_spline(const std::vector<double>& f, const Spline& sp) {
+  const size_t n = f.size();
+  std::vector<double> t(4 * n);
+  for (size_t i = 0; i < n; i++) {
+    t[i] = f[i];
+    t[n + i] = sp.c[0][i];
+    t[2 * n + i] = sp.c[1][i];
+    t[3 * n + i] = sp.c[2][i];
+  }
+  return t;
+}
+
+// dense map over the wavefunction's G_bounds box: grid position -> storage (box-order) index of kappa's plane waves
+struct BoxMap {
+  int lo[3], dim[3];
+  DevBuf map;
+};
+BoxMap build_box_map(const pawb200_pswf* wf, int kap) {
+  BoxMap B;
+  for (int d = 0; d < 3; d++) {
+    B.lo[d] = wf->G_bounds[2 * d];
+    B.dim[d] = wf->G_bounds[2 * d + 1] - wf->G_bounds[2 * d] + 1;
+  }
+  const KPointInfo& kp = wf->kp[kap];
+  std::vector<int> m((size_t)B.dim[0] * B.dim[1] * B.dim[2], -1);
+  for (int w = 0; w < kp.nplane; w++) {
+    const int a = kp.G[3 * w] - B.lo[0], b = kp.G[3 * w + 1] - B.lo[1], c = kp.G[3 * w + 2] - B.lo[2];
+    m[((size_t)a * B.dim[1] + b) * B.dim[2] + c] = kp.pos[w];
+  }
+  B.map = upload(m);
+  return B;
+}
+
+std::vector<cdouble> fetch_projection_row(pawb200_pswf* wf, int kap, int band) {
+  const int np = wf->proj_sites ? wf->proj_sites->nproj : 0;
+  std::vector<cdouble> row(std::max(np, 1));
+  CUDA_OK(cudaMemcpyAsync(row.data(), wf->P[kap].as<double2>() + (long)band * wf->ldp,
+                          (size_t)np * sizeof(double2), cudaMemcpyDeviceToHost, g_stream));
+  CUDA_OK(cudaStreamSynchronize(g_stream));
+  return row;
+}
+
+// Runs momentum_site_kernel for one set of per-element terms / per-site weights.
+struct SiteTermSet {
+  std::vector<MomElem> elems;
+  std::vector<MomTerm> terms;
+  std::vector<double> radial;
+  std::vector<long> slot_off;
+  std::vector<long> w_off;
+  std::vector<cdouble> W;
+};
+void run_site_terms(const SiteTermSet& S, pawb200_pswf* wf, int numg, const DevBuf& dig, const double dk[3],
+                    double gsign, const int* labels, const double* coords, double phase_sign, double pref,
+                    double2* out) {
+  const int ns = wf->num_sites;
+  std::vector<int> se(ns);
+  for (int s = 0; s < ns; s++) se[s] = labels[s];
+  std::vector<double> recl(wf->reclattice, wf->reclattice + 9), crd(coords, coords + 3 * ns);
+  DevBuf de = upload(S.elems), dt = upload(S.terms), dr = upload(S.radial), dso = upload(S.slot_off);
+  DevBuf dse = upload(se), dc = upload(crd), dwo = upload(S.w_off), dW = upload(S.W), drecl = upload(recl);
+  const size_t smem = std::max<size_t>(S.terms.size(), 1) * sizeof(double2);
+  if (smem > 48 * 1024)
+    CUDA_OK(cudaFuncSetAttribute(momentum_site_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  momentum_site_kernel<<<numg, 128, smem, g_stream>>>(
+      numg, dig.as<int>(), dk[0], dk[1], dk[2], gsign, drecl.as<double>(), (int)S.elems.size(), de.as<MomElem>(),
+      dt.as<MomTerm>(), dr.as<double>(), dso.as<long>(), ns, dse.as<int>(), dc.as<double>(), dwo.as<long>(),
+      dW.as<double2>(), phase_sign, pref, out);
+  count_launch();
+  check_launch();
+}
+
+}  // namespace
+
+extern "C" {
+
+void pawb200_momentum_grid_size(pawb200_pswf_t* wf, double* nb1max, double* nb2max, double* nb3max, int* npmax,
+                                double encut) {
+  API_BEGIN
+  if (!wf) throw std::runtime_error("NULL wavefunction pointer");
+  WavecarHeader hd;
+  hd.encut = encut;
+  memcpy(hd.lattice, wf->lattice, sizeof(hd.lattice));
+  wavecar_bounds(hd);                                   // reader.c:55-127 `setup`
+  *nb1max = hd.nbmax[0]; *nb2max = hd.nbmax[1]; *nb3max = hd.nbmax[2];
+  *npmax = hd.npmax;
+  API_END_VOID
+}
+
+int pawb200_get_momentum_grid(int* igall, pawb200_pswf_t* wf, double nb1max, double nb2max, double nb3max,
+                              double encut) {
+  API_BEGIN
+  if (!wf) throw std::runtime_error("NULL wavefunction pointer");
+  WavecarHeader hd;
+  hd.encut = encut;
+  memcpy(hd.lattice, wf->lattice, sizeof(hd.lattice));
+  memcpy(hd.reclattice, wf->reclattice, sizeof(hd.reclattice));
+  hd.nbmax[0] = nb1max; hd.nbmax[1] = nb2max; hd.nbmax[2] = nb3max;
+  const double k0[3] = {0, 0, 0};
+  std::vector<int32_t> g = enumerate_g(hd, k0, nullptr);  // momentum.c:402-445: the reader's loop at k = 0
+  memcpy(igall, g.data(), g.size() * sizeof(int32_t));
+  return (int)(g.size() / 3);
+  API_END(-1)
+}
+
+void pawb200_grid_bounds(int* G_bounds, int* gdim, const int* igall, int num_waves) {   // momentum.c:365-388
+  for (int w = 0; w < num_waves; w++)
+    for (int d = 0; d < 3; d++) {
+      const int g = igall[3 * w + d];
+      if (g < G_bounds[2 * d]) G_bounds[2 * d] = g;
+      else if (g > G_bounds[2 * d + 1]) G_bounds[2 * d + 1] = g;
+    }
+  for (int d = 0; d < 3; d++) gdim[d] = G_bounds[2 * d + 1] - G_bounds[2 * d] + 1;
+}
+
+void pawb200_list_to_grid_map(int* grid, const int* G_bounds, const int* gdim, const int* igall,
+                              int num_waves) {                                          // momentum.c:390-400
+  (void)G_bounds;
+  for (int w = 0; w < num_waves; w++) {
+    int G[3];
+    for (int d = 0; d < 3; d++) G[d] = (igall[3 * w + d] % gdim[d] + gdim[d]) % gdim[d];
+    grid[((long)G[0] * gdim[1] + G[1]) * gdim[2] + G[2]] = w;
+  }
+}
+
+pawb200_density_ft_t* pawb200_get_all_transforms(pawb200_pswf_t* wf, double encut) {
+  API_BEGIN
+  (void)encut;                                           // the reference ignores it too (fixed 1e7, momentum.c:129)
+  if (!wf || !wf->has_projections) throw std::runtime_error("setup_projections has not been run");
+  auto D = std::make_unique<pawb200_density_ft>();
+  for (const Element& pp : wf->pps->list.el) {
+    pawb200_density_ft::Elem E;
+    E.N = pp.wave_gridsize;
+    int lmax = 0;
+    for (auto& f : pp.funcs) lmax = std::max(lmax, f.l);
+    BesselTransform bt(1e7, 0.0, 2 * lmax, E.N, pp.wave_grid.data());
+    E.ks.assign(bt.kgrid().begin(), bt.kgrid().begin() + E.N);
+    std::vector<double> rho(E.N);
+    for (int n1 = 0; n1 < pp.num_projs; n1++)
+      for (int n2 = 0; n2 < pp.num_projs; n2++) {
+        const RadialFunc &f1 = pp.funcs[n1], &f2 = pp.funcs[n2];
+        for (int i = 0; i < E.N; i++)                    // make_rho, momentum.c:109-114
+          rho[i] = (f1.aewave[i] * f2.aewave[i] - f1.pswave[i] * f2.pswave[i]) / pp.wave_grid[i];
+        for (int L = std::abs(f1.l - f2.l); L <= f1.l + f2.l; L += 2) {
+          std::vector<double> tr = bt.forward(rho.data(), L);
+          tr.resize(E.N);
+          E.slot[{n1, n2, L}] = (int)E.tab.size();
+          E.tab.push_back(pack_spline(tr, make_spline_v(E.ks, tr)));
+        }
+      }
+    D->el.push_back(std::move(E));
+  }
+  return D.release();
+  API_END(nullptr)
+}
+
+void pawb200_free_density_ft_elem_list(pawb200_density_ft_t* elems, int num_elems) {
+  (void)num_elems;
+  delete elems;
+}
+
+// matrix[g] = < b1,k1,s1 | exp(i (G_g + k1 - k2).r) | b2,k2,s2 >  (momentum.c:278-357).  The plane-wave part is
+// accumulated in FP64 (reference: float complex); the one-centre part is FP64 in both.
+void pawb200_get_momentum_matrix(pawb200_c128* matrix, int numg, const int* igall, pawb200_pswf_t* wf,
+                                 const int* labels, const double* coords, int band1, int kpt1, int spin1, int band2,
+                                 int kpt2, int spin2, pawb200_density_ft_t* T, double encut) {
+  API_BEGIN
+  (void)encut;
+  require_device();
+  if (!wf || !T) throw std::runtime_error("NULL pointer");
+  if (wf->ncl) throw std::runtime_error("momentum matrix elements are implemented for collinear wavefunctions");
+  const int kap1 = kpt1 + spin1 * wf->nwk, kap2 = kpt2 + spin2 * wf->nwk;
+  check_kpoint(wf, band1, kap1);
+  check_kpoint(wf, band2, kap2);
+  if (!wf->has_projections) throw std::runtime_error("setup_projections has not been run");
+  if (numg <= 0) return;
+  std::vector<int> ig(igall, igall + 3 * (size_t)numg);
+  DevBuf dig = upload(ig);
+  DevBuf out((size_t)numg * sizeof(double2));
+  // ---- plane-wave part ----
+  {
+    BoxMap B = build_box_map(wf, kap1);
+    const KPointInfo& k2 = wf->kp[kap2];
+    std::vector<int> g2(3 * (size_t)k2.nplane);
+    for (int j = 0; j < k2.nplane; j++)
+      for (int d = 0; d < 3; d++) g2[3 * j + d] = k2.G[3 * k2.perm[j] + d];       // storage order
+    DevBuf dg2 = upload(g2);
+    wait_coeffs(wf, kap1, band1, band1 + 1);
+    wait_coeffs(wf, kap2, band2, band2 + 1);
+    momentum_pseudo_kernel<<<(numg * 32 + 255) / 256, 256, 0, g_stream>>>(
+        numg, dig.as<int>(), wf->C[kap1].as<float2>() + (long)band1 * wf->ldc[kap1],
+        wf->C[kap2].as<float2>() + (long)band2 * wf->ldc[kap2], dg2.as<int>(), k2.nplane, B.map.as<int>(), B.lo[0],
+        B.lo[1], B.lo[2], B.dim[0], B.dim[1], B.dim[2], out.as<double2>());
+    count_launch();
+    check_launch();
+  }
+  // ---- one-centre part: per site W[t] = sum over channel pairs feeding term t (momentum.c:318-350, 156-223) ----
+  const std::vector<cdouble> P1 = fetch_projection_row(wf, kap1, band1), P2 = fetch_projection_row(wf, kap2, band2);
+  SiteTermSet S;
+  const auto& els = wf->pps->list.el;
+  std::vector<std::map<std::tuple<int, int, int, int>, int>> term_index(els.size());
+  for (size_t e = 0; e < els.size(); e++) {
+    const auto& E = T->el[e];
+    MomElem me;
+    me.term_off = (int)S.terms.size();
+    me.N = E.N;
+    me.ks_off = (long)S.radial.size();
+    S.radial.insert(S.radial.end(), E.ks.begin(), E.ks.end());
+    std::vector<long> local_off(E.tab.size());
+    for (size_t q = 0; q < E.tab.size(); q++) {
+      local_off[q] = (long)S.radial.size();
+      S.radial.insert(S.radial.end(), E.tab[q].begin(), E.tab[q].end());
+    }
+    for (auto& kv : E.slot) {
+      const int L = std::get<2>(kv.first);
+      for (int M = -L; M <= L; M++) {
+        term_index[e][{std::get<0>(kv.first), std::get<1>(kv.first), L, M}] = (int)S.terms.size() - me.term_off;
+        S.slot_off.push_back(local_off[kv.second]);
+        S.terms.push_back(MomTerm{(int)S.slot_off.size() - 1, L, M, (L == 0 && M == 0) ? 1 : 0});
+      }
+    }
+    me.nterm = (int)S.terms.size() - me.term_off;
+    S.elems.push_back(me);
+  }
+  const cdouble I(0, 1);
+  for (int s = 0; s < wf->num_sites; s++) {
+    const int e = labels[s];
+    if (e < 0 || e >= (int)els.size()) throw std::runtime_error("element label out of range");
+    const Element& pp = els[e];
+    const SiteDev& sd = wf->proj_sites->host[s];
+    S.w_off.push_back((long)S.W.size());
+    const size_t base = S.W.size();
+    S.W.resize(base + S.elems[e].nterm, cdouble(0, 0));
+    for (int i = 0; i < pp.total_projs; i++)
+      for (int j = 0; j < pp.total_projs; j++) {
+        const Channel &ci = pp.chan[i], &cj = pp.chan[j];
+        const cdouble pq = std::conj(P1[sd.lm_off + i]) * P2[sd.lm_off + j];
+        int lx, ly, mx, my;
+        if (ci.l < cj.l) { lx = cj.l; ly = ci.l; mx = cj.m; my = ci.m; }
+        else { lx = ci.l; ly = cj.l; mx = ci.m; my = cj.m; }
+        if (my < 0) { mx = -mx; my = -my; }
+        const int M = cj.m - ci.m;
+        for (int L = std::abs(ci.l - cj.l); L <= ci.l + cj.l; L += 2) {
+          if (std::abs(M) > L) continue;                                   // Y_L^M vanishes identically
+          const cdouble fac = sbt_factor(lx, ly, L, mx, my) * 4 * kPi * std::pow(I, L) * std::pow(-1.0, cj.m);
+          S.W[base + term_index[e][{ci.n, cj.n, L, M}]] += pq * fac;
+        }
+      }
+  }
+  const double dk[3] = {wf->kp[kap1].k[0] - wf->kp[kap2].k[0], wf->kp[kap1].k[1] - wf->kp[kap2].k[1],
+                        wf->kp[kap1].k[2] - wf->kp[kap2].k[2]};
+  run_site_terms(S, wf, numg, dig, dk, 1.0, labels, coords, 1.0, 1.0, out.as<double2>());
+  CUDA_OK(cudaMemcpyAsync(matrix, out.p, (size_t)numg * sizeof(double2), cudaMemcpyDeviceToHost, g_stream));
+  stream_sync();
+  API_END_VOID
+}
+
+// Cs[g] += C(b,k,s,G_g) with | b,k,s > = V^-1/2 sum_G C exp(i (k+G).r): pseudo coefficient + partial-wave part
+// (momentum.c:465-543).  kpt_num is the kappa index k + s*nwk like the reference's call (pawpyc.pyx:790-791).
+void pawb200_fullwf_reciprocal(pawb200_c128* Cs, const int* igall, pawb200_pswf_t* wf, int numg, int band_num,
+                               int kpt_num, const int* labels, const double* coords) {
+  API_BEGIN
+  require_device();
+  if (wf && wf->ncl) throw std::runtime_error("fullwf_reciprocal is implemented for collinear wavefunctions");
+  check_kpoint(wf, band_num, kpt_num);
+  if (!wf->has_projections) throw std::runtime_error("setup_projections has not been run");
+  if (numg <= 0) return;
+  std::vector<int> ig(igall, igall + 3 * (size_t)numg);
+  DevBuf dig = upload(ig);
+  DevBuf out((size_t)numg * sizeof(double2));
+  {
+    void* st = g_arena.take((size_t)numg * sizeof(double2));
+    memcpy(st, Cs, (size_t)numg * sizeof(double2));                         // the reference accumulates into Cs
+    fetch_pinned(out.p, st, (size_t)numg * sizeof(double2), g_stream);
+  }
+  BoxMap B = build_box_map(wf, kpt_num);
+  wait_coeffs(wf, kpt_num, band_num, band_num + 1);
+  momentum_pick_kernel<<<(numg + 255) / 256, 256, 0, g_stream>>>(
+      numg, dig.as<int>(), wf->C[kpt_num].as<float2>() + (long)band_num * wf->ldc[kpt_num], B.map.as<int>(), B.lo[0],
+      B.lo[1], B.lo[2], B.dim[0], B.dim[1], B.dim[2], out.as<double2>());
+  count_launch();
+  check_launch();
+  const std::vector<cdouble> P = fetch_projection_row(wf, kpt_num, band_num);
+  SiteTermSet S;
+  const auto& els = wf->pps->list.el;
+  const cdouble I(0, 1);
+  for (size_t e = 0; e < els.size(); e++) {
+    const Element& pp = els[e];
+    MomElem me;
+    me.term_off = (int)S.terms.size();
+    me.N = pp.wave_gridsize;
+    me.ks_off = (long)S.radial.size();
+    S.radial.insert(S.radial.end(), pp.kwave_grid.begin(), pp.kwave_grid.begin() + me.N);
+    std::vector<long> foff(pp.num_projs);
+    for (int n = 0; n < pp.num_projs; n++) {
+      foff[n] = (long)S.radial.size();
+      std::vector<double> kw(pp.funcs[n].kwave.begin(), pp.funcs[n].kwave.begin() + me.N);
+      const std::vector<double> t = pack_spline(kw, pp.funcs[n].kwave_s);
+      S.radial.insert(S.radial.end(), t.begin(), t.end());
+    }
+    for (int p = 0; p < pp.total_projs; p++) {
+      S.slot_off.push_back(foff[pp.chan[p].n]);
+      S.terms.push_back(MomTerm{(int)S.slot_off.size() - 1, pp.chan[p].l, pp.chan[p].m, 1});
+    }
+    me.nterm = pp.total_projs;
+    S.elems.push_back(me);
+  }
+  for (int s = 0; s < wf->num_sites; s++) {
+    const Element& pp = els[labels[s]];
+    const SiteDev& sd = wf->proj_sites->host[s];
+    S.w_off.push_back((long)S.W.size());
+    for (int p = 0; p < pp.total_projs; p++) S.W.push_back(P[sd.lm_off + p] * std::pow(I, pp.chan[p].l));
+  }
+  const double* k = wf->kp[kpt_num].k;
+  const double dk[3] = {k[0], k[1], k[2]};
+  const double pref = 4 * kPi * std::pow(determinant3(wf->lattice), -0.5);
+  run_site_terms(S, wf, numg, dig, dk, -1.0, labels, coords, -1.0, pref, out.as<double2>());
+  CUDA_OK(cudaMemcpyAsync(Cs, out.p, (size_t)numg * sizeof(double2), cudaMemcpyDeviceToHost, g_stream));
+  stream_sync();
+  API_END_VOID
+}
+
+// < C1 | shift by dG | C2 > over the momentum grid (momentum.c:547-574); O(numg) host loop like the reference
+void pawb200_quick_overlap(const int* dG, const pawb200_c128* C1s, const pawb200_c128* C2s, int numg, const int* Gs,
+                           const int* gmap, const int* G_bounds, const int* gdim, double* re_im) {
+  const cdouble* c1 = (const cdouble*)C1s;
+  const cdouble* c2 = (const cdouble*)C2s;
+  cdouble total(0, 0);
+  for (int w = 0; w < numg; w++) {
+    int GP[3] = {Gs[3 * w] + dG[0], Gs[3 * w + 1] + dG[1], Gs[3 * w + 2] + dG[2]};
+    if (GP[0] >= G_bounds[0] && GP[0] <= G_bounds[1] && GP[1] >= G_bounds[2] && GP[1] <= G_bounds[3] &&
+        GP[2] >= G_bounds[4] && GP[2] <= G_bounds[5]) {
+      for (int d = 0; d < 3; d++) GP[d] = (GP[d] % gdim[d] + gdim[d]) % gdim[d];
+      const int wp = gmap[((long)GP[0] * gdim[1] + GP[1]) * gdim[2] + GP[2]];
+      if (wp >= 0) total += std::conj(c1[wp]) * c2[w];
+    }
+  }
+  re_im[0] = total.real();
+  re_im[1] = total.imag();
+}
+
+}  // extern "C"

@@ -596,6 +596,12 @@ void wavecar_bounds(WavecarHeader& h) {
   combo(0, 2, 1, nb[1]);
   combo(2, 1, 0, nb[2]);
   for (int d = 0; d < 3; d++) h.nbmax[d] = std::fmax(nb[0][d], std::fmax(nb[1][d], nb[2][d]));
+  int np = 0;
+  for (int c = 0; c < 3; c++) {
+    const int v = (int)std::round(4.0 / 3.0 * kPi * nb[c][0] * nb[c][1] * nb[c][2]);
+    if (c == 0 || v < np) np = v;
+  }
+  h.npmax = np;
 }
 
 std::vector<int32_t> enumerate_g(const WavecarHeader& h, const double* k, int* Gb) {

@@ -112,6 +112,7 @@ struct WavecarHeader {
   double encut = 0;
   double lattice[9], reclattice[9];
   double nbmax[3];
+  int npmax = 0;        // reader.c:26-57 upper bound on the plane-wave count
 };
 struct KPointInfo {
   int nplane = 0;               // coefficients per band as stored (2*ng for noncollinear)

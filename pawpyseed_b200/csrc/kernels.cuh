@@ -735,6 +735,128 @@ density_accum_il_kernel(const double2* __restrict__ x, long ngrid, int ngroups, 
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// (f4) momentum matrix elements  [momentum.c]
+// ---------------------------------------------------------------------------------------
+struct MomTerm {          // one (radial function, L, M) term of an element: F = f(|G|) * Y_LM(G^) * cfac
+  int slot;               // radial table: data[slot_off] = f[N], then 3N spline coefficients
+  int L, M;
+  int special0;           // value at |G| = 0: 1 -> Y(L,M;0,0) kept (the reference's L==0 && m1==m2 / r==0 rule), 0 -> zero
+};
+struct MomElem {          // per element
+  int nterm, term_off;    // terms of this element in the concatenated term list
+  int N;                  // radial grid size
+  long ks_off;            // offset of the k grid in `radial`
+};
+
+// pseudo part: out[g] = sum_w2 conj(C1[box(G2[w2] + GP_g)]) * C2[w2]   [momentum.c:47-107], one warp per GP.
+__global__ void __launch_bounds__(256)
+momentum_pseudo_kernel(int numg, const int* __restrict__ igall, const float2* __restrict__ C1,
+                       const float2* __restrict__ C2, const int* __restrict__ G2, int npw2,
+                       const int* __restrict__ boxmap, int lo0, int lo1, int lo2, int d0, int d1, int d2,
+                       double2* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (g >= numg) return;
+  const int p0 = igall[3 * g], p1 = igall[3 * g + 1], p2 = igall[3 * g + 2];
+  double re = 0, im = 0;
+  for (int w = lane; w < npw2; w += 32) {
+    const int a = G2[3 * w] + p0 - lo0, b = G2[3 * w + 1] + p1 - lo1, c = G2[3 * w + 2] + p2 - lo2;
+    if (a < 0 || a >= d0 || b < 0 || b >= d1 || c < 0 || c >= d2) continue;
+    const int j = boxmap[(a * d1 + b) * d2 + c];
+    if (j < 0) continue;
+    const float2 x = C1[j], y = C2[w];
+    re += (double)y.x * x.x + (double)y.y * x.y;       // y * conj(x)
+    im += (double)y.y * x.x - (double)y.x * x.y;
+  }
+  for (int o = 16; o; o >>= 1) {
+    re += __shfl_xor_sync(0xffffffffu, re, o);
+    im += __shfl_xor_sync(0xffffffffu, im, o);
+  }
+  if (lane == 0) out[g] = make_double2(re, im);
+}
+
+// out[g] += pref * sum_s exp(sgn 2 pi i GP.R_s) sum_t W[s][t] * F_{elem(s), t}(G),  G = gsign * (GP + dk) in Cartesian
+// One CTA per GP: the F terms of every element are evaluated once into shared memory, then threads run over sites.
+__global__ void __launch_bounds__(128)
+momentum_site_kernel(int numg, const int* __restrict__ igall, double dk0, double dk1, double dk2, double gsign,
+                     const double* __restrict__ recl, int nelem, const MomElem* __restrict__ elems,
+                     const MomTerm* __restrict__ terms, const double* __restrict__ radial,
+                     const long* __restrict__ slot_off, int nsites, const int* __restrict__ site_elem,
+                     const double* __restrict__ coords, const long* __restrict__ w_off,
+                     const double2* __restrict__ W, double phase_sign, double pref, double2* __restrict__ out) {
+  extern __shared__ double2 sF[];                 // all elements' terms
+  __shared__ double red[2][4];
+  const double PI = 3.14159265358979323846;
+  const int g = blockIdx.x;
+  if (g >= numg) return;
+  const double q0 = igall[3 * g], q1 = igall[3 * g + 1], q2 = igall[3 * g + 2];
+  double f[3] = {gsign * (q0 + dk0), gsign * (q1 + dk1), gsign * (q2 + dk2)};
+  double v[3];
+  for (int d = 0; d < 3; d++) v[d] = f[0] * recl[d] + f[1] * recl[3 + d] + f[2] * recl[6 + d];   // frac_to_cartesian
+  const double r = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+  double theta, phi;
+  d_angles(v, r, &theta, &phi);
+  for (int e = 0; e < nelem; e++) {
+    const MomElem me = elems[e];
+    const double* ks = radial + me.ks_off;
+    for (int t = threadIdx.x; t < me.nterm; t += blockDim.x) {
+      const MomTerm mt = terms[me.term_off + t];
+      double2 val = make_double2(0, 0);
+      const int am = mt.M < 0 ? -mt.M : mt.M;
+      if (am <= mt.L && (r != 0 || mt.special0)) {
+        const double* fr = radial + slot_off[mt.slot];
+        const double rad = d_eval_log(r, me.N, ks, fr, fr + me.N);
+        const double2 y = d_ylm(mt.L, mt.M, theta, phi);
+        val = make_double2(rad * y.x, rad * y.y);
+      }
+      sF[me.term_off + t] = val;
+    }
+  }
+  __syncthreads();
+  double re = 0, im = 0;
+  for (int s = threadIdx.x; s < nsites; s += blockDim.x) {
+    const MomElem me = elems[site_elem[s]];
+    const double2* w = W + w_off[s];
+    double ar = 0, ai = 0;
+    for (int t = 0; t < me.nterm; t++) {
+      const double2 a = w[t], b = sF[me.term_off + t];
+      ar += a.x * b.x - a.y * b.y;
+      ai += a.x * b.y + a.y * b.x;
+    }
+    double sn, cs;
+    sincos(phase_sign * 2 * PI * (q0 * coords[3 * s] + q1 * coords[3 * s + 1] + q2 * coords[3 * s + 2]), &sn, &cs);
+    re += ar * cs - ai * sn;
+    im += ar * sn + ai * cs;
+  }
+  for (int o = 16; o; o >>= 1) {
+    re += __shfl_xor_sync(0xffffffffu, re, o);
+    im += __shfl_xor_sync(0xffffffffu, im, o);
+  }
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = re; red[1][threadIdx.x >> 5] = im; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tr = 0, ti = 0;
+    for (int wq = 0; wq < 4; wq++) { tr += red[0][wq]; ti += red[1][wq]; }
+    out[g].x += pref * tr;
+    out[g].y += pref * ti;
+  }
+}
+
+// plane-wave part of fullwf_reciprocal [momentum.c:483-499]: out[g] += C[box(GP_g)] when GP is inside the box
+__global__ void momentum_pick_kernel(int numg, const int* __restrict__ igall, const float2* __restrict__ C,
+                                     const int* __restrict__ boxmap, int lo0, int lo1, int lo2, int d0, int d1,
+                                     int d2, double2* __restrict__ out) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= numg) return;
+  const int a = igall[3 * g] - lo0, b = igall[3 * g + 1] - lo1, c = igall[3 * g + 2] - lo2;
+  if (a < 0 || a >= d0 || b < 0 || b >= d1 || c < 0 || c >= d2) return;
+  const int j = boxmap[(a * d1 + b) * d2 + c];
+  if (j < 0) return;
+  out[g].x += (double)C[j].x;
+  out[g].y += (double)C[j].y;
+}
+
 // (a13) density accumulation  [density.c:170-173, 193-196]:  rho[g] += sum_box w[box] |x_box[g]|^2
 __global__ void __launch_bounds__(256)
 density_accum_kernel(const double2* __restrict__ x, long ngrid, int nbox,

@@ -534,3 +534,75 @@ class CProjector:
             1 if (pseudo_only or not have) else (2 if getattr(self, "_recip", False) else 0))
         check()
         return out
+
+
+class CMomentumMatrix:
+    """pawpyc.pyx:738-807."""
+
+    def __init__(self, wf, encut):
+        self.wf = wf
+        self.momentum_encut = float(encut)
+        self.elem_density_transforms = None
+        self._setup_momentum_grid()
+        self._setup_transforms()
+
+    def __del__(self):
+        try:
+            if getattr(self, "elem_density_transforms", None):
+                _lib.lib().pawb200_free_density_ft_elem_list(self.elem_density_transforms, 0)
+                self.elem_density_transforms = None
+        except Exception:
+            pass
+
+    def _setup_momentum_grid(self):
+        L = _lib.lib()
+        nb = [C.c_double(0), C.c_double(0), C.c_double(0)]
+        npmax = C.c_int(0)
+        L.pawb200_momentum_grid_size(self.wf.wf_ptr, C.byref(nb[0]), C.byref(nb[1]), C.byref(nb[2]),
+                                     C.byref(npmax), self.momentum_encut)
+        check()
+        grid = np.zeros(3 * max(npmax.value, 1), dtype=np.int32)
+        actual_size = L.pawb200_get_momentum_grid(ip(grid), self.wf.wf_ptr, nb[0].value, nb[1].value, nb[2].value,
+                                                  self.momentum_encut)
+        check()
+        self.ggrid = np.ascontiguousarray(grid[:3 * actual_size])
+        self.gbounds = np.zeros(6, dtype=np.int32)
+        self.gdim = np.zeros(3, dtype=np.int32)
+        L.pawb200_grid_bounds(ip(self.gbounds), ip(self.gdim), ip(self.ggrid), actual_size)
+        self.grid3d = -1 * np.ones(int(self.gdim[0]) * int(self.gdim[1]) * int(self.gdim[2]), dtype=np.int32)
+        L.pawb200_list_to_grid_map(ip(self.grid3d), ip(self.gbounds), ip(self.gdim), ip(self.ggrid), actual_size)
+
+    def _setup_transforms(self):
+        self.elem_density_transforms = _lib.lib().pawb200_get_all_transforms(self.wf.wf_ptr, self.momentum_encut)
+        check()
+
+    def _get_ggrid(self):
+        return self.ggrid.copy()
+
+    def _get_momentum_matrix_elems(self, b1, k1, s1, b2, k2, s2):
+        numg = self.ggrid.shape[0] // 3
+        res = np.zeros(numg, dtype=np.complex128)
+        _lib.lib().pawb200_get_momentum_matrix(
+            res.ctypes.data_as(_lib.c_dbl_p), numg, ip(self.ggrid), self.wf.wf_ptr, ip(self.wf.nums),
+            dp(self.wf.coords), int(b1), int(k1), int(s1), int(b2), int(k2), int(s2), self.elem_density_transforms,
+            self.momentum_encut)
+        check()
+        return res
+
+    def _get_reciprocal_fullfw(self, b, k, s):
+        numg = self.ggrid.shape[0] // 3
+        res = np.zeros(numg, dtype=np.complex128)
+        _lib.lib().pawb200_fullwf_reciprocal(res.ctypes.data_as(_lib.c_dbl_p), ip(self.ggrid), self.wf.wf_ptr, numg,
+                                             int(b), int(k + s * self.wf.nwk), ip(self.wf.nums), dp(self.wf.coords))
+        check()
+        return res
+
+    def _get_g_from_fullfw(self, b1, k1, s1, b2, k2, s2, G):
+        vec1 = self._get_reciprocal_fullfw(b1, k1, s1)
+        vec2 = self._get_reciprocal_fullfw(b2, k2, s2)
+        GP = np.array(G, dtype=np.int32)
+        out = np.zeros(2)
+        _lib.lib().pawb200_quick_overlap(ip(GP), vec1.ctypes.data_as(_lib.c_dbl_p), vec2.ctypes.data_as(_lib.c_dbl_p),
+                                         self.ggrid.shape[0] // 3, ip(self.ggrid), ip(self.grid3d), ip(self.gbounds),
+                                         ip(self.gdim), dp(out))
+        return complex(out[0], out[1])

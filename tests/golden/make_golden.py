@@ -1,7 +1,7 @@
 """Generates tests/golden/*.npz from the UNMODIFIED reference C (oracle/_ref/libpawpy_ref.so).
 
 Run in the build container (needs /root/reference for the bundled WAVECARs):
-    python tests/golden/make_golden.py [base] [realspace_proj] [volumetric] [desymm] [aug_recip]    (default: all)
+    python tests/golden/make_golden.py [base] [realspace_proj] [volumetric] [desymm] [aug_recip] [momentum]    (default: all)
 Inputs are (a) the first bands of the reference's own fixtures test_files/WAVECAR,
 WAVECAR2.gz and noncollinear/WAVECAR re-packed into small WAVECAR images, and (b) seeded
 synthetic cells from tests/cases.py.  Every stored output comes from the reference library
@@ -184,8 +184,25 @@ def make_recip():
     np.savez_compressed(os.path.join(HERE, "aug_recip.npz"), cat=np.array(cat, dtype=object), **out)
 
 
+def make_momentum():
+    """MomentumMatrix (momentum.c) on the synthetic two-element cell, encut = 2 * wf.encut: the G grid, matrix elements
+    for same-k and cross-k / cross-spin band pairs, the plane-wave expansion of an AE band and one g_from_wf value."""
+    c = cases.small_case(seed=7, nband=4, encut=120.0)
+    R = rd.RefWavefunction(c["image"], c["kws"])
+    R.setup_projections(c["pps"], c["labels"], c["coords"], c["dim"], c["grid_encut"])
+    mm = rd.RefMomentumMatrix(R, 2 * R.encut)
+    out = dict(ggrid=mm.ggrid, gbounds=mm.gbounds, gdim=mm.gdim, grid3d=mm.grid3d, encut=2 * R.encut)
+    for name, args in (("m_00_00", (0, 0, 0, 0, 0, 0)), ("m_0k0_1k1", (0, 0, 0, 1, 1, 0)), ("m_2k1s1_3k0s1", (2, 1, 1, 3, 0, 1))):
+        out[name] = mm.momentum_matrix_elems(*args)
+    out["full_b1k0s0"] = mm.reciprocal_fullfw(1, 0, 0)
+    out["full_b3k1s1"] = mm.reciprocal_fullfw(3, 1, 1)
+    out["gfrom"] = np.array(mm.g_from_fullfw(0, 0, 0, 1, 1, 0, [1, 0, 0]))
+    R.free()
+    np.savez_compressed(os.path.join(HERE, "momentum.npz"), **out)
+
+
 MAKERS = {"base": make_base, "realspace_proj": make_realspace_proj, "volumetric": make_volumetric,
-          "desymm": make_desymm, "aug_recip": make_recip}
+          "desymm": make_desymm, "aug_recip": make_recip, "momentum": make_momentum}
 
 
 def main():

@@ -330,3 +330,32 @@ def test_aug_recip_site_categories_vs_oracle(gan, cat):
         res = np.zeros(nb * 4, complex)
         pr._projection_recip(res, b, False)
         assert np.abs(res - want[b]).max() < 1e-7 * scale
+
+
+def test_momentum_matrix_vs_reference_and_oracle():
+    # MomentumMatrix (momentum.c).  One-centre terms, the AE plane-wave expansion and the grids are
+    # FP64 -> 1e-10 against the reference C; the plane-wave correlation is a float-complex sum in the reference
+    # (FP64 here), so full matrix elements are compared at FP32 round-off with it and at 1e-10 with the FP64 oracle.
+    g = np.load(os.path.join(G, "momentum.npz"))
+    c = cases.small_case(seed=7, nband=4, encut=120.0)
+    wf = from_case(c)
+    mm = pawpyc.CMomentumMatrix(wf, float(g["encut"]))
+    assert np.array_equal(mm.ggrid, g["ggrid"])                                  # G order: bit-exact
+    assert np.array_equal(mm.gbounds, g["gbounds"]) and np.array_equal(mm.gdim, g["gdim"])
+    assert np.array_equal(mm.grid3d, g["grid3d"])
+    for name, args in (("m_00_00", (0, 0, 0, 0, 0, 0)), ("m_0k0_1k1", (0, 0, 0, 1, 1, 0)),
+                       ("m_2k1s1_3k0s1", (2, 1, 1, 3, 0, 1))):
+        got = mm._get_momentum_matrix_elems(*args)
+        assert np.abs(got - g[name]).max() < 2e-6 * np.abs(g[name]).max()
+    assert rel(mm._get_reciprocal_fullfw(1, 0, 0), g["full_b1k0s0"]) < TOL
+    assert rel(mm._get_reciprocal_fullfw(3, 1, 1), g["full_b3k1s1"]) < TOL
+    assert abs(mm._get_g_from_fullfw(0, 0, 0, 1, 1, 0, [1, 0, 0]) - complex(g["gfrom"])) < 1e-12
+    # FP64 oracle on a sample of the grid
+    o = oracle_wf(c)
+    om = pn.MomentumMatrix(o, float(g["encut"]))
+    sel = list(range(0, len(om.ggrid), 53))
+    om.ggrid = om.ggrid[sel]
+    got = mm._get_momentum_matrix_elems(2, 1, 1, 3, 0, 1)[sel]
+    assert rel(got, om.momentum_matrix_elems(2, 1, 1, 3, 0, 1)) < TOL
+    with pytest.raises(_lib.PAWpyError):
+        mm._get_momentum_matrix_elems(9, 0, 0, 0, 0, 0)

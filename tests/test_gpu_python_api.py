@@ -174,3 +174,19 @@ def test_density_band_shards_sum_to_full_density(pair):
     assert rel(sum(parts), full) < 1e-13
     assert np.abs(parts[0]).max() > 0 and np.abs(parts[1]).max() > 0       # the occupied half is split over two shards
     assert pdist.sharded_chg_density(basis).shape == full.shape            # no process group: plain call
+
+
+def test_momentum_matrix_class(pair):
+    # momentum.py:4-91 through the public class; self matrix element at G = 0 is the AE norm of the band
+    from pawpyseed_b200 import MomentumMatrix
+    basis = pair[2]
+    mm = MomentumMatrix(basis, encut=1.5 * basis.encut)
+    grid = mm.momentum_grid
+    assert grid.shape[1] == 3 and (grid[0] == 0).all()
+    res = mm.get_momentum_matrix_elems(0, 0, 0, 0, 0, 0)
+    assert res.shape == (grid.shape[0],) and abs(res[0].imag) < 1e-12 and res[0].real > 0
+    full = mm.get_reciprocal_fullfw(0, 0, 0)
+    assert full.shape == res.shape
+    assert abs(mm.g_from_wf(0, 0, 0, 0, 0, 0, [0, 0, 0]).imag) < 1e-12
+    with pytest.raises(ValueError):
+        mm.get_momentum_matrix_elems(99, 0, 0, 0, 0, 0)

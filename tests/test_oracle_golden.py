@@ -164,3 +164,22 @@ def test_aug_recip_restatement_vs_reference():
         for flip in (0, 1):
             got = pr.compensation_terms_recip(b, bool(flip))
             assert np.abs(got - g["aug_f%d" % flip][b]).max() < 5e-6 * scale
+
+
+def test_momentum_matrix_restatement_vs_reference():
+    # MomentumMatrix (momentum.c); golden from the reference C.  The plane-wave correlation is a
+    # float-complex sum there, so matrix elements agree to FP32 round-off; everything else is FP64.
+    g = np.load(os.path.join(G, "momentum.npz"))
+    c = cases.small_case(seed=7, nband=4, encut=120.0)
+    o = pn.Wavefunction.from_image(c["image"], c["kws"])
+    o.setup_projections(c["pps"], c["labels"], c["coords"], c["dim"], c["grid_encut"])
+    mm = pn.MomentumMatrix(o, float(g["encut"]))
+    assert np.array_equal(mm.ggrid.reshape(-1), g["ggrid"])
+    assert np.array_equal(mm.gbounds, g["gbounds"]) and np.array_equal(mm.gdim, g["gdim"])
+    sel = list(range(0, len(mm.ggrid), 37))                    # the pure-python loops are slow: sample the grid
+    saved = mm.ggrid
+    mm.ggrid = saved[sel]
+    got = mm.momentum_matrix_elems(0, 0, 0, 1, 1, 0)
+    assert np.abs(got - g["m_0k0_1k1"][sel]).max() < 2e-6 * np.abs(g["m_0k0_1k1"]).max()
+    full = mm.reciprocal_fullfw(1, 0, 0)
+    assert rel(full, g["full_b1k0s0"][sel]) < TOL
