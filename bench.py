@@ -235,6 +235,32 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def bind_to_gpu_numa_node(gpu_index, world):
+    """Pin this rank's threads to a slice of the CPUs NVML reports as local to its GPU, so the pinned WAVECAR
+    images are first-touched on that NUMA node and eight ranks do not pull their H2D traffic across sockets."""
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(gpu_index).uuid)
+        handle = None
+        for i in range(pynvml.nvmlDeviceGetCount()):
+            h = pynvml.nvmlDeviceGetHandleByIndex(i)
+            u = pynvml.nvmlDeviceGetUUID(h)
+            if uuid in (u.decode() if isinstance(u, bytes) else u):
+                handle = h
+        if handle is None:
+            return
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (ncpu + 63) // 64)
+        cpus = [64 * wi + b for wi, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1]
+        allowed = sorted(set(cpus) & os.sched_getaffinity(0))
+        if len(allowed) >= 2:
+            os.sched_setaffinity(0, allowed)
+    except Exception:
+        pass
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -249,6 +275,7 @@ def run_b200(args):
         raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (N, world))
     torch.cuda.set_device(local)
     if world > 1:
+        bind_to_gpu_numa_node(local, world)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     L = _lib.lib()
     if L.pawb200_device_check() != 0:
