@@ -145,3 +145,31 @@ def test_write_volumetric_matches_reference_text(tmp_path):
     _lib.lib().pawb200_write_volumetric(fn.encode(), _lib.dp(x), _lib.ip(dim), float(g["scale"]))
     _lib.check()
     assert open(fn).read() == str(g["text"])
+
+
+def test_momentum_grid_helpers_vs_reference_golden():
+    # host-side pieces of MomentumMatrix (momentum.c:365-400, 547-574) need no GPU: compare with the reference's
+    # own outputs stored in tests/golden/momentum.npz
+    g = np.load(os.path.join(cases.GOLDEN, "momentum.npz"))
+    L = _lib.lib()
+    ggrid = np.ascontiguousarray(g["ggrid"], dtype=np.int32)
+    n = len(ggrid) // 3
+    gb, gd = np.zeros(6, np.int32), np.zeros(3, np.int32)
+    L.pawb200_grid_bounds(_lib.ip(gb), _lib.ip(gd), _lib.ip(ggrid), n)
+    assert np.array_equal(gb, g["gbounds"]) and np.array_equal(gd, g["gdim"])
+    grid3d = -np.ones(int(np.prod(gd)), dtype=np.int32)
+    L.pawb200_list_to_grid_map(_lib.ip(grid3d), _lib.ip(gb), _lib.ip(gd), _lib.ip(ggrid), n)
+    assert np.array_equal(grid3d, g["grid3d"])
+    # quick_overlap of two stored AE expansions against a direct evaluation
+    v1, v2 = np.ascontiguousarray(g["full_b1k0s0"]), np.ascontiguousarray(g["full_b3k1s1"])
+    dG = np.array([1, 0, -1], np.int32)
+    out = np.zeros(2)
+    L.pawb200_quick_overlap(_lib.ip(dG), v1.ctypes.data_as(_lib.c_dbl_p), v2.ctypes.data_as(_lib.c_dbl_p), n,
+                            _lib.ip(ggrid), _lib.ip(grid3d), _lib.ip(gb), _lib.ip(gd), _lib.dp(out))
+    look = {tuple(v): i for i, v in enumerate(ggrid.reshape(-1, 3).tolist())}
+    want = 0j
+    for w, v in enumerate(ggrid.reshape(-1, 3).tolist()):
+        q = (v[0] + 1, v[1], v[2] - 1)
+        if q in look and gb[0] <= q[0] <= gb[1] and gb[2] <= q[1] <= gb[3] and gb[4] <= q[2] <= gb[5]:
+            want += np.conj(v1[look[q]]) * v2[w]
+    assert abs(complex(out[0], out[1]) - want) < 1e-14
