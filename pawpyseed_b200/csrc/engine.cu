@@ -484,7 +484,7 @@ std::unique_ptr<SiteTables> build_site_tables(const std::vector<Element>& els, c
       const int ndiv = els[labels[s]].proj_gridsize;
       radius = (el.proj_gridsize - 1) * rmax / ndiv;
     }
-    geom[s] = sphere_geometry(coords + 3 * p, lattice, fftg, rmax, radius, mode == 2);
+    geom[s] = sphere_geometry(coords + 3 * p, lattice, fftg, rmax, radius);
   }
   delete hs_geom;
   long pt = 0, tab = 0;
@@ -509,24 +509,15 @@ std::unique_ptr<SiteTables> build_site_tables(const std::vector<Element>& els, c
   T->total_pts = pt;
   T->total_tab = tab;
   T->nproj = lm;
-  // pack index / path (/ wrap) arrays straight into pinned staging memory, in parallel over sites
+  // The host only ships the unwrapped grid coordinates of the selected points (8 B per point, packed straight into
+  // pinned staging memory in parallel over sites); expand_geometry_kernel rebuilds index, offsets and cell shifts.
   const size_t npt = (size_t)std::max<long>(pt, 1);
-  // one arena block for all three arrays (a later take() may recycle the arena)
-  unsigned char* blk = (unsigned char*)g_arena.take(npt * (3 * sizeof(double) + 4 * sizeof(int32_t)));
-  double* path = (double*)blk;
-  int32_t* idx = (int32_t*)(blk + 3 * npt * sizeof(double));
-  int32_t* wrap = mode == 2 ? idx + npt : nullptr;
+  int16_t* ijk = (int16_t*)g_arena.take(npt * 4 * sizeof(int16_t));
 #pragma omp parallel for schedule(dynamic)
   for (int s = 0; s < nlist; s++) {
     const SiteDev& sd = T->host[s];
-    for (int q = 0; q < sd.npts_pad; q++) {
-      const bool real = q < sd.npts;
-      idx[sd.pt_off + q] = real ? geom[s].index[q] : 0;
-      for (int d = 0; d < 3; d++) {
-        path[d * pt + sd.pt_off + q] = real ? geom[s].path[3 * q + d] : 0.0;
-        if (wrap) wrap[d * pt + sd.pt_off + q] = real ? geom[s].wrap[3 * q + d] : 0;
-      }
-    }
+    if (sd.npts) memcpy(ijk + 4 * sd.pt_off, geom[s].ijk.data(), (size_t)sd.npts * 4 * sizeof(int16_t));
+    memset(ijk + 4 * (sd.pt_off + sd.npts), 0, (size_t)(sd.npts_pad - sd.npts) * 4 * sizeof(int16_t));
   }
   if (keep_host_idx) {
     T->host_idx.resize(nlist);
@@ -534,12 +525,23 @@ std::unique_ptr<SiteTables> build_site_tables(const std::vector<Element>& els, c
   }
   T->sites = upload(T->host);
   T->idx.alloc(npt * sizeof(int32_t));
-  fetch_pinned(T->idx.p, idx, npt * sizeof(int32_t), g_stream);
   T->path.alloc(3 * npt * sizeof(double));
-  fetch_pinned(T->path.p, path, 3 * npt * sizeof(double), g_stream);
-  if (wrap) {
-    T->wrap.alloc(3 * npt * sizeof(int32_t));
-    fetch_pinned(T->wrap.p, wrap, 3 * npt * sizeof(int32_t), g_stream);
+  if (mode == 2) T->wrap.alloc(3 * npt * sizeof(int32_t));
+  {
+    DevBuf dijk(npt * 4 * sizeof(int16_t));
+    fetch_pinned(dijk.p, ijk, npt * 4 * sizeof(int16_t), g_stream);
+    int maxpad = 0;
+    for (auto& sd : T->host) maxpad = std::max(maxpad, sd.npts_pad);
+    if (nlist > 0 && maxpad > 0) {
+      Lattice9 L9;
+      for (int i = 0; i < 9; i++) L9.a[i] = lattice[i];
+      dim3 grid((maxpad + 255) / 256, nlist);
+      expand_geometry_kernel<<<grid, 256, 0, g_stream>>>(T->sites.as<SiteDev>(), dijk.as<short4>(), L9, fftg[0], fftg[1],
+                                                         fftg[2], T->idx.as<int>(), T->path.as<double>(),
+                                                         mode == 2 ? T->wrap.as<int>() : nullptr, (long)pt);
+      count_launch();
+      check_launch();
+    }
   }
   T->table.alloc(std::max<size_t>(1, tab) * sizeof(double2));
   T->by_mt.assign(4, {});

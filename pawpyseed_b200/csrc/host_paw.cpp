@@ -413,7 +413,7 @@ std::vector<Element> build_elements(int num_els, const int* labels, const int* l
 // sphere geometry
 // ---------------------------------------------------------------------------------------
 SphereGeom sphere_geometry(const double* coord, const double* L, const int* fftg,
-                           double rmax_box, double radius_test, bool want_wrap) {
+                           double rmax_box, double radius_test) {
   SphereGeom g;
   const double vol = determinant3(L);
   double res[3];
@@ -432,8 +432,7 @@ SphereGeom sphere_geometry(const double* coord, const double* L, const int* fftg
     const double dv = std::fabs(vol) / ((double)N0 * N1 * N2);
     const size_t guess = (size_t)(4.19 * radius_test * radius_test * radius_test / dv * 1.15) + 64;
     g.index.reserve(guess);
-    g.path.reserve(3 * guess);
-    if (want_wrap) g.wrap.reserve(3 * guess);
+    g.ijk.reserve(4 * guess);
   }
   // per-axis fractional offsets of the box (exactly (double)i / N - coord like utils.c:656-658)
   std::vector<double> tz(2 * half[2] + 1);
@@ -467,15 +466,10 @@ SphereGeom sphere_geometry(const double* coord, const double* L, const int* fftg
           inside = std::pow(d2, 0.5) < radius_test;
         if (inside) {
           g.index.push_back(rowbase + kz[q]);
-          g.path.push_back(x);
-          g.path.push_back(y);
-          g.path.push_back(z);
-          if (want_wrap) {
-            const int k = -half[2] + cen[2] + q;
-            g.wrap.push_back((ii - i) / N0);
-            g.wrap.push_back((jj - j) / N1);
-            g.wrap.push_back((kz[q] - k) / N2);
-          }
+          g.ijk.push_back((int16_t)i);
+          g.ijk.push_back((int16_t)j);
+          g.ijk.push_back((int16_t)(-half[2] + cen[2] + q));
+          g.ijk.push_back(0);
         }
       }
     }

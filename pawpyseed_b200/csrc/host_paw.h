@@ -91,12 +91,12 @@ std::vector<Element> build_elements(int num_els, const int* labels, const int* l
 // ---- sphere geometry (utils.c:636-671; density.c:262-296) ------------------------------------
 struct SphereGeom {
   std::vector<int32_t> index;     // wrapped linear grid index, ascending (i,j,k) box order
-  std::vector<double> path;       // 3 per point: Cartesian offset from the atom
-  std::vector<int32_t> wrap;      // 3 per point: (ii-i)/N integer cell shifts (density.c:293-295)
+  std::vector<int16_t> ijk;       // 4 per point: unwrapped grid coordinates (i, j, k, 0) - the device rebuilds the
+                                  // Cartesian offset, the wrapped index and the cell shifts from them
 };
 // radius_test: points with |r| < radius_test are kept; box from rmax_box.
 SphereGeom sphere_geometry(const double* coord, const double* lattice, const int* fftg,
-                           double rmax_box, double radius_test, bool want_wrap);
+                           double rmax_box, double radius_test);
 
 // ---- off-site partial-wave overlap (radial.c:116-196, SBTFACS regenerated) ----------------
 double wigner3j(int j1, int j2, int j3, int m1, int m2, int m3);

@@ -231,6 +231,41 @@ struct SiteDev {            // per site in a table set
   double coord[3];          // fractional position of the atom
 };
 
+// Sphere geometry on the device from the unwrapped grid coordinates the host selected (bit-exact membership):
+//   path = frac_to_cartesian((i/N0, j/N1, k/N2) - coord)  with the operation order of utils.c:656-660 and no FMA
+//          contraction, so it equals the host / reference value bit for bit;
+//   idx  = wrapped linear index;  wrap = (wrapped - unwrapped) / N  integer cell shifts (density.c:293-295).
+// Uploading 8 bytes per point instead of 28-40 keeps the setup off the PCIe critical path.
+struct Lattice9 { double a[9]; };
+__global__ void __launch_bounds__(256)
+expand_geometry_kernel(const SiteDev* __restrict__ sites, const short4* __restrict__ ijk, Lattice9 L, int n0, int n1,
+                       int n2, int* __restrict__ idx, double* __restrict__ path, int* __restrict__ wrap, long ld) {
+  const SiteDev sd = sites[blockIdx.y];
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < sd.npts_pad; p += gridDim.x * blockDim.x) {
+    const long q = sd.pt_off + p;
+    if (p >= sd.npts) {
+      idx[q] = 0;
+      path[q] = path[ld + q] = path[2 * ld + q] = 0.0;
+      if (wrap) wrap[q] = wrap[ld + q] = wrap[2 * ld + q] = 0;
+      continue;
+    }
+    const short4 v = ijk[q];
+    const int i = v.x, j = v.y, k = v.z;
+    const double t0 = __dsub_rn(__ddiv_rn((double)i, (double)n0), sd.coord[0]);
+    const double t1 = __dsub_rn(__ddiv_rn((double)j, (double)n1), sd.coord[1]);
+    const double t2 = __dsub_rn(__ddiv_rn((double)k, (double)n2), sd.coord[2]);
+    for (int d = 0; d < 3; d++)
+      path[d * ld + q] = __dadd_rn(__dadd_rn(__dmul_rn(t0, L.a[d]), __dmul_rn(t1, L.a[3 + d])), __dmul_rn(t2, L.a[6 + d]));
+    const int ii = (i % n0 + n0) % n0, jj = (j % n1 + n1) % n1, kk = (k % n2 + n2) % n2;
+    idx[q] = (ii * n1 + jj) * n2 + kk;
+    if (wrap) {
+      wrap[q] = (ii - i) / n0;
+      wrap[ld + q] = (jj - j) / n1;
+      wrap[2 * ld + q] = (kk - k) / n2;
+    }
+  }
+}
+
 // mode 0: linear-grid radial function (projector or filtered phi-phit), value = R(r) Y_lm,
 //         r from the minimum-image path of the wrapped grid point (utils.c:566-588)
 // mode 1: log-grid partial wave difference, value = R(r)/r Y_lm from the direct offset
