@@ -173,7 +173,14 @@ _pinned_free = {}   # nbytes -> [ptr]: page-locked blocks are recycled (cudaMall
 
 
 def _pinned_release(nbytes, ptr):
-    _pinned_free.setdefault(nbytes, []).append(ptr)
+    cached = _pinned_free.setdefault(nbytes, [])
+    if len(cached) < 4:
+        cached.append(ptr)          # recycled by the next result of this size
+    else:
+        try:
+            lib().pawb200_free_pinned(ptr)
+        except Exception:
+            pass
 
 
 def pinned_empty(shape, dtype):
