@@ -190,3 +190,26 @@ def test_momentum_matrix_class(pair):
     assert abs(mm.g_from_wf(0, 0, 0, 0, 0, 0, [0, 0, 0]).imag) < 1e-12
     with pytest.raises(ValueError):
         mm.get_momentum_matrix_elems(99, 0, 0, 0, 0, 0)
+
+
+def test_wavecar_file_and_gz_ingest_match_memory_image(tmp_path):
+    # the reference's test_projector_gz / PWFPointer(filename) path (pawpyc.pyx:217-224): plain file through the
+    # staged reader, .gz through the in-memory reader; 40 bands = two ingest chunks per (k,spin) block
+    import gzip
+    from pawpyseed_b200 import pawpyc
+    c = cases.small_case(seed=13, nband=40)
+    plain = tmp_path / "WAVECAR"
+    plain.write_bytes(c["image"].tobytes())
+    gz = tmp_path / "WAVECAR2.gz"
+    with gzip.open(gz, "wb") as f:
+        f.write(c["image"].tobytes())
+    mem = pawpyc.CWavefunction(pawpyc.PWFPointer.from_arrays(c["image"], c["kpts"], c["kws"]))
+    for src in (str(plain), str(gz)):
+        wf = pawpyc.CWavefunction(pawpyc.PWFPointer.from_arrays(src, c["kpts"], c["kws"]))
+        assert (wf.nband, wf.nwk, wf.nspin, wf.ncl) == (40, 2, 2, False) and wf.encut == mem.encut
+        for kap in range(4):
+            for b in (0, 31, 32, 39):
+                assert np.array_equal(wf._get_coefficients(b, kap), mem._get_coefficients(b, kap))
+        assert np.array_equal(wf._get_occs(), mem._get_occs())
+    with pytest.raises(PAWpyError):
+        pawpyc.PWFPointer.from_arrays(str(tmp_path / "missing"), c["kpts"], c["kws"])
