@@ -14,8 +14,9 @@ from .utils import PAWpyError, el
 class Projector(pawpyc.CProjector):
     METHODS = ["pseudo", "realspace", "aug_recip", "aug_real"]
 
-    def __init__(self, wf, basis, unsym_basis=False, unsym_wf=False, method="aug_real"):
-        """projector.py:42-113."""
+    def __init__(self, wf, basis, unsym_basis=False, unsym_wf=False, method="aug_real", symmops=None):
+        """projector.py:42-113.  `symmops` (extension): space-group operators in reciprocal fractional coordinates
+        for the unsym_* options, instead of the pymatgen space-group search (see symmetry.get_symmops)."""
         self.method = method
         if self.method == "pseudo":
             self._single_band_projection = self._single_band_projection_pseudo
@@ -31,16 +32,16 @@ class Projector(pawpyc.CProjector):
             raise PAWpyError("Projection not supported for noncollinear case!")
         # projector.py:77-95: bring both onto one unreduced mesh (GPU remap, pawb200_expand_symm_wf)
         if unsym_basis and unsym_wf:
-            basis = basis.desymmetrized_copy()
-            wf = wf.desymmetrized_copy(basis.kpts, basis.kws)
+            basis = basis.desymmetrized_copy(symmops=symmops)
+            wf = wf.desymmetrized_copy(basis.kpts, basis.kws, symmops=symmops)
         elif unsym_wf:
             if basis.kpts.shape[0] < wf.kpts.shape[0]:
                 raise PAWpyError("Basis doesn't have enough kpoints, needs to be desymmetrized!")
-            wf = wf.desymmetrized_copy(basis.kpts, basis.kws)
+            wf = wf.desymmetrized_copy(basis.kpts, basis.kws, symmops=symmops)
         elif unsym_basis:
             if wf.kpts.shape[0] < basis.kpts.shape[0]:
                 raise PAWpyError("Defect doesn't have enough kpoints, needs to be desymmetrized!")
-            basis = basis.desymmetrized_copy(wf.kpts, wf.kws)
+            basis = basis.desymmetrized_copy(wf.kpts, wf.kws, symmops=symmops)
         if basis.kpts.shape != wf.kpts.shape:
             raise PAWpyError("k-point grids for projection are not matched.")
         if np.linalg.norm(basis.kpts - wf.kpts) > 1e-10:

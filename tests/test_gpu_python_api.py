@@ -213,3 +213,28 @@ def test_wavecar_file_and_gz_ingest_match_memory_image(tmp_path):
         assert np.array_equal(wf._get_occs(), mem._get_occs())
     with pytest.raises(PAWpyError):
         pawpyc.PWFPointer.from_arrays(str(tmp_path / "missing"), c["kpts"], c["kws"])
+
+
+def test_projector_with_desymmetrised_pair():
+    # projector.py:77-95: unsym_basis + unsym_wf bring both onto the unreduced mesh (GPU remap), then the usual
+    # PAW-corrected projection; oracle = numpy expand_symm_wf + numpy Projector with the same mapping
+    from pawpyseed_b200 import symmetry
+    cR, cS = cases.desymm_case(seed=21), cases.desymm_case(seed=22)
+    sym = ["Ga", "N", "Ga", "N"]
+    basis, wf = build(cR, sym), build(cS, sym)
+    ops = [symmetry.SymmOp(m) for m in cases.cubic_point_group()]
+    pr = Projector(wf, basis, unsym_basis=True, unsym_wf=True, symmops=ops)
+    assert pr.basis.nwk == pr.wf.nwk == 14 and np.allclose(pr.basis.kpts, pr.wf.kpts)
+    allk, orig, opn, _, trs = symmetry.get_nosym_kpoints(cR["kpts"], symmops=ops)
+    o_ops, o_drs = symmetry.make_c_ops(opn, ops)
+    exp = []
+    for c in (cR, cS):
+        w = pn.Wavefunction.from_image(c["image"], c["kws"])
+        e = pn.expand_symm_wf(w, orig, o_ops.reshape(-1, 3, 3), o_drs.reshape(-1, 3), pr.basis.kws, trs)
+        e.setup_projections(c["pps"], c["labels"], c["coords"], c["dim"], c["grid_encut"])
+        exp.append(e)
+    opr = pn.Projector(exp[1], exp[0], pr.site_cat)
+    want = opr.single_band_projection(1)
+    got = pr.single_band_projection(1)
+    # coefficients of the expanded sets carry complex64 phase factors whose last bit may differ between numpy and libm
+    assert np.abs(got - want).max() < 5e-6 * np.abs(want).max()
