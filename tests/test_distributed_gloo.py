@@ -18,6 +18,19 @@ def _free_port():
     return p
 
 
+class _FakeWavefunction:
+    """Stands in for a CWavefunction in the CPU test of the band-split density reduction: band b contributes
+    (b + 1) * pattern to the grid, so the exact sum over all bands is known."""
+    nband = 7
+    pattern = np.arange(24, dtype=np.float64).reshape(2, 3, 4) + 1.0
+
+    def _get_realspace_density_shard(self, lo, hi):
+        return sum((b + 1) * self.pattern for b in range(lo, hi)) if hi > lo else np.zeros_like(self.pattern)
+
+    def _get_realspace_density(self):
+        return self._get_realspace_density_shard(0, self.nband)
+
+
 def _worker(rank, world, port, nk, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -30,7 +43,10 @@ def _worker(rank, world, port, nk, q):
     got = pd.gather_blocks(local)
     got2 = pd.all_gather_own_blocks(full[own], own, nk)
     tmax = pd.max_over_ranks(float(rank + 1))
-    q.put((rank, bool(np.array_equal(got, full) and np.array_equal(got2, full)), tmax, own))
+    fake = _FakeWavefunction()
+    dens = pd.sharded_chg_density(fake)                       # bands split 4 + 3, one all-reduce
+    dens_ok = bool(np.allclose(dens, fake._get_realspace_density(), rtol=0, atol=1e-12))
+    q.put((rank, bool(np.array_equal(got, full) and np.array_equal(got2, full) and dens_ok), tmax, own))
     dist.destroy_process_group()
 
 
