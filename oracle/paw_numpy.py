@@ -5,10 +5,10 @@ and bench.py's cpu_baseline / --impl reference legs may import it.  The product
 (pawpyseed_b200/) never does.
 
 Every function cites the reference file:line (relative to /root/reference/pawpyseed/core)
-whose arithmetic it restates.  Pinning: tests/test_oracle_vs_ref.py checks this module
+whose arithmetic it restates.  Pinning: tests/test_oracle_vs_ref.py checks this module live
 against oracle/_ref/libpawpy_ref.so (the unmodified reference C built by oracle/Makefile)
-and against the committed fixtures under tests/golden/ generated from that library
-(tests/golden/make_golden.py).
+and tests/test_oracle_golden.py against the committed fixtures under tests/golden/ generated
+from that library (tests/golden/make_golden.py).
 
 One deliberate divergence, stated in DESIGN.md: `pseudoprojection` here accumulates
 in FP64; the reference accumulates and returns single precision (pseudoprojector.c:86).
