@@ -668,7 +668,7 @@ struct ByteSource {
   }
 };
 
-// Staging ring for raw WAVECAR records.  Copies and the column permutation run on their own stream in band
+// Staging ring for raw WAVECAR records.  Copies and the column permutation run on their own streams in band
 // chunks; each chunk records an event that the consumers of those bands (FFT / scatter / GEMM launches on the
 // main stream) wait on.  The H2D of a wavefunction therefore overlaps both the kernels of the previous
 // wavefunction and - with pawb200_set_async_ingest(1) - its own transform pipeline.
@@ -830,8 +830,8 @@ pawb200_pswf* ingest(ByteSource src, const double* kws) {
       src.read(stage, (base + 1) * hd.nrecl, need);
       from = stage;
     }
-    // raw records -> HBM in band chunks on the copy stream, each followed by its column permutation into
-    // box order; consumers wait on the per-chunk events (wait_coeffs)
+    // raw records -> HBM in band chunks on the copy stream; the unpack stream permutes each chunk into box order
+    // and writes its interleaved copy; consumers wait on the per-chunk events (wait_coeffs)
     {
       wf->perm_dev[kap] = upload(kp.perm, ring.unpack, true);
       alloc_interleaved(wf.get(), kap, ring.unpack);
