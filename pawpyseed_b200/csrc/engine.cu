@@ -1245,8 +1245,10 @@ void pruned_fft(const pawb200_pswf* wf, int kap, const PrunedPlan& P, int slot0,
   const long ngrid = (long)g.n1 * g.n2 * g.n3;
   const size_t t1_grp = (size_t)g.ncol * g.n3 * FFT_B * sizeof(double2);
   const size_t t2_grp = (size_t)g.nplane * g.n2 * g.n3 * FFT_B * sizeof(double2);
-  // groups per launch: scratch kept small so pass outputs tend to stay in the 126 MB L2
-  int gc = 4;
+  // groups per launch: measured on config 2 (fft ms per step) 2: 11.8, 4: 10.8, 8: 10.3, 16: 10.1, all 38: 10.0 -
+  // fewer, longer persistent launches win over L2 residency of the scratch.  8 groups = 128 bands is also one ingest
+  // chunk, so a launch never waits for more than the chunk it needs.
+  int gc = 8;
   if (const char* e = getenv("PAWB200_FFT_GROUPS")) gc = std::max(1, atoi(e));
   gc = std::min(gc, ngroups);
   g_fft_t1.ensure(t1_grp * gc);
