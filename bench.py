@@ -354,18 +354,24 @@ def run_b200(args):
     del basis, wf
     e2e_steps = max(1, min(args.steps, 3))
     L.pawb200_set_async_ingest(1)   # the pinned images outlive the wavefunctions; H2D overlaps the transforms
-    barrier()
-    f0, f1 = torch.cuda.Event(True), torch.cuda.Event(True)
-    f0.record()
-    for _ in range(e2e_steps):
+    def e2e_step():
         # the reference flow Wavefunction(..., setup_projectors=True) for basis then wf, then Projector(wf, basis):
         # the second WAVECAR's H2D (copy stream) overlaps the first structure's kernels
         basis = read(0)
         setup(basis, 0)
         wf = read(1)
         setup(wf, 1)
-        res2 = hot_path(basis, wf, do_setup=False)
+        out = hot_path(basis, wf, do_setup=False)
         del basis, wf
+        return out
+
+    if args.warmup > 0:
+        e2e_step()      # one untimed pass: side-stream / staging buffers of the asynchronous path are created here
+    barrier()
+    f0, f1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    f0.record()
+    for _ in range(e2e_steps):
+        res2 = e2e_step()
     f1.record()
     barrier()
     ms2 = torch.tensor([f0.elapsed_time(f1)], dtype=torch.float64, device="cuda")
