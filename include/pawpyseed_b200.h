@@ -208,6 +208,15 @@ void pawb200_projection_matrix(pawb200_c128 *out, pawb200_pswf_t *wf_S, pawb200_
                                const int *M_R, const int *M_S, const int *N_R, const int *N_S,
                                const int *N_RS_R, const int *N_RS_S, int flip_spin,
                                int kappa_lo, int kappa_hi, int pseudo_only);
+/* Same blocks written to DEVICE memory owned by the caller, out_dev[kappa - kappa_lo][b_S][b_R] (complex128).
+ * Kernels are queued on the library's main stream (the CUDA legacy default stream) and the call returns without
+ * synchronising: a collective the caller launches on that stream afterwards - the NCCL all-gather of the per-k
+ * matrices - needs no host round trip.  Blocks not resident on this rank are zero-filled. */
+void pawb200_projection_matrix_dev(void *out_dev, pawb200_pswf_t *wf_S, pawb200_pswf_t *wf_R,
+                                   int num_M, int num_N_R, int num_N_S, int num_N_RS,
+                                   const int *M_R, const int *M_S, const int *N_R, const int *N_S,
+                                   const int *N_RS_R, const int *N_RS_S, int flip_spin,
+                                   int kappa_lo, int kappa_hi, int pseudo_only);
 /* Band shard of pawb200_ae_chg_density: occupied bands in [band_lo, band_hi) only, same weights; += into P.
  * Ranks that hold the same wavefunction split the bands and all-reduce their grids (distributed.py). */
 void pawb200_ae_chg_density_bands(double *P, pawb200_pswf_t *wf, const int *fftg, const int *labels,

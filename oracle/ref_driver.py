@@ -324,7 +324,20 @@ class RefWavefunction:
         fn(_dp(res), self.ptr, _ip(fd), _ip(self.nums), _dp(self.coords))
         return res.reshape(tuple(fd))
 
-    def site_tables(self, which="proj", site_list=None):
+    def time_projector_values(self):
+        """Wall time of the reference's serial per-site table build (`projector_values` -> `setup_site`,
+        projector.c:193-208, utils.c:590-696) for the sites given to setup_projections; the tables are freed."""
+        import time
+        L = lib()
+        w = self.ptr.contents
+        t0 = time.perf_counter()
+        sp = L.projector_values(self.num_sites, _ip(self.nums), _dp(self.coords), w.lattice, w.reclattice,
+                                self.pps_ptr, _ip(self.dimv))
+        dt = time.perf_counter() - t0
+        L.free_real_proj_site_list(sp, self.num_sites)
+        return dt
+
+    def site_tables(self, which="proj", site_list=None, indices_only=False):
         """projector_values / smooth_pw_values (projector.c:193-221) -> python lists."""
         L = lib()
         w = self.ptr.contents
@@ -344,6 +357,9 @@ class RefWavefunction:
             st = sp[s]
             n = st.num_indices
             idx = np.ctypeslib.as_array(st.indices, shape=(n,)).copy()
+            if indices_only:
+                out.append(dict(indices=idx))
+                continue
             paths = np.ctypeslib.as_array(st.paths, shape=(n, 3)).copy()
             vals = np.stack([np.ctypeslib.as_array(st.projs[p].values, shape=(2 * n,)).copy()
                              .view(np.complex128) for p in range(st.total_projs)]) \

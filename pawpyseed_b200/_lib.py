@@ -109,6 +109,8 @@ _SIGS = {
     "pawb200_quick_overlap": (None, [c_int_p, c_dbl_p, c_dbl_p, C.c_int, c_int_p, c_int_p, c_int_p, c_int_p, c_dbl_p]),
     "pawb200_projection_matrix": (None, [c_dbl_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                          C.c_int] + [c_int_p] * 6 + [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "pawb200_projection_matrix_dev": (None, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                             C.c_int] + [c_int_p] * 6 + [C.c_int, C.c_int, C.c_int, C.c_int]),
     "pawb200_set_kappa_range": (None, [C.c_void_p, C.c_int, C.c_int]),
     "pawb200_set_read_shard": (None, [C.c_int, C.c_int]),
     "pawb200_set_host_threads": (None, [C.c_int]),

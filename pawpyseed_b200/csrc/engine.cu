@@ -15,6 +15,7 @@
 #include <unordered_map>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -55,7 +56,12 @@ void set_error(const std::string& m) {
       throw std::runtime_error("cuFFT error " + std::to_string((int)r_) + " at " + __FILE__ + \
                                ":" + std::to_string(__LINE__));                             \
   } while (0)
+// The engine is not re-entrant (one main stream, shared scratch, stream-ordered pools): every C-ABI entry point
+// that touches device state is serialised on one process-wide lock, so Python threads that call in with the
+// GIL released queue up instead of corrupting each other's buffers.
+std::recursive_mutex g_api_mutex;
 #define API_BEGIN \
+  std::lock_guard<std::recursive_mutex> api_lock_(g_api_mutex); \
   g_has_error = false; \
   try {
 #define API_END(ret)                      \
@@ -70,6 +76,17 @@ void set_error(const std::string& m) {
     set_error(e.what());                  \
     return;                               \
   }
+
+// Exceptions must not leave an OpenMP region (std::terminate): loop bodies run through OmpErr::run, the first
+// exception is kept and rethrown after the loop.
+struct OmpErr {
+  std::exception_ptr e;
+  std::atomic<bool> has{false};
+  template <class F> void run(F&& f) noexcept {
+    try { f(); } catch (...) { if (!has.exchange(true)) e = std::current_exception(); }
+  }
+  void rethrow() { if (has) std::rethrow_exception(e); }
+};
 
 cudaStream_t g_stream = 0;   // legacy default stream: ordered with torch's default stream
 std::atomic<long long> g_launches{0};
@@ -473,8 +490,9 @@ std::unique_ptr<SiteTables> build_site_tables(const std::vector<Element>& els, c
   T->site_id.assign(site_list, site_list + nlist);
   std::vector<SphereGeom> geom(nlist);
   auto* hs_geom = new HostSection("  sphere_geometry");
+  OmpErr oe;
 #pragma omp parallel for schedule(dynamic)
-  for (int s = 0; s < nlist; s++) {
+  for (int s = 0; s < nlist; s++) oe.run([&] {
     const int p = site_list[s];
     const Element& el = els[labels[p]];
     const double rmax = mode == 0 ? el.rmax : el.wave_rmax;
@@ -485,8 +503,9 @@ std::unique_ptr<SiteTables> build_site_tables(const std::vector<Element>& els, c
       radius = (el.proj_gridsize - 1) * rmax / ndiv;
     }
     geom[s] = sphere_geometry(coords + 3 * p, lattice, fftg, rmax, radius);
-  }
+  });
   delete hs_geom;
+  oe.rethrow();
   long pt = 0, tab = 0;
   int lm = 0;
   for (int s = 0; s < nlist; s++) {
@@ -512,6 +531,15 @@ std::unique_ptr<SiteTables> build_site_tables(const std::vector<Element>& els, c
   // The host only ships the unwrapped grid coordinates of the selected points (8 B per point, packed straight into
   // pinned staging memory in parallel over sites); expand_geometry_kernel rebuilds index, offsets and cell shifts.
   const size_t npt = (size_t)std::max<long>(pt, 1);
+  // NOTE: a host pointer returned by g_arena.take() is only valid until the next take() (which may wrap or grow
+  // the arena), so every other upload of this function happens before the ijk block is taken and the block is
+  // fetched to the device before anything else touches the arena.
+  T->sites = upload(T->host);
+  T->by_mt.assign(4, {});
+  for (int s = 0; s < nlist; s++) T->by_mt[(T->host[s].nlm + 7) / 8].push_back(s);
+  T->by_mt_dev.resize(4);
+  for (int m = 1; m <= 3; m++)
+    if (!T->by_mt[m].empty()) T->by_mt_dev[m] = upload(T->by_mt[m]);
   int16_t* ijk = (int16_t*)g_arena.take(npt * 4 * sizeof(int16_t));
 #pragma omp parallel for schedule(dynamic)
   for (int s = 0; s < nlist; s++) {
@@ -523,7 +551,6 @@ std::unique_ptr<SiteTables> build_site_tables(const std::vector<Element>& els, c
     T->host_idx.resize(nlist);
     for (int s = 0; s < nlist; s++) T->host_idx[s] = std::move(geom[s].index);
   }
-  T->sites = upload(T->host);
   T->idx.alloc(npt * sizeof(int32_t));
   T->path.alloc(3 * npt * sizeof(double));
   if (mode == 2) T->wrap.alloc(3 * npt * sizeof(int32_t));
@@ -544,11 +571,6 @@ std::unique_ptr<SiteTables> build_site_tables(const std::vector<Element>& els, c
     }
   }
   T->table.alloc(std::max<size_t>(1, tab) * sizeof(double2));
-  T->by_mt.assign(4, {});
-  for (int s = 0; s < nlist; s++) T->by_mt[(T->host[s].nlm + 7) / 8].push_back(s);
-  T->by_mt_dev.resize(4);
-  for (int m = 1; m <= 3; m++)
-    if (!T->by_mt[m].empty()) T->by_mt_dev[m] = upload(T->by_mt[m]);
 
   if (nlist > 0 && pt > 0) {
     ScopedStage tm(ST_TABLE);
@@ -761,10 +783,20 @@ pawb200_pswf* ingest(ByteSource src, const double* kws) {
   hd.nrecl = (long)std::round(h0[0]);
   hd.nspin = (int)std::round(h0[1]);
   if (hd.nrecl < 96 || hd.nspin < 1 || hd.nspin > 2) throw std::runtime_error("not a WAVECAR header");
+  // VASP writes 45200 for complex64 and 45210 for complex128 coefficients; reader.c:143 reads the tag and ignores it,
+  // so a double-precision file is silently
+  // reinterpreted as complex64 garbage there.  Here it is an error.
+  if ((long)std::round(h0[2]) != 45200)
+    throw std::runtime_error("unsupported WAVECAR precision tag " + std::to_string((long)std::round(h0[2])) +
+                             " (only 45200, complex64 coefficients, is supported - as in the reference)");
   std::vector<double> rec(hd.nrecl / 8);
   src.read(rec.data(), hd.nrecl, 12 * 8);
   hd.nwk = (int)std::round(rec[0]);
   hd.nband = (int)std::round(rec[1]);
+  if (hd.nwk <= 0 || hd.nband <= 0) throw std::runtime_error("WAVECAR header: k-point / band count must be positive");
+  if ((size_t)hd.nrecl / 8 < 4 + 3 * (size_t)hd.nband)
+    throw std::runtime_error("WAVECAR record length " + std::to_string(hd.nrecl) + " is too short for the " +
+                             std::to_string(hd.nband) + "-band k-point header (truncated or malformed file)");
   hd.encut = rec[2];
   for (int i = 0; i < 9; i++) hd.lattice[i] = rec[3 + i];
   wavecar_bounds(hd);
@@ -784,6 +816,7 @@ pawb200_pswf* ingest(ByteSource src, const double* kws) {
     src.read(rec.data(), base * hd.nrecl, hdr_doubles * 8);
     KPointInfo& kp = wf->kp[kap];
     kp.nplane = (int)std::round(rec[0]);
+    if (kp.nplane <= 0) throw std::runtime_error("k-point " + std::to_string(kap) + " has no plane waves");
     kp.k[0] = rec[1]; kp.k[1] = rec[2]; kp.k[2] = rec[3];
     kp.energy.resize(hd.nband); kp.occ.resize(hd.nband);
     for (int b = 0; b < hd.nband; b++) { kp.energy[b] = rec[4 + 3 * b]; kp.occ[b] = rec[6 + 3 * b]; }
@@ -1760,8 +1793,10 @@ void recip_block(pawb200_pswf* S, pawb200_pswf* R, const SiteLists& L, int kap, 
   }
 }
 
+// dev_out: `out` is DEVICE memory [hi - lo][nbS][nbR]; the blocks are computed in place on the main stream and
+// nothing is copied or synchronised (the caller orders its own work after the main stream).
 void overlap_matrix(pawb200_pswf* S, pawb200_pswf* R, const SiteLists* L, int flip, int lo, int hi,
-                    bool pseudo, bool aug, cdouble* out, bool recip = false) {
+                    bool pseudo, bool aug, cdouble* out, bool recip = false, bool dev_out = false) {
   HostSection hs_("overlap_matrix");
   check_pair(S, R);
   const int nS = S->nband, nR = R->nband;
@@ -1772,45 +1807,53 @@ void overlap_matrix(pawb200_pswf* S, pawb200_pswf* R, const SiteLists* L, int fl
   for (int kap = lo; kap < hi && pseudo && !side; kap++)
     if (S->resident[kap] && coeffs_in_flight(S, kap)) side = true;
   DevBuf blk;
-  if (!side) blk.alloc(blk_bytes);
+  if (!side && !dev_out) blk.alloc(blk_bytes);
   AugPlan A;
   if (aug) A = plan_aug(S, R, *L, recip);
   int use = 0;
   for (int kap = lo; kap < hi; kap++) {
     cdouble* dst = out + (size_t)(kap - lo) * nS * nR;
     const int kr = flipped(R, kap, flip);
-    if (!S->resident[kap] || !R->resident[kr]) {
-      std::fill(dst, dst + (size_t)nS * nR, cdouble(0, 0));   // another rank's block
+    if (!S->resident[kap] || !R->resident[kr]) {              // another rank's block
+      if (dev_out) CUDA_OK(cudaMemsetAsync(dst, 0, blk_bytes, g_stream));
+      else std::fill(dst, dst + (size_t)nS * nR, cdouble(0, 0));
       continue;
     }
     double2* b;
     if (side) {
-      // pseudo block on the GEMM stream into a dedicated buffer; the main stream joins before it adds the
-      // augmentation GEMM and copies the block out
+      // pseudo block on the GEMM stream into a dedicated buffer (or the caller's device block); the main stream
+      // joins before it adds the augmentation GEMM and copies the block out
       cudaStream_t st2 = gemm_stream();
       const int slot = use++ & 1;
-      g_pblk[slot].ensure(blk_bytes);
-      b = (double2*)g_pblk[slot].p;
+      if (dev_out) {
+        b = (double2*)dst;
+        CUDA_OK(cudaEventRecord(g_pblk_free[slot], g_stream));     // earlier main-stream users of the block are done
+      } else {
+        g_pblk[slot].ensure(blk_bytes);
+        b = (double2*)g_pblk[slot].p;
+      }
       CUDA_OK(cudaStreamWaitEvent(st2, g_pblk_free[slot], 0));
       pseudo_block(S, R, kap, flip, b, nR, st2, true);
       CUDA_OK(cudaEventRecord(g_pblk_done[slot], st2));
       CUDA_OK(cudaStreamWaitEvent(g_stream, g_pblk_done[slot], 0));
       if (aug) aug_block(S, R, A, kap, flip, b, nR, true);
       if (aug && recip) recip_block(S, R, *L, kap, flip, b, nR);
+      if (dev_out) continue;
       ScopedStage tm(ST_D2H);
       CUDA_OK(cudaMemcpyAsync(dst, b, blk_bytes, cudaMemcpyDeviceToHost, g_stream));
       trace_mark("d2h block done", g_stream);
       CUDA_OK(cudaEventRecord(g_pblk_free[slot], g_stream));
       continue;
     }
-    b = blk.as<double2>();
+    b = dev_out ? (double2*)dst : blk.as<double2>();
     if (pseudo) pseudo_block(S, R, kap, flip, b, nR);
     if (aug) aug_block(S, R, A, kap, flip, b, nR, pseudo);
     if (aug && recip) recip_block(S, R, *L, kap, flip, b, nR);
+    if (dev_out) continue;
     ScopedStage tm(ST_D2H);
     CUDA_OK(cudaMemcpyAsync(dst, b, blk_bytes, cudaMemcpyDeviceToHost, g_stream));
   }
-  stream_sync();
+  if (!dev_out) stream_sync();
 }
 
 // ---- real-space states -----------------------------------------------------------------------
@@ -2111,15 +2154,19 @@ double pawb200_get_encut(pawb200_pswf_t* wf) { return wf ? wf->encut : 0; }
 
 double pawb200_get_energy(pawb200_pswf_t* wf, int band, int kpt, int spin) {
   API_BEGIN
+  if (!wf) throw std::runtime_error("NULL wavefunction pointer");
   const int kap = kpt + spin * wf->nwk;
-  if (!wf || band < 0 || band >= wf->nband || kap < 0 || kap >= wf->nkappa()) throw std::runtime_error("index out of range");
+  if (band < 0 || band >= wf->nband || kpt < 0 || kpt >= wf->nwk || spin < 0 || spin >= wf->nspin)
+    throw std::runtime_error("index out of range");
   return wf->kp[kap].energy[band];
   API_END(NAN)
 }
 double pawb200_get_occ(pawb200_pswf_t* wf, int band, int kpt, int spin) {
   API_BEGIN
+  if (!wf) throw std::runtime_error("NULL wavefunction pointer");
   const int kap = kpt + spin * wf->nwk;
-  if (!wf || band < 0 || band >= wf->nband || kap < 0 || kap >= wf->nkappa()) throw std::runtime_error("index out of range");
+  if (band < 0 || band >= wf->nband || kpt < 0 || kpt >= wf->nwk || spin < 0 || spin >= wf->nspin)
+    throw std::runtime_error("index out of range");
   return wf->kp[kap].occ[band];
   API_END(NAN)
 }
@@ -2188,6 +2235,30 @@ void pawb200_projection_matrix(pawb200_c128* out, pawb200_pswf_t* wf_S, pawb200_
   API_END_VOID
 }
 
+// Same blocks, left in DEVICE memory the caller owns (e.g. a torch tensor): out_dev[kappa - lo][b_S][b_R].  The
+// kernels are queued on the library's main stream (the legacy default stream, i.e. torch's default stream) and
+// the call returns without synchronising, so a collective launched by the caller on that stream - the NCCL
+// all-gather of the per-k matrices - follows without a host round trip.
+void pawb200_projection_matrix_dev(void* out_dev, pawb200_pswf_t* wf_S, pawb200_pswf_t* wf_R, int num_M,
+                                   int num_N_R, int num_N_S, int num_N_RS, const int* M_R, const int* M_S,
+                                   const int* N_R, const int* N_S, const int* N_RS_R, const int* N_RS_S,
+                                   int flip_spin, int kappa_lo, int kappa_hi, int pseudo_only) {
+  API_BEGIN
+  require_device();
+  check_pair(wf_S, wf_R);
+  if (!out_dev) throw std::runtime_error("NULL device output pointer");
+  if (kappa_lo < 0 || kappa_hi > wf_S->nkappa() || kappa_lo > kappa_hi) throw std::runtime_error("bad kappa range");
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, out_dev) != cudaSuccess || at.type != cudaMemoryTypeDevice) {
+    cudaGetLastError();
+    throw std::runtime_error("pawb200_projection_matrix_dev needs a device pointer");
+  }
+  SiteLists L = make_lists(num_M, num_N_R, num_N_S, num_N_RS, M_R, M_S, N_R, N_S, N_RS_R, N_RS_S);
+  overlap_matrix(wf_S, wf_R, &L, flip_spin, kappa_lo, kappa_hi, true, pseudo_only != 1, (cdouble*)out_dev,
+                 pseudo_only == 2, true);
+  API_END_VOID
+}
+
 void pawb200_pseudoprojection(pawb200_c128* projections, pawb200_pswf_t* wf_ref, pawb200_pswf_t* wf_proj,
                               int BAND_NUM, int flip_spin) {
   API_BEGIN
@@ -2196,10 +2267,11 @@ void pawb200_pseudoprojection(pawb200_c128* projections, pawb200_pswf_t* wf_ref,
   if (BAND_NUM < 0 || BAND_NUM >= wf_proj->nband) throw std::runtime_error("band index out of range");
   HostMatrixCache& c = wf_proj->pseudo_cache;
   const int NK = wf_ref->nkappa(), nS = wf_proj->nband, nR = wf_ref->nband;
-  if (!c.valid || c.other_id != wf_ref->id || c.flip != (flip_spin ? 1 : 0)) {
+  if (!c.valid || c.other_id != wf_ref->id || c.other_gen != wf_ref->gen || c.self_gen != wf_proj->gen ||
+      c.flip != (flip_spin ? 1 : 0)) {
     c.data.assign((size_t)NK * nS * nR, cdouble(0, 0));
     overlap_matrix(wf_proj, wf_ref, nullptr, flip_spin, 0, NK, true, false, c.data.data());
-    c.other_id = wf_ref->id;
+    c.other_id = wf_ref->id; c.other_gen = wf_ref->gen; c.self_gen = wf_proj->gen;
     c.flip = flip_spin ? 1 : 0;
     c.valid = true;
   }
@@ -2207,6 +2279,37 @@ void pawb200_pseudoprojection(pawb200_c128* projections, pawb200_pswf_t* wf_ref,
   for (int k = 0; k < NK; k++)
     for (int b = 0; b < nR; b++) out[(size_t)b * NK + k] = c.data[((size_t)k * nS + BAND_NUM) * nR + b];
   API_END_VOID
+}
+
+// Argument checks shared by overlap_setup_real / _recip: every site index against the structure it indexes, every
+// label against the element list (the reference indexes pps[labels[s]] and coords + 3*s unchecked,
+// projector.c:625-719).  The arrays hold num_sites entries of the structure they describe, as in the reference.
+void check_overlap_setup_args(const pawb200_pswf* wf_R, const pawb200_pswf* wf_S, const int* labels_R,
+                              const int* labels_S, const double* coords_R, const double* coords_S, const int* N_R,
+                              const int* N_S, const int* N_RS_R, const int* N_RS_S, int num_N_R, int num_N_S,
+                              int num_N_RS) {
+  if (num_N_R < 0 || num_N_S < 0 || num_N_RS < 0) throw std::runtime_error("negative site-list length");
+  if (!labels_R || !labels_S || !coords_R || !coords_S) throw std::runtime_error("NULL label / coordinate array");
+  if ((num_N_R && !N_R) || (num_N_S && !N_S) || (num_N_RS && (!N_RS_R || !N_RS_S)))
+    throw std::runtime_error("NULL site list with a non-zero length");
+  auto check_struct = [](const pawb200_pswf* wf, const int* labels, const double* coords, const char* who) {
+    const int nel = (int)wf->pps->list.el.size();
+    for (int s = 0; s < wf->num_sites; s++) {
+      if (labels[s] < 0 || labels[s] >= nel) throw std::runtime_error(std::string("site label out of range (") + who + ")");
+      for (int d = 0; d < 3; d++)
+        if (!std::isfinite(coords[3 * s + d])) throw std::runtime_error(std::string("non-finite site coordinate (") + who + ")");
+    }
+  };
+  check_struct(wf_R, labels_R, coords_R, "basis");
+  check_struct(wf_S, labels_S, coords_S, "wf");
+  auto check_list = [](const int* v, int n, int nsites, const char* who) {
+    for (int i = 0; i < n; i++)
+      if (v[i] < 0 || v[i] >= nsites) throw std::runtime_error(std::string("site index out of range in ") + who);
+  };
+  check_list(N_R, num_N_R, wf_R->num_sites, "N_R");
+  check_list(N_S, num_N_S, wf_S->num_sites, "N_S");
+  check_list(N_RS_R, num_N_RS, wf_R->num_sites, "N_RS_R");
+  check_list(N_RS_S, num_N_RS, wf_S->num_sites, "N_RS_S");
 }
 
 // part 3 of overlap_setup_real / _recip (projector.c:682-719, 799-841): off-site partial-wave overlaps, host
@@ -2220,8 +2323,9 @@ void setup_offsite(pawb200_pswf* wf_R, pawb200_pswf* wf_S, const int* labels_R, 
   wf_S->dcoords.assign(3 * (size_t)num_N_RS, 0.0);
   wf_S->omega_n1.assign(num_N_RS, 0);
   wf_S->omega_n2.assign(num_N_RS, 0);
+  OmpErr oe;
 #pragma omp parallel for schedule(dynamic)
-  for (int i = 0; i < num_N_RS; i++) {
+  for (int i = 0; i < num_N_RS; i++) oe.run([&] {
     const int s1 = N_RS_R[i], s2 = N_RS_S[i];
     const Element& p1 = elsR[labels_R[s1]];
     const Element& p2 = elsS[labels_S[s2]];
@@ -2240,7 +2344,8 @@ void setup_offsite(pawb200_pswf* wf_R, pawb200_pswf* wf_S, const int* labels_R, 
       }
     wf_S->omega_n1[i] = p1.total_projs;
     wf_S->omega_n2[i] = p2.total_projs;
-  }
+  });
+  oe.rethrow();
 }
 
 // (f3) get_aug_freqs for every band of `wf` (projector.c:420-453): the (phi - phit) augmentation of the listed
@@ -2320,6 +2425,8 @@ void pawb200_overlap_setup_real(pawb200_pswf_t* wf_R, pawb200_pswf_t* wf_S, cons
   require_device();
   check_pair(wf_S, wf_R);
   if (!wf_R->has_projections || !wf_S->has_projections) throw std::runtime_error("setup_projections has not been run");
+  check_overlap_setup_args(wf_R, wf_S, labels_R, labels_S, coords_R, coords_S, N_R, N_S, N_RS_R, N_RS_S, num_N_R,
+                           num_N_S, num_N_RS);
   wf_R->gen++;
   wf_S->gen++;
   wf_R->aug_cache.valid = wf_S->aug_cache.valid = false;
@@ -2382,6 +2489,8 @@ void pawb200_overlap_setup_recip(pawb200_pswf_t* wf_R, pawb200_pswf_t* wf_S, con
   require_device();
   check_pair(wf_S, wf_R);
   if (!wf_R->has_projections || !wf_S->has_projections) throw std::runtime_error("setup_projections has not been run");
+  check_overlap_setup_args(wf_R, wf_S, labels_R, labels_S, coords_R, coords_S, N_R, N_S, N_RS_R, N_RS_S, num_N_R,
+                           num_N_S, num_N_RS);
   wf_R->gen++;
   wf_S->gen++;
   wf_R->aug_cache.valid = wf_S->aug_cache.valid = false;
@@ -2799,8 +2908,27 @@ void pawb200_reciprocal_offsite_wave_overlap(const double* dcoord, const double*
 // ---- extensions ------------------------------------------------------------------------------------
 void pawb200_set_kappa_range(pawb200_pswf_t* wf, int lo, int hi) {
   if (!wf) return;
-  for (int k = 0; k < wf->nkappa(); k++)
-    if (k < lo || k >= hi) wf->resident[k] = 0;   // blocks outside the range are dropped
+  API_BEGIN
+  // blocks outside the range are dropped: their HBM goes back to the pools (after every stream that may still
+  // touch them has drained) and the per-band host caches, which hold full-range matrices, are invalidated
+  bool any = false;
+  for (int k = 0; k < wf->nkappa(); k++) any = any || ((k < lo || k >= hi) && wf->resident[k]);
+  if (!any) return;
+  cudaStreamSynchronize(ingest_ring().copy);
+  cudaStreamSynchronize(ingest_ring().unpack);
+  if (g_stream2) cudaStreamSynchronize(g_stream2);
+  cudaStreamSynchronize(g_stream);
+  for (int k = 0; k < wf->nkappa(); k++) {
+    if (!(k < lo || k >= hi) || !wf->resident[k]) continue;
+    wf->resident[k] = 0;
+    auto drop = [k](std::vector<DevBuf>& v) { if (k < (int)v.size()) v[k].release(); };
+    drop(wf->C); drop(wf->Cil); drop(wf->perm_dev); drop(wf->P); drop(wf->W); drop(wf->CA); drop(wf->boxes);
+  }
+  wf->gen++;
+  wf->pseudo_cache.valid = wf->aug_cache.valid = false;
+  wf->pseudo_cache.data = std::vector<cdouble>();
+  wf->aug_cache.data = std::vector<cdouble>();
+  API_END_VOID
 }
 int pawb200_num_projections(pawb200_pswf_t* wf, int which) {
   if (!wf) return 0;

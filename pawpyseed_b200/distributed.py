@@ -77,6 +77,60 @@ def all_gather_own_blocks(own: np.ndarray, own_kappas, nkappa: int, group=None, 
     return host.view(np.complex128).reshape((nkappa,) + own.shape[1:])
 
 
+_gather_bufs = {}
+
+
+def exchange_blocks(send, nkappa: int, blk: int, group=None, recv=None):
+    """All-gather of the rank-local send buffers ([per * blk] float64, block j of rank r = kappa j*world + r,
+    zero padded) into a kappa-major tensor [nkappa * blk] on the same device (NCCL on GPUs, gloo on CPU)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    per = -(-nkappa // world)
+    if world == 1:
+        return send[: nkappa * blk]
+    if recv is None:
+        recv = torch.empty(world * per * blk, dtype=send.dtype, device=send.device)
+    dist.all_gather_into_tensor(recv, send, group=group)
+    if per > 1:     # rank-major [world][per] -> kappa-major (kappa = j*world + r)
+        recv = recv.view(world, per, blk).transpose(0, 1).contiguous().view(-1)
+    return recv[: nkappa * blk]
+
+
+def gather_projection_blocks(pr, own_kappas, nkappa: int, group=None, pinned_out=None, want_host=True):
+    """The (k,spin) blocks this rank owns, computed straight into a device send buffer
+    (`pawb200_projection_matrix_dev`) and exchanged with one NCCL all-gather - the result never visits the host
+    on the way (one allgather of the per-k projection matrices over NVLink).  `pr` is a CProjector /
+    Projector whose wavefunctions were read with `set_read_shard(rank, world)`.
+
+    Returns the full [nkappa, nband_wf, nband_basis] complex128 array on the host when want_host (a view of
+    `pinned_out` if given), else the gathered, kappa-major device tensor (float64 pairs)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    nS, nR = pr.wf.nband, pr.basis.nband
+    blk = nS * nR * 2
+    per = -(-nkappa // world)
+    key = (per, blk, world)
+    if key not in _gather_bufs:
+        _gather_bufs.clear()
+        _gather_bufs[key] = (torch.zeros(per * blk, dtype=torch.float64, device="cuda"),
+                             torch.empty(world * per * blk, dtype=torch.float64, device="cuda"))
+    send, recv = _gather_bufs[key]
+    for j, k in enumerate(sorted(own_kappas)):
+        pr._projection_matrix_dev(send[j * blk:(j + 1) * blk], kappa_range=(k, k + 1))
+    valid = exchange_blocks(send, nkappa, blk, group, recv)
+    if not want_host:
+        return valid
+    if pinned_out is not None:
+        dst = pinned_out[: valid.numel()]
+        dst.copy_(valid, non_blocking=False)
+        host = dst.numpy()
+    else:
+        host = valid.cpu().numpy()
+    return host.view(np.complex128).reshape(nkappa, nS, nR)
+
+
 def band_block(nband: int, rank: int, world: int):
     """Contiguous band range [lo, hi) of `rank` when the bands of one (k,spin) block are split over ranks."""
     per = -(-nband // world)

@@ -536,6 +536,27 @@ class CProjector:
         return out
 
 
+    def _projection_matrix_dev(self, out_dev, flip_spin=False, kappa_range=None, pseudo_only=False):
+        """Same blocks, written to the DEVICE tensor `out_dev` (torch complex128 / float64 view, contiguous,
+        [(hi - lo), nband_wf, nband_basis]).  Nothing is copied to the host and nothing is synchronised: the work is
+        queued on the legacy default stream, which is torch's default stream."""
+        NK = self.basis.nwk * self.basis.nspin
+        lo, hi = (0, NK) if kappa_range is None else kappa_range
+        need = (hi - lo) * self.wf.nband * self.basis.nband * 16
+        if out_dev.numel() * out_dev.element_size() < need or not out_dev.is_cuda or not out_dev.is_contiguous():
+            raise ValueError("out_dev must be a contiguous CUDA tensor of at least %d bytes" % need)
+        have = hasattr(self, "M_R")
+        z = np.zeros(0, np.int32)
+        lists = [getattr(self, n) if have else z for n in ("M_R", "M_S", "N_R", "N_S", "N_RS_R", "N_RS_S")]
+        _lib.lib().pawb200_projection_matrix_dev(
+            C.c_void_p(out_dev.data_ptr()), self.wf.wf_ptr, self.basis.wf_ptr, len(lists[0]),
+            len(lists[2]), len(lists[3]), len(lists[4]), *[ip(a) for a in lists],
+            int(bool(flip_spin)), int(lo), int(hi),
+            1 if (pseudo_only or not have) else (2 if getattr(self, "_recip", False) else 0))
+        check()
+        return out_dev
+
+
 class CMomentumMatrix:
     """pawpyc.pyx:738-807."""
 

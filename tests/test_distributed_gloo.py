@@ -42,11 +42,18 @@ def _worker(rank, world, port, nk, q):
     local[own] = full[own]
     got = pd.gather_blocks(local)
     got2 = pd.all_gather_own_blocks(full[own], own, nk)
+    # the device-resident exchange used by gather_projection_blocks (here on CPU tensors over gloo)
+    blk, per = 6 * 5 * 2, -(-nk // world)
+    send = torch.zeros(per * blk, dtype=torch.float64)
+    for j, k in enumerate(own):
+        send[j * blk:(j + 1) * blk] = torch.from_numpy(np.ascontiguousarray(full[k]).reshape(-1).view(np.float64))
+    got3 = pd.exchange_blocks(send, nk, blk).numpy().view(np.complex128).reshape(full.shape)
     tmax = pd.max_over_ranks(float(rank + 1))
     fake = _FakeWavefunction()
     dens = pd.sharded_chg_density(fake)                       # bands split 4 + 3, one all-reduce
     dens_ok = bool(np.allclose(dens, fake._get_realspace_density(), rtol=0, atol=1e-12))
-    q.put((rank, bool(np.array_equal(got, full) and np.array_equal(got2, full) and dens_ok), tmax, own))
+    q.put((rank, bool(np.array_equal(got, full) and np.array_equal(got2, full) and np.array_equal(got3, full)
+                      and dens_ok), tmax, own))
     dist.destroy_process_group()
 
 
