@@ -101,13 +101,20 @@ def workload(name, nk=1, nband=None):
     return w
 
 
+def shard_mode(w, world):
+    """(k,spin) blocks round-robin over ranks when there are enough of them, else band blocks of the blocks."""
+    return "kappa" if world == 1 or w["nk"] * w["nspin"] >= world else "bands"
+
+
 def config_dict(w, world, scaling):
     """`config` of the JSON line - built by the same function for both arms so that they compare like with like."""
     NK = w["nk"] * w["nspin"]
+    how = ("(k,spin) blocks round-robin" if shard_mode(w, world) == "kappa" else
+           "band blocks of each (k,spin) block (basis rows all-gathered over NVLink)")
     return {"workload": w["name"], "nband": w["nband"], "npw": [len(g) for g in w["gvecs"]],
             "fft_grid": [int(x) for x in w["dim"]], "sites": [len(w["labels_R"]), len(w["labels_S"])],
             "kappa_blocks": NK, "pairs_per_step": w["nband"] ** 2 * NK,
-            "parallelism": "(k,spin) blocks round-robin over %d GPU(s), %s" % (world, scaling),
+            "parallelism": "%s over %d GPU(s), %s" % (how, world, scaling),
             "l2": "inputs (%.1f GB coefficients + FFT boxes per step) exceed the 126 MB L2" %
                   (2 * 8 * w["nband"] * sum(len(g) for g in w["gvecs"]) * w["nspin"] / 1e9)}
 
@@ -139,18 +146,26 @@ def make_images(w, own=None, nband=None, pinned=False, use_gpu=None):
                 return synth.random_coeffs(2000 + _sid, nband)(kap, npw)
             img = synth.wavecar_image(w["lattice"], w["encut"], w["kpts"], w["nspin"], nband, gen, gvecs=w["gvecs"])
         nrecl = _block_bytes(img)
+        pinned_spans = None
         if pinned:
             # page-lock only the coefficient records this rank reads (the image of a sharded job is mostly
             # other ranks' zero pages)
             rt = torch.cuda.cudart()
+            spans = []          # page-aligned [a0, a1), adjacent / overlapping blocks merged (a page registers once)
             for kap in kaps:
                 lo = (2 + kap * (1 + nband)) * nrecl
                 hi = lo + (1 + nband) * nrecl
                 a0 = (img.ctypes.data + lo) // 4096 * 4096
                 a1 = min(-(-(img.ctypes.data + hi) // 4096) * 4096, img.ctypes.data + img.nbytes)
+                if spans and a0 <= spans[-1][1]:
+                    spans[-1][1] = max(spans[-1][1], a1)
+                else:
+                    spans.append([a0, a1])
+            for a0, a1 in spans:
                 err = rt.cudaHostRegister(a0, a1 - a0, 0)
                 if int(err) != 0:
-                    raise SystemExit("cudaHostRegister failed: %s" % err)
+                    raise SystemExit("cudaHostRegister(%d bytes) failed: %s" % (a1 - a0, err))
+            pinned_spans = spans
         if use_gpu:
             for kap in kaps:
                 npw = len(w["gvecs"][kap % w["nk"]])
@@ -164,8 +179,20 @@ def make_images(w, own=None, nband=None, pinned=False, use_gpu=None):
                 dst.copy_(c.view(-1))
                 del c
             torch.cuda.synchronize()
-        imgs.append((img, None))
+        imgs.append((img, pinned_spans))
     return imgs
+
+
+def unpin_images(imgs):
+    """Undo make_images(pinned=True) before the arrays are freed: the allocator may hand the same pages to the
+    next image, and a page cannot be registered twice."""
+    import torch
+    torch.cuda.synchronize()
+    rt = torch.cuda.cudart()
+    for i, (img, spans) in enumerate(imgs):
+        for a0, _ in spans or []:
+            rt.cudaHostUnregister(a0)
+        imgs[i] = (img, None)
 
 
 def coefficient_block(w, img, kap, nband_total, nb):
@@ -610,8 +637,15 @@ def measure_b200(args, w, rank, world, local, steps, warmup, scaling, e2e_steps)
     from pawpyseed_b200 import distributed as pdist
     L = _lib.lib()
     nband, NK = w["nband"], w["nk"] * w["nspin"]
-    own = {k for k in range(NK) if k % world == rank}
-    L.pawb200_set_read_shard(rank, world)
+    bands = shard_mode(w, world) == "bands"
+    if bands:       # every rank holds every (k,spin) block, but only its band block of it
+        own = set(range(NK))
+        L.pawb200_set_read_shard(0, 1)
+        L.pawb200_set_band_shard(rank, world)
+    else:
+        own = {k for k in range(NK) if k % world == rank}
+        L.pawb200_set_read_shard(rank, world)
+        L.pawb200_set_band_shard(0, 1)
     imgs = make_images(w, own=own, pinned=True)
     h2d_bytes = sum(2 * 8 * nband * len(w["gvecs"][k % w["nk"]]) for k in range(NK))   # both structures, all ranks
     d2h_bytes = 16 * nband * nband * NK
@@ -636,6 +670,8 @@ def measure_b200(args, w, rank, world, local, steps, warmup, scaling, e2e_steps)
         pr._setup_overlap(w["site_cat"], False)
         if world == 1:
             return pr._projection_matrix()     # [NK][nbS][nbR] on host
+        if bands:   # all-gather the basis rows, multiply the own wf rows, all-gather the result rows (NCCL)
+            return pdist.band_sharded_projection_matrix(pr, pinned_out=gather_pin, want_host=(rank == 0))
         # one process per GPU: compute only the owned (k,spin) blocks, then all-gather the per-k matrices over NCCL
         ks = sorted(own)
         return pdist.gather_projection_blocks(pr, ks, NK, pinned_out=gather_pin, want_host=(rank == 0))
@@ -700,6 +736,8 @@ def measure_b200(args, w, rank, world, local, steps, warmup, scaling, e2e_steps)
         dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
     e2e_ms = float(ms2.item()) / e2e_steps
     L.pawb200_set_async_ingest(0)
+    L.pawb200_set_band_shard(0, 1)
+    L.pawb200_set_read_shard(0, 1)
 
     stage = {k: v / steps for k, v in tm.items() if k.endswith("_ms")}
     if os.environ.get("PAWB200_BENCH_DEBUG") or world > 1:
@@ -718,7 +756,8 @@ def measure_b200(args, w, rank, world, local, steps, warmup, scaling, e2e_steps)
     return dict(ms_per_step=ms_per_step, value=pairs_total / (ms_per_step * 1e-3), e2e_ms=e2e_ms,
                 e2e_value=pairs_total / (e2e_ms * 1e-3), h2d_bytes=h2d_bytes, d2h_bytes=d2h_bytes, tm=tm, stage=stage,
                 wall_ms=wall * 1e3 / steps, clocks=clocks, checksum=checksum, mean_abs_diagonal=diag, own=own,
-                imgs=imgs, pairs_total=pairs_total, per_rank=per_rank, e2e_steps=e2e_steps, steps=steps)
+                imgs=imgs, pairs_total=pairs_total, per_rank=per_rank, e2e_steps=e2e_steps, steps=steps,
+                band_rows=(-(-nband // world) if bands else nband))
 
 
 def rooflines(w, m, fp64_peak, hbm_peak, hbm_src):
@@ -730,7 +769,8 @@ def rooflines(w, m, fp64_peak, hbm_peak, hbm_src):
     npw_mean = float(np.mean(npw_own)) if npw_own else 0.0
     ngrid = int(np.prod(w["dim"]))
     gemm_launches = steps * len(own)
-    gemm_flops = 8.0 * nband * nband * npw_mean                      # SURVEY 8d, per launch (4 real products)
+    mrows = m.get("band_rows", nband)                                # wf rows of this rank's GEMMs (band-sharded: 1/N)
+    gemm_flops = 8.0 * mrows * nband * npw_mean                      # SURVEY 8d, per launch (4 real products)
     gemm_ms = tm["gemm_pseudo_ms"] / max(gemm_launches, 1)
     gemm_tflops = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
     kern = {}
@@ -758,7 +798,7 @@ def rooflines(w, m, fp64_peak, hbm_peak, hbm_src):
     total_stage = sum(v for k, v in tm.items() if k.endswith("_ms"))
     use4m = bool(os.environ.get("PAWB200_GEMM_4M"))
     bn = 64 if use4m else 48
-    pad_m, pad_n = -(-nband // 64) * 64, -(-nband // bn) * bn
+    pad_m, pad_n = -(-mrows // 64) * 64, -(-nband // bn) * bn
     issued = (8.0 if use4m else 6.0) * pad_m * pad_n * npw_mean
     issued_tflops = issued / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
     roof = {"kernel": "zgemm_abh_kernel<float2,%s> (pseudo overlap, DMMA.8x8x4, stream-K) + fixup" %
@@ -817,13 +857,13 @@ def run_b200(args):
     host_threads = int(os.environ.get("PAWB200_BENCH_THREADS", max(1, (os.cpu_count() or 1) // world)))
     L.pawb200_set_host_threads(host_threads)   # torchrun exports OMP_NUM_THREADS=1
 
-    weak = args.config == "cfg2" and world > 1      # config 2 has one (k,spin) block: N GPUs = N k-points (weak)
+    weak = args.weak and world > 1      # --weak: config 2 replicated over N k-points, one per GPU (round-1 curve)
     scaling = "weak" if weak else "strong"
     w = workload(args.config, nk=world if weak else 1, nband=args.nband)
-    NK = w["nk"] * w["nspin"]
     e2e_steps = max(1, min(args.steps, 3))
     m = measure_b200(args, w, rank, world, local, args.steps, args.warmup, scaling, e2e_steps)
     if rank != 0:
+        unpin_images(m["imgs"])
         if world > 1:
             dist.destroy_process_group()
         return
@@ -853,6 +893,7 @@ def run_b200(args):
     }
     if m["per_rank"]:
         line["per_rank_ms_per_step"] = m["per_rank"]
+    unpin_images(m["imgs"])
     del m
     # ---- secondary workload: config 2 on one GPU ----------------------------------------------------------------
     if world == 1 and args.config == "cfg3" and not args.no_secondary:
@@ -863,6 +904,7 @@ def run_b200(args):
         cpu2, par2 = (None, None)
         if not args.no_cpu:
             cpu2, par2 = cpu_leg(args, w2, m2["imgs"], want_parity=True)
+        unpin_images(m2["imgs"])
         line["cfg2"] = {"config": config_dict(w2, 1, "strong"), "value": m2["value"], "unit": UNIT,
                         "ms_per_step": m2["ms_per_step"], "steps": k2, "warmup": w2s,
                         "e2e": {"value": m2["e2e_value"], "unit": UNIT, "h2d_bytes_per_step": m2["h2d_bytes"],
@@ -885,7 +927,7 @@ def run_reference(args):
     if rank != 0:
         return
     world = int(os.environ.get("WORLD_SIZE", 1))
-    weak = args.config == "cfg2" and world > 1
+    weak = args.weak and world > 1
     scaling = "weak" if weak else "strong"
     w = workload(args.config, nk=world if weak else 1, nband=args.nband)
     threads = os.cpu_count() or 1
@@ -952,6 +994,8 @@ def main():
     ap.add_argument("--cpu-sites", type=int, default=0, help="sites per element in the CPU sample")
     ap.add_argument("--cpu-pair-bands", type=int, default=0, help="wf bands whose pair rows the CPU sample computes")
     ap.add_argument("--ref-full", action="store_true", help="reference arm: time the complete workload (no sample)")
+    ap.add_argument("--weak", action="store_true",
+                    help="config 2 only: N GPUs = N k-points of the config's shape (weak scaling over (k,spin) blocks)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the config-2 secondary measurement")
     args = ap.parse_args()

@@ -229,6 +229,20 @@ void pawb200_free_pinned(void *p);
  * only the (k,spin) blocks with kappa % world == rank in HBM; blocks of other ranks come back
  * as zeros from pawb200_projection_matrix and are summed/gathered by the caller (NCCL). */
 void pawb200_set_read_shard(int rank, int world);
+/* Band-block sharding of ONE (k,spin) block over ranks (SURVEY 8e level 2, for jobs with fewer (k,spin) blocks
+ * than GPUs, e.g. Gamma-only): wavefunctions read after this call keep only the coefficient records of bands
+ * [rank*per, (rank+1)*per), per = ceil(nband/world), and setup_projections / overlap_setup_real transform and
+ * project only those bands.  Row buffers are allocated with per*world rows so the callers can all-gather the
+ * blocks in place: the basis needs all its rows (coefficients, projections, wave projections) before
+ * pawb200_projection_matrix[_dev], which then fills only the rows of the wf bands this rank owns (others zero).
+ * Independent of pawb200_set_read_shard (which distributes whole (k,spin) blocks). */
+void pawb200_set_band_shard(int rank, int world);
+/* Device pointer of a row buffer of block kappa for in-place collectives.  which: 0 = plane-wave coefficients
+ * (complex64 [rows][ld], box-ordered columns), 1 = projections, 2 = wave projections (complex128 [rows][ld]).
+ * rows = allocated rows (per*world, x2 for spinors), [own_lo, own_hi) = the rows this rank computed.  For
+ * which == 0 the library's main stream is made to wait for the coefficient copies first. */
+void *pawb200_get_device_buffer(pawb200_pswf_t *wf, int which, int kappa, long *ld, int *rows, int *own_lo,
+                                int *own_hi);
 /* With on != 0, pawb200_read_wavefunctions_from_str returns while the host->device copies are still in
  * flight: the CALLER MUST KEEP THE BUFFER ALIVE AND UNMODIFIED until the wavefunction has been used in a call
  * that returns results (or is freed). Later launches wait per band chunk, so the transfer overlaps the

@@ -113,6 +113,9 @@ _SIGS = {
                                              C.c_int] + [c_int_p] * 6 + [C.c_int, C.c_int, C.c_int, C.c_int]),
     "pawb200_set_kappa_range": (None, [C.c_void_p, C.c_int, C.c_int]),
     "pawb200_set_read_shard": (None, [C.c_int, C.c_int]),
+    "pawb200_set_band_shard": (None, [C.c_int, C.c_int]),
+    "pawb200_get_device_buffer": (C.c_void_p, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_long), c_int_p, c_int_p,
+                                               c_int_p]),
     "pawb200_set_host_threads": (None, [C.c_int]),
     "pawb200_set_async_ingest": (None, [C.c_int]),
     "pawb200_get_projections": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_dbl_p]),

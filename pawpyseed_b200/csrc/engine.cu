@@ -24,7 +24,7 @@
 #include "host_paw.h"
 #include "kernels.cuh"
 #include "zgemm.cuh"
-#include "fft3d.cuh"
+#include "fft_launch.h"
 
 using namespace pawb200;
 
@@ -463,6 +463,7 @@ struct SiteTables {
   long total_tab = 0;                 // double2 elements
   int nproj = 0;                      // concatenated channel count
   DevBuf sites, idx, path, wrap, table, tablek;
+  DevBuf ureal, phk, chan_m;          // real-table form of the projection (modes 0/1): see sphere_project_real_kernel
   std::vector<std::vector<int>> by_mt;   // site indices grouped by m-tile count (1..3)
   std::vector<DevBuf> by_mt_dev;
   std::vector<std::vector<int32_t>> host_idx;   // kept for the index-parity accessor
@@ -585,6 +586,21 @@ std::unique_ptr<SiteTables> build_site_tables(const std::vector<Element>& els, c
         T->table.as<double2>(), dlat.as<double>(), fftg[0], fftg[1], fftg[2], mode == 2 ? 1 : 0);
     count_launch();
     check_launch();   // ed / dlat return to the stream-ordered pool
+    if (mode != 2) {
+      // real rows of the table + the m of every channel (k-independent)
+      std::vector<int> cm((size_t)std::max(lm, 1), 0);
+      for (int s = 0; s < nlist; s++) {
+        const Element& el = els[labels[site_list[s]]];
+        for (int c = 0; c < T->host[s].nlm; c++) cm[T->host[s].lm_off + c] = el.chan[c].m;
+      }
+      T->chan_m = upload(cm);
+      T->ureal.alloc(std::max<size_t>(1, tab) * sizeof(double));
+      dim3 grid2((maxpts + 255) / 256, nlist);
+      real_table_kernel<<<grid2, 256, 0, g_stream>>>(T->sites.as<SiteDev>(), T->chan_m.as<int>(),
+                                                     T->table.as<double2>(), T->ureal.as<double>());
+      count_launch();
+      check_launch();
+    }
   }
   return T;
 }
@@ -666,15 +682,23 @@ struct pawb200_pswf {
   // per-band call caches
   HostMatrixCache pseudo_cache, aug_cache;
 
+  // band-block sharding of one (k,spin) block over ranks (SURVEY 8e level 2): this process transforms / projects /
+  // multiplies only the bands [band_lo, band_hi); row buffers (C, P, W) hold band_rows = per * world rows so that the
+  // blocks of all ranks can be all-gathered in place (pawb200_get_device_buffer + NCCL)
+  int band_lo = 0, band_hi = 0, band_rows = 0;
   int nkappa() const { return nwk * nspin; }
   int halves() const { return ncl ? 2 : 1; }
   int nslot() const { return nband * halves(); }
+  int slot_lo() const { return band_lo * halves(); }
+  int slot_own() const { return (band_hi - band_lo) * halves(); }
+  bool band_sharded() const { return band_lo != 0 || band_hi != nband; }
   int npw_half(int kap) const { return kp[kap].nplane / halves(); }
 };
 
 namespace {
 
 int g_shard_rank = 0, g_shard_world = 1;
+int g_band_rank = 0, g_band_world = 1;
 
 // ---- WAVECAR ingest -----------------------------------------------------------------------
 struct ByteSource {
@@ -801,6 +825,12 @@ pawb200_pswf* ingest(ByteSource src, const double* kws) {
   for (int i = 0; i < 9; i++) hd.lattice[i] = rec[3 + i];
   wavecar_bounds(hd);
   wf->nspin = hd.nspin; wf->nwk = hd.nwk; wf->nband = hd.nband; wf->encut = hd.encut;
+  {
+    const int per = (hd.nband + g_band_world - 1) / g_band_world;
+    wf->band_lo = std::min(hd.nband, g_band_rank * per);
+    wf->band_hi = std::min(hd.nband, (g_band_rank + 1) * per);
+    wf->band_rows = per * g_band_world;
+  }
   memcpy(wf->lattice, hd.lattice, sizeof(hd.lattice));
   memcpy(wf->reclattice, hd.reclattice, sizeof(hd.reclattice));
   const int NK = hd.nwk * hd.nspin;
@@ -847,8 +877,8 @@ pawb200_pswf* ingest(ByteSource src, const double* kws) {
     wf->ldc[kap] = ld;
     // cross-stream buffers from the quiescent pool: the unpack stream fills them without being ordered behind
     // whatever the main stream still has queued (e.g. the previous structure's transforms)
-    wf->C[kap].alloc_x((size_t)hd.nband * ld * sizeof(float2));
-    wf->C[kap].zero((size_t)hd.nband * ld * sizeof(float2), ring.unpack);
+    wf->C[kap].alloc_x((size_t)wf->band_rows * ld * sizeof(float2));
+    wf->C[kap].zero((size_t)wf->band_rows * ld * sizeof(float2), ring.unpack);
     const unsigned char* from;
     if (src.mem) {
       from = src.mem + (base + 1) * hd.nrecl;
@@ -869,12 +899,13 @@ pawb200_pswf* ingest(ByteSource src, const double* kws) {
       wf->perm_dev[kap] = upload(kp.perm, ring.unpack, true);
       alloc_interleaved(wf.get(), kap, ring.unpack);
       const int half_len = kp.nplane / (wf->ncl ? 2 : 1);
-      const int nchunk = std::max(1, std::min(8, hd.nband / 16));
+      const int nown = wf->band_hi - wf->band_lo;      // band-sharded ranks read only their band block
+      const int nchunk = std::max(1, std::min(8, nown / 16));
       // whole GEMM row tiles (64) per chunk when there are enough bands, else whole interleave groups (16)
-      const int gran = hd.nband >= 256 ? 64 : 16;
-      const int per = ((hd.nband + nchunk - 1) / nchunk + gran - 1) / gran * gran;
-      for (int b0 = 0; b0 < hd.nband; b0 += per) {
-        const int nb = std::min(per, hd.nband - b0);
+      const int gran = nown >= 256 ? 64 : 16;
+      const int per = ((nown + nchunk - 1) / nchunk + gran - 1) / gran * gran;
+      for (int b0 = wf->band_lo; b0 < wf->band_hi; b0 += per) {
+        const int nb = std::min(per, wf->band_hi - b0);
         IngestRing::Slot& sl = ring.slots[ring.next++ % 3];
         const size_t raw_bytes = (size_t)per * ld * sizeof(float2);
         if (raw_bytes > sl.bytes) {
@@ -1047,19 +1078,28 @@ void launch_project(const SiteTables& T, const double2* x, long ngrid, int nslot
   launch_project_mt<3>(T, x, ngrid, nslot, P, ldp, slot0);
 }
 
-void make_phase_table(SiteTables& T, const pawb200_pswf* wf, int kap, const int* fftg) {
+// Per-k phase data of a table set.  interleaved: the real-table kernel needs only dv e^{i k.path} per sphere point;
+// otherwise the planar kernel's complex per-k table Tk = conj(T) dv e^{i k.path} is built.
+void make_phase_table(SiteTables& T, const pawb200_pswf* wf, int kap, const int* fftg, bool interleaved) {
   if (T.nsites == 0 || T.total_pts == 0) return;
-  T.tablek.ensure(std::max<size_t>(1, T.total_tab) * sizeof(double2));
   double kc[3] = {wf->kp[kap].k[0], wf->kp[kap].k[1], wf->kp[kap].k[2]};
   frac_to_cart(kc, wf->reclattice);                                           // projector.c:233-237
   const double dv = determinant3(wf->lattice) / fftg[0] / fftg[1] / fftg[2];   // projector.c:229
-  int maxpts = 0;
-  for (auto& sd : T.host) maxpts = std::max(maxpts, sd.npts_pad);
-  dim3 grid((maxpts + 255) / 256, T.nsites);
   ScopedStage tm(ST_TABLE);
-  phase_table_kernel<<<grid, 256, 0, g_stream>>>(T.sites.as<SiteDev>(), T.path.as<double>(), T.total_pts,
-                                                 T.table.as<double2>(), T.tablek.as<double2>(), kc[0],
-                                                 kc[1], kc[2], dv);
+  if (interleaved && T.ureal.p) {
+    T.phk.ensure((size_t)T.total_pts * sizeof(double2));
+    const unsigned blocks = (unsigned)std::min<long>((T.total_pts + 255) / 256, (long)g_num_sms * 8);
+    phase_points_kernel<<<blocks, 256, 0, g_stream>>>(T.path.as<double>(), T.total_pts, T.total_pts,
+                                                      T.phk.as<double2>(), kc[0], kc[1], kc[2], dv);
+  } else {
+    T.tablek.ensure(std::max<size_t>(1, T.total_tab) * sizeof(double2));
+    int maxpts = 0;
+    for (auto& sd : T.host) maxpts = std::max(maxpts, sd.npts_pad);
+    dim3 grid((maxpts + 255) / 256, T.nsites);
+    phase_table_kernel<<<grid, 256, 0, g_stream>>>(T.sites.as<SiteDev>(), T.path.as<double>(), T.total_pts,
+                                                   T.table.as<double2>(), T.tablek.as<double2>(), kc[0],
+                                                   kc[1], kc[2], dv);
+  }
   count_launch();
   check_launch();
 }
@@ -1070,7 +1110,7 @@ DevBuf g_grid;   // FFT box batch, reused across calls
 struct PrunedPlan {
   bool ok = false;
   FftGeom g;
-  DevBuf col_start, col_cnt, zpos, col_run, ysrc, xsrc, tw[3];
+  DevBuf col_start, col_cnt, zpos, col_run, plane_run, ysrc, xsrc, tw[3];
 };
 
 bool factor_pair(int n, int& r1, int& r2) {
@@ -1086,20 +1126,6 @@ bool factor_pair(int n, int& r1, int& r2) {
         found = true;
       }
   return found;
-}
-
-void init_small_twiddles() {
-  static bool done = false;
-  if (done) return;
-  double2 h[FFT_MAXR + 1][FFT_MAXR];
-  memset(h, 0, sizeof(h));
-  for (int R = 1; R <= FFT_MAXR; R++)
-    for (int m = 0; m < R; m++) {
-      const long double a = 2.0L * 3.141592653589793238462643383279502884L * m / R;
-      h[R][m] = make_double2((double)cosl(a), (double)sinl(a));
-    }
-  CUDA_OK(cudaMemcpyToSymbol(c_small_tw, h, sizeof(h)));
-  done = true;
 }
 
 std::shared_ptr<PrunedPlan> build_pruned_plan(const pawb200_pswf* wf, int kap, const int* fftg) {
@@ -1167,6 +1193,23 @@ std::shared_ptr<PrunedPlan> build_pruned_plan(const pawb200_pswf* wf, int kap, c
   }
   if (runs_ok) P->col_run = upload(col_run);
   g.col_run = runs_ok ? P->col_run.as<int4>() : nullptr;
+  // cyclic y-run of the active columns of each x-plane (same encoding; consumed by the fused pass Y+X)
+  std::vector<int4> plane_run(g.nplane);
+  bool planes_ok = true;
+  for (int p = 0; p < g.nplane && planes_ok; p++) {
+    const int c0 = plane_col0[p], cnt = plane_ncol[p];
+    int gap = -1;
+    for (int j = 0; j + 1 < cnt; j++)
+      if (col_ypos[c0 + j + 1] != col_ypos[c0 + j] + 1) {
+        if (gap >= 0) planes_ok = false;
+        gap = j;
+      }
+    if (gap >= 0 && !(col_ypos[c0] == 0 && col_ypos[c0 + cnt - 1] == fftg[1] - 1)) planes_ok = false;
+    plane_run[p] = gap < 0 ? make_int4(c0, cnt, col_ypos[c0], cnt)
+                           : make_int4(c0, cnt, col_ypos[c0 + gap + 1], cnt - (gap + 1));
+  }
+  if (planes_ok) P->plane_run = upload(plane_run);
+  g.plane_run = planes_ok ? P->plane_run.as<int4>() : nullptr;
   P->col_start = upload(col_start); P->col_cnt = upload(col_cnt); P->zpos = upload(zpos);
   P->ysrc = upload(ysrc); P->xsrc = upload(xsrc);
   g.col_start = P->col_start.as<int>(); g.col_cnt = P->col_cnt.as<int>(); g.zpos = P->zpos.as<int>();
@@ -1196,99 +1239,48 @@ std::shared_ptr<PrunedPlan> get_pruned_plan(pawb200_pswf* wf, int kap, const int
   return wf->fft_plans[kap];
 }
 
-DevBuf g_fft_t1, g_fft_t2;
+DevBuf g_fft_t1, g_fft_t2, g_fft_flags;
+
+size_t fused_l2_budget() {
+  // ring of the fused pass Y+X: must stay L2-resident next to the streams that pass through (126 MB L2)
+  if (const char* e = getenv("PAWB200_FFT_RING_BYTES")) return (size_t)atoll(e);
+  return (size_t)40 << 20;
+}
 
 // Inverse transform of slots [slot0, slot0 + nslot) of kappa into X (interleaved groups of FFT_B slots).
-// One launcher per pass, templated on the largest radix of ITS axis (10 / 12 / 14 / 16): thread count, register
-// budget and resident CTAs follow the axis, not the worst axis of the grid.
-constexpr int kFftSmemOptIn = 227 * 1024;
-inline unsigned fft_grid_dim(long lines, int occ) {
-  return (unsigned)std::min<long>(lines, (long)g_num_sms * std::max(occ, 1));
-}
-
-template <int RMAX>
-void launch_pass_z(const pawb200_pswf* wf, int kap, const FftGeom& g, int s0, int ns, int ng, double scale) {
-  static int occ_run = 0, occ_staged = 0;
-  const int threads = std::max(g.r1[2], g.r2[2]) * FFT_B;
-  const size_t smem = (size_t)(2 * g.n3 * FFT_B + g.n3) * sizeof(double2);
-  const bool runs = g.col_run != nullptr && !wf->Cil.empty() && wf->Cil[kap].p;
-  int& occ = runs ? occ_run : occ_staged;
-  if (!occ) {
-    if (runs) {
-      CUDA_OK(cudaFuncSetAttribute(fft_pass_z_kernel<RMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFftSmemOptIn));
-      CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fft_pass_z_kernel<RMAX>, threads, smem));
-    } else {
-      CUDA_OK(cudaFuncSetAttribute(fft_pass_z_staged_kernel<RMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFftSmemOptIn));
-      CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fft_pass_z_staged_kernel<RMAX>, threads, smem));
-    }
-    occ = std::max(occ, 1);
-  }
-  if (runs)
-    fft_pass_z_kernel<RMAX><<<fft_grid_dim((long)ng * g.ncol, occ), threads, smem, g_stream>>>(
-        g, wf->Cil[kap].as<float2>(), wf->ldil[kap], s0, ns, scale, g_fft_t1.as<double2>(), ng);
-  else
-    fft_pass_z_staged_kernel<RMAX><<<fft_grid_dim((long)ng * g.ncol, occ), threads, smem, g_stream>>>(
-        g, wf->C[kap].as<float2>(), wf->ldc[kap], wf->halves(), wf->npw_half(kap), s0, ns, scale,
-        g_fft_t1.as<double2>(), ng);
-}
-
-template <int RMAX>
-void launch_pass_y(const FftGeom& g, int ng) {
-  static int occ = 0;
-  const int threads = std::max(g.r1[1], g.r2[1]) * FFT_B;
-  const size_t smem = (size_t)(2 * g.n2 * FFT_B + g.n2) * sizeof(double2) + g.n2 * sizeof(int);
-  if (!occ) {
-    CUDA_OK(cudaFuncSetAttribute(fft_pass_y_kernel<RMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFftSmemOptIn));
-    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fft_pass_y_kernel<RMAX>, threads, smem));
-    occ = std::max(occ, 1);
-  }
-  fft_pass_y_kernel<RMAX><<<fft_grid_dim((long)ng * g.nplane * ((g.n3 + FFT_ZC - 1) / FFT_ZC), occ), threads, smem,
-                            g_stream>>>(g, g_fft_t1.as<double2>(), g_fft_t2.as<double2>(), ng);
-}
-
-template <int RMAX>
-void launch_pass_x(const FftGeom& g, double2* X, int ng) {
-  static int occ = 0;
-  const int threads = std::max(g.r1[0], g.r2[0]) * FFT_B;
-  const size_t smem = (size_t)(2 * g.n1 * FFT_B + g.n1) * sizeof(double2) + g.n1 * sizeof(int);
-  if (!occ) {
-    CUDA_OK(cudaFuncSetAttribute(fft_pass_x_kernel<RMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFftSmemOptIn));
-    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fft_pass_x_kernel<RMAX>, threads, smem));
-    occ = std::max(occ, 1);
-  }
-  fft_pass_x_kernel<RMAX><<<fft_grid_dim((long)ng * g.n2 * g.n3, occ), threads, smem, g_stream>>>(
-      g, g_fft_t2.as<double2>(), X, ng);
-}
-
-#define PAWB200_AXIS_SWITCH(r, CALL) \
-  do {                               \
-    if ((r) <= 10) { CALL(10); }     \
-    else if ((r) <= 12) { CALL(12); } \
-    else if ((r) <= 14) { CALL(14); } \
-    else if ((r) <= 16) { CALL(16); } \
-    else { CALL(20); }               \
-  } while (0)
-
-// Inverse transform of slots [slot0, slot0 + nslot) of kappa into X (interleaved groups of FFT_B slots).
-// NOTE: the cached occupancies assume one grid shape per process and axis class; they only size the persistent
-// grids, so a stale value costs efficiency, never correctness.
 void pruned_fft(const pawb200_pswf* wf, int kap, const PrunedPlan& P, int slot0, int nslot, double2* X) {
   const FftGeom& g = P.g;
   const int ngroups = (nslot + FFT_B - 1) / FFT_B;
   const long ngrid = (long)g.n1 * g.n2 * g.n3;
   const size_t t1_grp = (size_t)g.ncol * g.n3 * FFT_B * sizeof(double2);
   const size_t t2_grp = (size_t)g.nplane * g.n2 * g.n3 * FFT_B * sizeof(double2);
-  // groups per launch: measured on config 2 (fft ms per step) 2: 11.8, 4: 10.8, 8: 10.3, 16: 10.1, all 38: 10.0 -
-  // fewer, longer persistent launches win over L2 residency of the scratch.  8 groups = 128 bands is also one ingest
-  // chunk, so a launch never waits for more than the chunk it needs.
+  // groups per launch: measured on config 2 (fft ms per step, stand-alone passes) 2: 11.8, 4: 10.8, 8: 10.3, 16: 10.1,
+  // all 38: 10.0.  8 groups = 128 bands is also one ingest chunk, so a launch never waits for more than the chunk
+  // it needs.
   int gc = 8;
   if (const char* e = getenv("PAWB200_FFT_GROUPS")) gc = std::max(1, atoi(e));
   gc = std::min(gc, ngroups);
+  const YxConfig yx = plan_fused_yx(g, g_num_sms, fused_l2_budget());
   g_fft_t1.ensure(t1_grp * gc);
-  g_fft_t2.ensure(t2_grp * gc);
+  if (yx.ok) {
+    g_fft_t2.ensure(yx.ring_bytes);
+    g_fft_flags.ensure(yx.flag_words(gc) * sizeof(unsigned));
+  } else {
+    g_fft_t2.ensure(t2_grp * gc);
+  }
   const double scale = std::pow(determinant3(wf->lattice), -0.5);
   const int h = wf->halves();
-  const int rz = std::max(g.r1[2], g.r2[2]), ry = std::max(g.r1[1], g.r2[1]), rx = std::max(g.r1[0], g.r2[0]);
+  FftInput in;
+  in.Cil = (!wf->Cil.empty() && wf->Cil[kap].p) ? wf->Cil[kap].as<float2>() : nullptr;
+  in.ldil = in.Cil ? wf->ldil[kap] : 0;
+  in.C = wf->C[kap].as<float2>();
+  in.ldc = wf->ldc[kap];
+  in.halves = h;
+  in.half_len = wf->npw_half(kap);
+  FftWork w;
+  w.T1 = g_fft_t1.as<double2>();
+  w.T2 = g_fft_t2.as<double2>();
+  w.flags = yx.ok ? g_fft_flags.as<unsigned>() : nullptr;
   ScopedStage tm(ST_FFT);
   g_boxes_fft += nslot;
   for (int g0 = 0; g0 < ngroups; g0 += gc) {
@@ -1296,16 +1288,8 @@ void pruned_fft(const pawb200_pswf* wf, int kap, const PrunedPlan& P, int slot0,
     const int s0 = slot0 + g0 * FFT_B;
     const int ns = std::min(nslot - g0 * FFT_B, ng * FFT_B);
     wait_coeffs(wf, kap, s0 / h, (s0 + ns + h - 1) / h);
-#define PASS_Z(R) launch_pass_z<R>(wf, kap, g, s0, ns, ng, scale)
-#define PASS_Y(R) launch_pass_y<R>(g, ng)
-#define PASS_X(R) launch_pass_x<R>(g, X + (long)g0 * ngrid * FFT_B, ng)
-    PAWB200_AXIS_SWITCH(rz, PASS_Z);
-    PAWB200_AXIS_SWITCH(ry, PASS_Y);
-    PAWB200_AXIS_SWITCH(rx, PASS_X);
-#undef PASS_Z
-#undef PASS_Y
-#undef PASS_X
-    count_launch(3);
+    count_launch(launch_pruned_passes(g, in, s0, ns, ng, scale, w, &yx, X + (long)g0 * ngrid * FFT_B, g_num_sms,
+                                      g_stream));
     trace_mark("fft done slots " + std::to_string(s0) + "+" + std::to_string(ns), g_stream);
   }
   check_launch();
@@ -1318,13 +1302,28 @@ void launch_project_il_mt(const SiteTables& T, const double2* X, long ngrid, int
   int maxpts = 0;
   for (int s : T.by_mt[MT]) maxpts = std::max(maxpts, T.host[s].npts_pad);
   const int idx_cap = std::min(maxpts, 16384);
+  dim3 grid((nslot + PROJ_NB - 1) / PROJ_NB, (unsigned)T.by_mt[MT].size());
+  if (T.ureal.p && T.phk.p) {
+    // real tables + phase on the samples: 2 DMMA per k-step and channel tile instead of 4
+    const size_t smem = sphere_project_real_smem<MT>() + (size_t)idx_cap * sizeof(int);
+    static size_t configured_r = 0;
+    if (smem > configured_r) {
+      CUDA_OK(cudaFuncSetAttribute(sphere_project_real_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured_r = smem;
+    }
+    sphere_project_real_kernel<MT><<<grid, 128, smem, g_stream>>>(
+        T.sites.as<SiteDev>(), T.by_mt_dev[MT].as<int>(), T.idx.as<int>(), T.ureal.as<double>(),
+        T.phk.as<double2>(), T.chan_m.as<int>(), X, ngrid, nslot, (nslot + FFT_B - 1) / FFT_B, P, ldp, slot0, idx_cap);
+    count_launch();
+    check_launch();
+    return;
+  }
   const size_t smem = sphere_project_smem(MT) + (size_t)idx_cap * sizeof(int);
   static size_t configured = 0;
   if (smem > configured) {
     CUDA_OK(cudaFuncSetAttribute(sphere_project_il_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  dim3 grid((nslot + PROJ_NB - 1) / PROJ_NB, (unsigned)T.by_mt[MT].size());
   sphere_project_il_kernel<MT><<<grid, 128, smem, g_stream>>>(
       T.sites.as<SiteDev>(), T.by_mt_dev[MT].as<int>(), T.idx.as<int>(), T.tablek.as<double2>(), X, ngrid, nslot,
       (nslot + FFT_B - 1) / FFT_B, P, ldp, slot0, idx_cap);
@@ -1362,7 +1361,7 @@ size_t keep_boxes_budget() {
 // geometry and tables (which then overlaps the transforms).  Returns false when the boxes do not fit the
 // budget or the grid needs the generic path; project_all_bands then transforms batch by batch.
 bool prefft_all_bands(pawb200_pswf* wf, const int* fftg) {
-  const int NK = wf->nkappa(), nslot = wf->nslot();
+  const int NK = wf->nkappa(), nslot = wf->slot_own();      // boxes[kap] holds the slots of the own band block
   const long ngrid = (long)fftg[0] * fftg[1] * fftg[2];
   const int ngroups_all = (nslot + FFT_B - 1) / FFT_B;
   const size_t il_bytes = (size_t)ngroups_all * FFT_B * ngrid * sizeof(double2);
@@ -1378,7 +1377,8 @@ bool prefft_all_bands(pawb200_pswf* wf, const int* fftg) {
   for (int kap = 0; kap < NK; kap++) {
     if (!wf->resident[kap]) continue;
     wf->boxes[kap].alloc(il_bytes);
-    pruned_fft(wf, kap, *get_pruned_plan(wf, kap, fftg), 0, nslot, wf->boxes[kap].as<double2>());
+    if (nslot > 0)
+      pruned_fft(wf, kap, *get_pruned_plan(wf, kap, fftg), wf->slot_lo(), nslot, wf->boxes[kap].as<double2>());
   }
   return true;
 }
@@ -1393,12 +1393,13 @@ void project_all_bands(pawb200_pswf* wf, SiteTables& T, const int* fftg, std::ve
   ld = ((long)std::max(T.nproj, 1) + 7) / 8 * 8;
   out.clear();
   out.resize(NK);
-  const int nslot = wf->nslot();
+  const int nslot = wf->slot_own(), slo = wf->slot_lo();   // own band block (all bands unless band-sharded)
+  const size_t out_rows = (size_t)wf->band_rows * wf->halves();
   long batch = (long)(fft_budget_bytes() / (sizeof(double2) * ngrid));
   batch = std::max<long>(batch, wf->halves());
   if (batch >= 32) batch = batch / 32 * 32;
   batch -= batch % wf->halves();
-  batch = std::min<long>(batch, nslot);
+  batch = std::max<long>(std::min<long>(batch, nslot), 1);
   int nres = 0;
   for (int kap = 0; kap < NK; kap++) nres += wf->resident[kap] ? 1 : 0;
   const size_t box_bytes = (size_t)nslot * ngrid * sizeof(double2);
@@ -1416,22 +1417,24 @@ void project_all_bands(pawb200_pswf* wf, SiteTables& T, const int* fftg, std::ve
   const size_t il_bytes = (size_t)ngroups_all * FFT_B * ngrid * sizeof(double2);
   for (int kap = 0; kap < NK; kap++) {
     if (!wf->resident[kap]) continue;
-    out[kap].alloc((size_t)nslot * ld * sizeof(double2));
+    out[kap].alloc(out_rows * ld * sizeof(double2));
     out[kap].zero();
-    if (T.nsites == 0) continue;
-    make_phase_table(T, wf, kap, fftg);
+    if (T.nsites == 0 || nslot == 0) continue;
     const bool reuse = !main_pass && same_grid && (int)wf->boxes.size() == NK && wf->boxes[kap].p;
+    std::shared_ptr<PrunedPlan> plan = reuse ? nullptr : get_pruned_plan(wf, kap, fftg);
+    make_phase_table(T, wf, kap, fftg, reuse ? wf->boxes_interleaved : plan->ok);
     if (reuse) {
       for (int s0 = 0; s0 < nslot; s0 += 2048) {
         const int nb = std::min(2048, nslot - s0);
         if (wf->boxes_interleaved)
-          launch_project_il(T, wf->boxes[kap].as<double2>() + (long)s0 * ngrid, ngrid, nb, out[kap].as<double2>(), ld, s0);
+          launch_project_il(T, wf->boxes[kap].as<double2>() + (long)s0 * ngrid, ngrid, nb, out[kap].as<double2>(), ld,
+                            slo + s0);
         else
-          launch_project(T, wf->boxes[kap].as<double2>() + (long)s0 * ngrid, ngrid, nb, out[kap].as<double2>(), ld, s0);
+          launch_project(T, wf->boxes[kap].as<double2>() + (long)s0 * ngrid, ngrid, nb, out[kap].as<double2>(), ld,
+                         slo + s0);
       }
       continue;
     }
-    std::shared_ptr<PrunedPlan> plan = get_pruned_plan(wf, kap, fftg);
     if (plan->ok) {
       // pruned band-interleaved FFT: chunks of whole 32-slot CTAs
       long chunk = std::max<long>(32, batch / 32 * 32);
@@ -1447,8 +1450,8 @@ void project_all_bands(pawb200_pswf* wf, SiteTables& T, const int* fftg, std::ve
       for (int s0 = 0; s0 < nslot; s0 += (int)chunk) {
         const int nb = (int)std::min<long>(chunk, nslot - s0);
         double2* x = keep ? base + (long)s0 * ngrid : base;
-        pruned_fft(wf, kap, *plan, s0, nb, x);
-        launch_project_il(T, x, ngrid, nb, out[kap].as<double2>(), ld, s0);
+        pruned_fft(wf, kap, *plan, slo + s0, nb, x);
+        launch_project_il(T, x, ngrid, nb, out[kap].as<double2>(), ld, slo + s0);
       }
       continue;
     }
@@ -1465,9 +1468,9 @@ void project_all_bands(pawb200_pswf* wf, SiteTables& T, const int* fftg, std::ve
     for (int s0 = 0; s0 < nslot; s0 += (int)batch) {
       const int nb = (int)std::min<long>(batch, nslot - s0);
       double2* x = keep ? base + (long)s0 * ngrid : base;
-      launch_scatter(wf, kap, s0, nb, inv, x, fftg);
+      launch_scatter(wf, kap, slo + s0, nb, inv, x, fftg);
       launch_fft(x, fftg, nb, CUFFT_INVERSE);
-      launch_project(T, x, ngrid, nb, out[kap].as<double2>(), ld, s0);
+      launch_project(T, x, ngrid, nb, out[kap].as<double2>(), ld, slo + s0);
     }
   }
 }
@@ -1613,8 +1616,10 @@ void pseudo_block(pawb200_pswf* S, pawb200_pswf* R, int kap, int flip, double2* 
     return;
   }
   wait_coeffs(S, kap, 0, S->nband, st);
-  run_zgemm<float2>(S->C[kap].as<float2>(), S->ldc[kap], R->C[kr].as<float2>(), R->ldc[kr], S->nband,
-                    R->nband, S->ldc[kap], out, ldo, false, ST_GEMM_PS, st, side_stream);
+  // rows of the result = the wf bands this process owns (all of them unless band-sharded)
+  run_zgemm<float2>(S->C[kap].as<float2>() + (long)S->band_lo * S->ldc[kap], S->ldc[kap], R->C[kr].as<float2>(),
+                    R->ldc[kr], S->band_hi - S->band_lo, R->nband, S->ldc[kap], out + (long)S->band_lo * ldo, ldo, false,
+                    ST_GEMM_PS, st, side_stream);
 }
 
 struct SiteLists {
@@ -1769,8 +1774,8 @@ void aug_block(pawb200_pswf* S, pawb200_pswf* R, AugPlan& A, int kap, int flip, 
     apply_ops(A.opsR_P, mats, R->P[kr].as<double2>(), R->ldp, opR.as<double2>(), A.Kpad, R->nband);
     apply_ops(A.opsR_W, mats, R->W.empty() ? nullptr : R->W[kr].as<double2>(), R->ldw, opR.as<double2>(), A.Kpad, R->nband);
   }
-  run_zgemm<double2>(opS.as<double2>(), A.Kpad, opR.as<double2>(), A.Kpad, S->nband, R->nband, A.Kpad, out, ldo,
-                     accumulate, ST_GEMM_AUG);
+  run_zgemm<double2>(opS.as<double2>() + (long)S->band_lo * A.Kpad, A.Kpad, opR.as<double2>(), A.Kpad,
+                     S->band_hi - S->band_lo, R->nband, A.Kpad, out + (long)S->band_lo * ldo, ldo, accumulate, ST_GEMM_AUG);
 }
 
 // Full block(s) to host: out[kap - lo][bS][bR]
@@ -1782,14 +1787,16 @@ void recip_block(pawb200_pswf* S, pawb200_pswf* R, const SiteLists& L, int kap, 
   if (!L.N_R.empty()) {
     if (R->CA.empty() || !R->CA[kr].p) throw std::runtime_error("overlap_setup_recip was not run for these site lists (N_R)");
     wait_coeffs(S, kap, 0, S->nband);
-    run_zgemm<float2>(S->C[kap].as<float2>(), S->ldc[kap], R->CA[kr].as<float2>(), R->ldc[kr], S->nband, R->nband,
-                      S->ldc[kap], out, ldo, true, ST_GEMM_AUG);
+    run_zgemm<float2>(S->C[kap].as<float2>() + (long)S->band_lo * S->ldc[kap], S->ldc[kap], R->CA[kr].as<float2>(),
+                      R->ldc[kr], S->band_hi - S->band_lo, R->nband, S->ldc[kap], out + (long)S->band_lo * ldo, ldo, true,
+                      ST_GEMM_AUG);
   }
   if (!L.N_S.empty()) {
     if (S->CA.empty() || !S->CA[kap].p) throw std::runtime_error("overlap_setup_recip was not run for these site lists (N_S)");
     wait_coeffs(R, kr, 0, R->nband);
-    run_zgemm<float2>(S->CA[kap].as<float2>(), S->ldc[kap], R->C[kr].as<float2>(), R->ldc[kr], S->nband, R->nband,
-                      S->ldc[kap], out, ldo, true, ST_GEMM_AUG);
+    run_zgemm<float2>(S->CA[kap].as<float2>() + (long)S->band_lo * S->ldc[kap], S->ldc[kap], R->C[kr].as<float2>(),
+                      R->ldc[kr], S->band_hi - S->band_lo, R->nband, S->ldc[kap], out + (long)S->band_lo * ldo, ldo, true,
+                      ST_GEMM_AUG);
   }
 }
 
@@ -1833,6 +1840,7 @@ void overlap_matrix(pawb200_pswf* S, pawb200_pswf* R, const SiteLists* L, int fl
         b = (double2*)g_pblk[slot].p;
       }
       CUDA_OK(cudaStreamWaitEvent(st2, g_pblk_free[slot], 0));
+      if (S->band_sharded()) CUDA_OK(cudaMemsetAsync(b, 0, blk_bytes, st2));        // rows of other ranks' bands
       pseudo_block(S, R, kap, flip, b, nR, st2, true);
       CUDA_OK(cudaEventRecord(g_pblk_done[slot], st2));
       CUDA_OK(cudaStreamWaitEvent(g_stream, g_pblk_done[slot], 0));
@@ -1846,6 +1854,7 @@ void overlap_matrix(pawb200_pswf* S, pawb200_pswf* R, const SiteLists* L, int fl
       continue;
     }
     b = dev_out ? (double2*)dst : blk.as<double2>();
+    if (S->band_sharded()) CUDA_OK(cudaMemsetAsync(b, 0, blk_bytes, g_stream));    // rows of other ranks' bands
     if (pseudo) pseudo_block(S, R, kap, flip, b, nR);
     if (aug) aug_block(S, R, A, kap, flip, b, nR, pseudo);
     if (aug && recip) recip_block(S, R, *L, kap, flip, b, nR);
@@ -1943,6 +1952,7 @@ void check_kpoint(const pawb200_pswf* wf, int band, int kap) {
   if (band < 0 || band >= wf->nband) throw std::runtime_error("band index out of range");
   if (kap < 0 || kap >= wf->nkappa()) throw std::runtime_error("k-point/spin index out of range");
   if (!wf->resident[kap]) throw std::runtime_error("(k,spin) block not resident on this rank");
+  if (band < wf->band_lo || band >= wf->band_hi) throw std::runtime_error("band belongs to another rank's band block");
 }
 
 // Device -> arbitrary (pageable or pinned) host memory through two page-locked staging buffers: the copy of
@@ -2024,7 +2034,7 @@ void density_to_host(double* Pout, pawb200_pswf* wf, const int* fftg, const int*
       bands.push_back(only_band);
       wts.push_back(1.0);                                    // ae_state_density, density.c:35-37
     } else {
-      for (int b = std::max(0, band_lo); b < std::min(wf->nband, band_hi); b++)
+      for (int b = std::max(wf->band_lo, band_lo); b < std::min(wf->band_hi, band_hi); b++)   // own band block only
         if (wf->kp[kap].occ[b] > 0) {                        // density.c:168
           bands.push_back(b);
           wts.push_back(wf->weight[kap] * wf->kp[kap].occ[b] * spin_mult);
@@ -2103,6 +2113,40 @@ void pawb200_set_async_ingest(int on) { g_async_ingest = on != 0; }
 
 void pawb200_set_host_threads(int n) {
   if (n > 0) omp_set_num_threads(n);
+}
+
+void pawb200_set_band_shard(int rank, int world) {
+  if (world < 1) world = 1;
+  g_band_rank = ((rank % world) + world) % world;
+  g_band_world = world;
+}
+
+void* pawb200_get_device_buffer(pawb200_pswf_t* wf, int which, int kappa, long* ld, int* rows, int* own_lo,
+                                int* own_hi) {
+  API_BEGIN
+  if (!wf) throw std::runtime_error("NULL wavefunction pointer");
+  if (kappa < 0 || kappa >= wf->nkappa() || !wf->resident[kappa]) throw std::runtime_error("(k,spin) block not resident");
+  const int h = wf->halves();
+  void* p = nullptr;
+  long l = 0;
+  int r = 0, lo = 0, hi = 0;
+  if (which == 0) {                      // plane-wave coefficients: one row per band
+    // everything queued after this call on the main (legacy default) stream sees the landed coefficients
+    wait_coeffs(wf, kappa, 0, wf->nband);
+    p = wf->C[kappa].p; l = wf->ldc[kappa]; r = wf->band_rows; lo = wf->band_lo; hi = wf->band_hi;
+  } else if (which == 1 || which == 2) {   // projections / wave projections: one row per slot
+    std::vector<DevBuf>& v = which == 1 ? wf->P : wf->W;
+    if (kappa >= (int)v.size() || !v[kappa].p) throw std::runtime_error("projections have not been set up");
+    p = v[kappa].p; l = which == 1 ? wf->ldp : wf->ldw; r = wf->band_rows * h; lo = wf->band_lo * h; hi = wf->band_hi * h;
+  } else {
+    throw std::runtime_error("unknown buffer id");
+  }
+  if (ld) *ld = l;
+  if (rows) *rows = r;
+  if (own_lo) *own_lo = lo;
+  if (own_hi) *own_hi = hi;
+  return p;
+  API_END(nullptr)
 }
 
 void pawb200_set_read_shard(int rank, int world) {
@@ -2498,6 +2542,8 @@ void pawb200_overlap_setup_recip(pawb200_pswf_t* wf_R, pawb200_pswf_t* wf_S, con
   wf_R->wp_nlm.clear(); wf_S->wp_nlm.clear();
   wf_R->wp_num = num_N_S; wf_S->wp_num = num_N_R;    // projector.c:735-736
   wf_R->CA.clear(); wf_S->CA.clear();
+  if (wf_R->band_sharded() || wf_S->band_sharded())
+    throw std::runtime_error("method aug_recip is not available on band-sharded wavefunctions (use aug_real)");
   if (num_N_R > 0) compute_aug_freqs(wf_R, N_R, num_N_R, labels_R, coords_R);   // part 1 (:748-767)
   if (num_N_S > 0) compute_aug_freqs(wf_S, N_S, num_N_S, labels_S, coords_S);   // part 2 (:770-792)
   setup_offsite(wf_R, wf_S, labels_R, labels_S, coords_R, coords_S, N_RS_R, N_RS_S, num_N_RS);
@@ -2541,7 +2587,9 @@ pawb200_pswf_t* pawb200_expand_symm_wf(pawb200_pswf_t* rwf, int num_kpts, const 
   if (rwf->ncl) throw std::runtime_error("desymmetrisation of noncollinear wavefunctions is not defined "
                                          "(NCLWavefunction.desymmetrized_copy raises in the reference too)");
   auto wf = std::make_unique<pawb200_pswf>();
+  if (rwf->band_sharded()) throw std::runtime_error("desymmetrisation of a band-sharded wavefunction is not supported");
   wf->nspin = rwf->nspin; wf->nband = rwf->nband; wf->nwk = num_kpts; wf->encut = rwf->encut; wf->ncl = 0;
+  wf->band_lo = 0; wf->band_hi = wf->nband; wf->band_rows = wf->nband;
   memcpy(wf->lattice, rwf->lattice, sizeof(wf->lattice));
   memcpy(wf->reclattice, rwf->reclattice, sizeof(wf->reclattice));
   const int NK = num_kpts * wf->nspin;

@@ -15,10 +15,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-namespace pawb200 {
+#include "fft_launch.h"
 
-constexpr int FFT_B = 16;          // interleaved bands per group
-constexpr int FFT_MAXR = 20;
+namespace pawb200 {
 
 // exp(+2 pi i m / R) for R <= FFT_MAXR (filled by the host at start-up)
 __constant__ double2 c_small_tw[FFT_MAXR + 1][FFT_MAXR];
@@ -159,21 +158,6 @@ __device__ __forceinline__ void line_phase2(const double2* __restrict__ buf, int
   for (int k2 = 0; k2 < R; k2++) store(k1 + R1 * k2, v[k2]);
 }
 
-struct FftGeom {            // device-side description of one (k-point, grid) pruned transform
-  int n1, n2, n3;           // grid
-  int r1[3], r2[3];         // n_d = r1[d] * r2[d] (index 0: x, 1: y, 2: z)
-  int ncol, nplane;         // active (g1,g2) columns / active g1 planes
-  const int* col_start;     // [ncol] first sorted plane-wave index of the column
-  const int* col_cnt;       // [ncol]
-  const int* zpos;          // [npw]  wrapped g3 of each sorted plane wave
-  const int4* col_run;      // [ncol] {start, cnt, zlo, nfirst}: the column's plane waves occupy the cyclic z-run
-                            //        zlo .. zlo+cnt-1 (mod n3); the first nfirst of the run sit at the END of the
-                            //        sorted list (they wrap), see fft_pass_z_kernel.  Null if some column is not a run.
-  const int* ysrc;          // [nplane][n2] column index holding (plane, y) or -1
-  const int* xsrc;          // [n1] plane index holding x or -1
-  const double2* tw[3];     // exp(+2 pi i m / n_d), m < n_d
-};
-
 template <int RMAX> struct FftLaunch {
   static constexpr int THREADS = RMAX * FFT_B;          // q-slots x 16 bands
   // resident CTAs per SM the register budget is tuned for (10: 160 thr x 5, 12: 192 x 3, 14: 224 x 2, 16: 256 x 2,
@@ -285,7 +269,6 @@ fft_pass_z_staged_kernel(FftGeom g, const float2* __restrict__ C, long ldc, int 
 // ---- pass Y: T1 -> T2[group][plane][y][z][FFT_B] ------------------------------------------------------
 // Work unit = (group, plane, chunk of FFT_ZC z-lines): the plane's row->column table is fetched into shared
 // memory once per unit, so the data loads do not wait behind a dependent global lookup.
-constexpr int FFT_ZC = 9;
 template <int RMAX>
 __global__ void __launch_bounds__(FftLaunch<RMAX>::THREADS, FftLaunch<RMAX>::MINB)
 fft_pass_y_kernel(FftGeom g, const double2* __restrict__ T1, double2* __restrict__ T2, int ngroups) {
@@ -372,6 +355,193 @@ fft_pass_x_kernel(FftGeom g, const double2* __restrict__ T2, double2* __restrict
 #undef P2
     }
   }
+}
+
+// ---- fused pass Y + X: T1 -> (L2-resident ring) -> X ----------------------------------------------------------
+// The stand-alone passes write the y-transformed planes T2 (0.68 N points per band) to HBM and read them back:
+// 45 % of the transform's traffic.  Here both passes run in ONE persistent kernel and T2 only ever exists for a few
+// z values at a time: a "chunk" c = (band group, zch consecutive z) owns slot c % ring of a ring buffer of a few tens
+// of MB that is written and re-read within microseconds, i.e. it stays in the 126 MB L2 and never reaches DRAM.
+//
+// Work items are single lines, handed out IN ORDER through a global ticket counter (atomicAdd), so every item an
+// item depends on has a smaller ticket and is held by a running CTA - the waits below cannot deadlock, whatever the
+// residency of the grid.  Ticket order, step s = 0, 1, ...:  the X lines of chunk s - lead, then the Y lines of chunk
+// s.  A Y line of chunk c waits until the X lines of chunk c - ring have consumed the slot; an X line of chunk c waits
+// for all Y lines of c.  `lead` steps (more items than there are CTAs) separate producer and consumer, so in steady
+// state the waits are satisfied on the first poll.  Completion is signalled per warp (syncwarp, fence, one atomic);
+// consumers poll with ld.acquire and read the ring with ld.global.cg (L2) - slots are recycled, L1 may be stale.
+struct YxArgs {
+  int zch, nzc, ring, lead, nchunks;
+  unsigned* ticket;         // next item
+  unsigned* ydone;          // [nchunks] warps that finished a Y line of the chunk
+  unsigned* xdone;          // [nchunks] warps that finished an X line of the chunk
+};
+
+// Polls are relaxed loads: an acquire load invalidates the whole L1 of the SM (CCTL.IVALL) on every poll, and the
+// only data ordered behind a poll - the ring - is read with ld.global.cg, which never looks at L1.
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void wait_count(const unsigned* p, unsigned target) {
+  while (ld_acquire_u32(p) < target) __nanosleep(64);
+}
+
+template <int RMAX>
+__global__ void __launch_bounds__(FftLaunch<RMAX>::THREADS, FftLaunch<RMAX>::MINB)
+fft_pass_yx_kernel(FftGeom g, YxArgs a, const double2* __restrict__ T1, double2* T2c, double2* __restrict__ X) {
+  extern __shared__ __align__(16) unsigned char fft_smem[];
+  const int nmax = max(g.n1, g.n2);
+  double2* bufs = reinterpret_cast<double2*>(fft_smem);      // [2][nmax][FFT_B] exchange buffers
+  double2* twy = bufs + 2 * nmax * FFT_B;                    // [n2]
+  double2* twx = twy + g.n2;                                 // [n1]
+  int4* srun = reinterpret_cast<int4*>(twx + g.n1);          // [nplane] y-run of every active x-plane
+  int* sxsrc = reinterpret_cast<int*>(srun + g.nplane);      // [n1] plane holding each x row (or -1)
+  unsigned* sticket = reinterpret_cast<unsigned*>(sxsrc + g.n1);   // [2]
+  const int tid = threadIdx.x, q = tid / FFT_B, b = tid % FFT_B, lane = tid & 31;
+  const unsigned nwarps = (blockDim.x + 31) >> 5;             // the last warp may be half full (16-thread q slots)
+  for (int i = tid; i < g.n2; i += blockDim.x) twy[i] = g.tw[1][i];
+  for (int i = tid; i < g.n1; i += blockDim.x) {
+    twx[i] = g.tw[0][i];
+    sxsrc[i] = g.xsrc[i];
+  }
+  for (int i = tid; i < g.nplane; i += blockDim.x) srun[i] = g.plane_run[i];
+  if (tid == 0) sticket[0] = atomicAdd(a.ticket, 1u);
+  __syncthreads();
+  const unsigned items_x = (unsigned)g.n2 * a.zch, items_y = (unsigned)g.nplane * a.zch;
+  const unsigned per_step = items_x + items_y;
+  const unsigned total = (unsigned)(a.nchunks + a.lead) * per_step;
+  const long plane = (long)g.n2 * g.n3;
+  const long slot_elems = (long)g.nplane * g.n2 * a.zch * FFT_B;
+  unsigned cur = sticket[0];
+  // what item `t` must wait for: (counter, target), counter == nullptr when nothing
+  auto dependency = [&](unsigned t, const unsigned*& ctr, unsigned& target) {
+    ctr = nullptr;
+    target = 0;
+    if (t >= total) return;
+    const int step = (int)(t / per_step);
+    const unsigned r = t % per_step;
+    if (r < items_x) {
+      const int c = step - a.lead;
+      if (c >= 0) { ctr = a.ydone + c; target = items_y * nwarps; }
+    } else {
+      const int c = step;
+      if (c < a.nchunks && c >= a.ring) { ctr = a.xdone + (c - a.ring); target = items_x * nwarps; }
+    }
+  };
+  // lane 0 of every warp: value of the dependency counter of the CURRENT item, sampled during the previous item
+  unsigned seen = 0;
+  {
+    const unsigned* ctr; unsigned target;
+    dependency(cur, ctr, target);
+    if (lane == 0 && ctr) seen = ld_acquire_u32(ctr);
+  }
+  unsigned* pending = nullptr;      // completion of the previous item, not yet published (lane 0)
+  auto publish = [&]() {
+    if (lane == 0 && pending) red_release_add(pending, 1u);
+    pending = nullptr;
+  };
+  for (int it = 0; cur < total; it++) {
+    if (tid == 0) sticket[(it + 1) & 1] = atomicAdd(a.ticket, 1u);     // next item, off the critical path
+    const int step = (int)(cur / per_step);
+    unsigned r = cur % per_step;
+    const bool isx = r < items_x;
+    const int c = isx ? step - a.lead : step;
+    const bool valid = isx ? (c >= 0) : (c < a.nchunks);
+    if (!isx) r -= items_x;
+    const int row = (int)(r / a.zch), zz = (int)(r % a.zch);           // X: row = y;  Y: row = plane
+    int grp = 0, z = 0;
+    if (valid) {
+      grp = c / a.nzc;
+      z = (c % a.nzc) * a.zch + zz;
+    }
+    const bool work = valid && z < g.n3;
+    double2* buf = bufs + (it & 1) * nmax * FFT_B;
+    double2* ring = T2c + (long)(valid ? c % a.ring : 0) * slot_elems;
+    if (work) {
+      const unsigned* ctr; unsigned target;
+      dependency(cur, ctr, target);
+      if (lane == 0 && ctr && seen < target) {
+        publish();                 // never wait while holding an unpublished completion
+        wait_count(ctr, target);
+      }
+      __syncwarp();
+      if (isx) {
+        if (q < g.r2[0]) {
+          const double2* in = ring + ((long)row * a.zch + zz) * FFT_B + b;
+          const long pstride = (long)g.n2 * a.zch * FFT_B;
+          auto load = [&](int x) {
+            const int p = sxsrc[x];
+            return p >= 0 ? __ldcg(in + (long)p * pstride) : make_double2(0, 0);
+          };
+          const int R2 = g.r2[0];
+#define P1(R) line_phase1<R>(buf, twx, R2, q, b, load)
+          PAWB200_RADIX_SWITCH(g.r1[0], P1)
+#undef P1
+        }
+      } else {
+        if (q < g.r2[1]) {
+          const int4 run = srun[row];
+          const double2* in = T1 + ((long)grp * g.ncol * g.n3 + z) * FFT_B + b;
+          const long cstride = (long)g.n3 * FFT_B;
+          const int n2 = g.n2;
+          auto load = [&](int y) {
+            int d = y - run.z;
+            if (d < 0) d += n2;
+            if (d >= run.y) return make_double2(0, 0);
+            const int col = run.x + (d < run.w ? run.y - run.w + d : d - run.w);
+            return __ldg(in + (long)col * cstride);
+          };
+          const int R2 = g.r2[1];
+#define P1(R) line_phase1<R>(buf, twy, R2, q, b, load)
+          PAWB200_RADIX_SWITCH(g.r1[1], P1)
+#undef P1
+        }
+      }
+    }
+    __syncthreads();
+    const unsigned nxt = sticket[(it + 1) & 1];
+    // The previous item's stores were issued a whole phase ago: publishing them now costs a short fence.  The
+    // next item's dependency counter is sampled here too, so that its value is in a register when the item starts.
+    publish();
+    {
+      const unsigned* ctr; unsigned target;
+      dependency(nxt, ctr, target);
+      seen = (lane == 0 && ctr) ? ld_acquire_u32(ctr) : 0u;
+    }
+    if (work) {
+      if (isx) {
+        if (q < g.r1[0]) {
+          double2* out = X + ((long)grp * g.n1 * plane + (long)row * g.n3 + z) * FFT_B + b;
+          auto store = [&](int x, double2 v) { out[(long)x * plane * FFT_B] = v; };
+          const int R1 = g.r1[0];
+#define P2(R) line_phase2<R>(buf, R1, q, b, store)
+          PAWB200_RADIX_SWITCH(g.r2[0], P2)
+#undef P2
+        }
+      } else {
+        if (q < g.r1[1]) {
+          double2* out = ring + ((long)row * g.n2 * a.zch + zz) * FFT_B + b;
+          const long ystride = (long)a.zch * FFT_B;
+          auto store = [&](int y, double2 v) { __stcg(out + (long)y * ystride, v); };
+          const int R1 = g.r1[1];
+#define P2(R) line_phase2<R>(buf, R1, q, b, store)
+          PAWB200_RADIX_SWITCH(g.r2[1], P2)
+#undef P2
+        }
+      }
+    }
+    if (valid) {        // padded z (z >= n3) items only count
+      __syncwarp();
+      pending = isx ? a.xdone + c : a.ydone + c;
+    }
+    cur = nxt;
+  }
+  publish();
 }
 
 }  // namespace pawb200

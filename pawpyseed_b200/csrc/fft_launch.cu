@@ -1,0 +1,206 @@
+// Launchers of the pruned band-interleaved inverse 3-D FFT (kernels: fft3d.cuh).  One launcher per pass,
+// templated on the largest radix of ITS axis (10 / 12 / 14 / 16 / 20): thread count, register budget and resident
+// CTAs follow the axis, not the worst axis of the grid.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <stdexcept>
+#include <string>
+
+#include "fft3d.cuh"
+
+namespace pawb200 {
+
+namespace {
+
+#define FFT_CUDA_OK(expr)                                                                   \
+  do {                                                                                      \
+    cudaError_t e_ = (expr);                                                                \
+    if (e_ != cudaSuccess)                                                                  \
+      throw std::runtime_error(std::string("CUDA: ") + cudaGetErrorString(e_) + " at " +    \
+                               __FILE__ + ":" + std::to_string(__LINE__));                  \
+  } while (0)
+
+constexpr int kFftSmemOptIn = 227 * 1024;
+
+inline unsigned fft_grid_dim(long lines, int occ, int num_sms) {
+  return (unsigned)std::min<long>(lines, (long)num_sms * std::max(occ, 1));
+}
+
+// Resident CTAs per SM of a kernel at a given block size / dynamic shared memory, cached per (kernel, threads,
+// smem): grids differ between wavefunctions of one process (config 2 and config 3 in one bench run).
+struct OccKey {
+  const void* fn; int threads; size_t smem;
+  bool operator<(const OccKey& o) const {
+    return fn != o.fn ? fn < o.fn : threads != o.threads ? threads < o.threads : smem < o.smem;
+  }
+};
+std::map<OccKey, int> g_occ;
+std::map<const void*, bool> g_attr_set;
+
+template <class K>
+int cached_occupancy(K kernel, int threads, size_t smem) {
+  const void* fn = (const void*)kernel;
+  if (!g_attr_set[fn]) {
+    FFT_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFftSmemOptIn));
+    g_attr_set[fn] = true;
+  }
+  const OccKey key{fn, threads, smem};
+  auto it = g_occ.find(key);
+  if (it != g_occ.end()) return it->second;
+  int occ = 0;
+  FFT_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem));
+  occ = std::max(occ, 1);
+  g_occ[key] = occ;
+  return occ;
+}
+
+template <int RMAX>
+void launch_pass_z(const FftGeom& g, const FftInput& in, int s0, int ns, int ng, double scale, double2* T1,
+                   int num_sms, cudaStream_t st) {
+  const int threads = std::max(g.r1[2], g.r2[2]) * FFT_B;
+  const size_t smem = (size_t)(2 * g.n3 * FFT_B + g.n3) * sizeof(double2);
+  const bool runs = g.col_run != nullptr && in.Cil != nullptr;
+  if (runs) {
+    const int occ = cached_occupancy(fft_pass_z_kernel<RMAX>, threads, smem);
+    fft_pass_z_kernel<RMAX><<<fft_grid_dim((long)ng * g.ncol, occ, num_sms), threads, smem, st>>>(
+        g, in.Cil, in.ldil, s0, ns, scale, T1, ng);
+  } else {
+    const int occ = cached_occupancy(fft_pass_z_staged_kernel<RMAX>, threads, smem);
+    fft_pass_z_staged_kernel<RMAX><<<fft_grid_dim((long)ng * g.ncol, occ, num_sms), threads, smem, st>>>(
+        g, in.C, in.ldc, in.halves, in.half_len, s0, ns, scale, T1, ng);
+  }
+}
+
+template <int RMAX>
+void launch_pass_y(const FftGeom& g, int ng, const double2* T1, double2* T2, int num_sms, cudaStream_t st) {
+  const int threads = std::max(g.r1[1], g.r2[1]) * FFT_B;
+  const size_t smem = (size_t)(2 * g.n2 * FFT_B + g.n2) * sizeof(double2) + g.n2 * sizeof(int);
+  const int occ = cached_occupancy(fft_pass_y_kernel<RMAX>, threads, smem);
+  fft_pass_y_kernel<RMAX><<<fft_grid_dim((long)ng * g.nplane * ((g.n3 + FFT_ZC - 1) / FFT_ZC), occ, num_sms), threads,
+                            smem, st>>>(g, T1, T2, ng);
+}
+
+template <int RMAX>
+void launch_pass_x(const FftGeom& g, int ng, const double2* T2, double2* X, int num_sms, cudaStream_t st) {
+  const int threads = std::max(g.r1[0], g.r2[0]) * FFT_B;
+  const size_t smem = (size_t)(2 * g.n1 * FFT_B + g.n1) * sizeof(double2) + g.n1 * sizeof(int);
+  const int occ = cached_occupancy(fft_pass_x_kernel<RMAX>, threads, smem);
+  fft_pass_x_kernel<RMAX><<<fft_grid_dim((long)ng * g.n2 * g.n3, occ, num_sms), threads, smem, st>>>(g, T2, X, ng);
+}
+
+inline int yx_threads(const FftGeom& g) {
+  return std::max(std::max(g.r1[0], g.r2[0]), std::max(g.r1[1], g.r2[1])) * FFT_B;
+}
+inline size_t yx_smem(const FftGeom& g) {
+  const int nmax = std::max(g.n1, g.n2);
+  return (size_t)(2 * nmax * FFT_B + g.n1 + g.n2) * sizeof(double2) + (size_t)g.nplane * sizeof(int4) +
+         (size_t)g.n1 * sizeof(int) + 2 * sizeof(unsigned) + 16;
+}
+
+template <int RMAX>
+int yx_occupancy(const FftGeom& g) {
+  return cached_occupancy(fft_pass_yx_kernel<RMAX>, yx_threads(g), yx_smem(g));
+}
+
+template <int RMAX>
+void launch_pass_yx(const FftGeom& g, const YxConfig& yx, int ng, const double2* T1, double2* ring, unsigned* flags,
+                    double2* X, cudaStream_t st) {
+  YxArgs a;
+  a.zch = yx.zch; a.nzc = yx.nzc; a.ring = yx.ring; a.lead = yx.lead;
+  a.nchunks = ng * yx.nzc;
+  a.ticket = flags;
+  a.ydone = flags + 8;
+  a.xdone = flags + 8 + a.nchunks;
+  FFT_CUDA_OK(cudaMemsetAsync(flags, 0, yx.flag_words(ng) * sizeof(unsigned), st));
+  fft_pass_yx_kernel<RMAX><<<yx.grid, yx_threads(g), yx_smem(g), st>>>(g, a, T1, ring, X);
+}
+
+}  // namespace
+
+#define PAWB200_AXIS_SWITCH(r, CALL) \
+  do {                               \
+    if ((r) <= 10) { CALL(10); }     \
+    else if ((r) <= 12) { CALL(12); } \
+    else if ((r) <= 14) { CALL(14); } \
+    else if ((r) <= 16) { CALL(16); } \
+    else { CALL(20); }               \
+  } while (0)
+
+void init_small_twiddles() {
+  static bool done = false;
+  if (done) return;
+  double2 h[FFT_MAXR + 1][FFT_MAXR];
+  memset(h, 0, sizeof(h));
+  for (int R = 1; R <= FFT_MAXR; R++)
+    for (int m = 0; m < R; m++) {
+      const long double a = 2.0L * 3.141592653589793238462643383279502884L * m / R;
+      h[R][m] = make_double2((double)cosl(a), (double)sinl(a));
+    }
+  FFT_CUDA_OK(cudaMemcpyToSymbol(c_small_tw, h, sizeof(h)));
+  done = true;
+}
+
+YxConfig plan_fused_yx(const FftGeom& g, int num_sms, size_t l2_budget_bytes) {
+  YxConfig c;
+  // Opt-in (PAWB200_FFT_FUSED=1): measured on config 2 the fused pass moves 43 % fewer DRAM bytes (ncu: 2.27 GB
+  // instead of 4.0 GB per 128 bands) but the per-line inter-CTA synchronisation makes it slower than the two
+  // stand-alone passes (1.29 ms against 0.88 ms), which are latency- rather than bandwidth-bound.
+  const char* e = getenv("PAWB200_FFT_FUSED");
+  if (!e || atoi(e) == 0) return c;
+  if (!g.plane_run) return c;
+  if (yx_smem(g) > (size_t)kFftSmemOptIn) return c;
+  const int ryx = std::max(std::max(g.r1[0], g.r2[0]), std::max(g.r1[1], g.r2[1]));
+  int occ = 1;
+#define OCC(R) occ = yx_occupancy<R>(g)
+  PAWB200_AXIS_SWITCH(ryx, OCC);
+#undef OCC
+  const long grid = (long)num_sms * occ;
+  // z values per chunk: the largest of 4..1 whose ring fits the L2 budget, preferring divisors of n3 (no padding)
+  int best = 0;
+  for (int pass = 0; pass < 2 && !best; pass++)
+    for (int zch = 4; zch >= 1 && !best; zch--) {
+      if (pass == 0 && g.n3 % zch) continue;
+      const long per_step = (long)(g.n2 + g.nplane) * zch;
+      const int lead = (int)((2 * grid + per_step - 1) / per_step) + 1;   // a CTA holds an item and the next ticket
+      const size_t bytes = (size_t)(2 * lead) * g.nplane * g.n2 * zch * FFT_B * sizeof(double2);
+      if (bytes <= l2_budget_bytes) best = zch;
+    }
+  if (!best) return c;
+  const long per_step = (long)(g.n2 + g.nplane) * best;
+  c.zch = best;
+  c.nzc = (g.n3 + best - 1) / best;
+  c.lead = (int)((2 * grid + per_step - 1) / per_step) + 1;
+  c.ring = 2 * c.lead;
+  c.grid = (int)grid;
+  c.ring_bytes = (size_t)c.ring * g.nplane * g.n2 * best * FFT_B * sizeof(double2);
+  c.ok = true;
+  return c;
+}
+
+int launch_pruned_passes(const FftGeom& g, const FftInput& in, int s0, int ns, int ng, double scale,
+                         const FftWork& w, const YxConfig* yx, double2* X, int num_sms, cudaStream_t st) {
+  const int rz = std::max(g.r1[2], g.r2[2]), ry = std::max(g.r1[1], g.r2[1]), rx = std::max(g.r1[0], g.r2[0]);
+#define PASS_Z(R) launch_pass_z<R>(g, in, s0, ns, ng, scale, w.T1, num_sms, st)
+  PAWB200_AXIS_SWITCH(rz, PASS_Z);
+#undef PASS_Z
+  if (yx && yx->ok) {
+    const int ryx = std::max(ry, rx);
+#define PASS_YX(R) launch_pass_yx<R>(g, *yx, ng, w.T1, w.T2, w.flags, X, st)
+    PAWB200_AXIS_SWITCH(ryx, PASS_YX);
+#undef PASS_YX
+    FFT_CUDA_OK(cudaGetLastError());
+    return 2;
+  }
+#define PASS_Y(R) launch_pass_y<R>(g, ng, w.T1, w.T2, num_sms, st)
+#define PASS_X(R) launch_pass_x<R>(g, ng, w.T2, X, num_sms, st)
+  PAWB200_AXIS_SWITCH(ry, PASS_Y);
+  PAWB200_AXIS_SWITCH(rx, PASS_X);
+#undef PASS_Y
+#undef PASS_X
+  FFT_CUDA_OK(cudaGetLastError());
+  return 3;
+}
+
+}  // namespace pawb200

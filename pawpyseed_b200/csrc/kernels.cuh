@@ -537,6 +537,156 @@ sphere_project_il_kernel(const SiteDev* __restrict__ sites, const int* __restric
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// (a5) the same contraction with REAL tables: half the FP64 tensor work and half the table bytes
+// ---------------------------------------------------------------------------------------
+// The table value of a channel is R_n(r) Y_lm(r^) (projector.c:259-271 contracts conj(value) with the sample), and
+// Y_l,-m = (-1)^m conj(Y_l,m) (utils.c:377-449 builds both from the same Legendre / cexp factors; they agree to
+// rounding).  So per radial channel n only the 2l+1 REAL functions
+//     row(m > 0) = Re T(n,+m),   row(m = 0) = T(n,0) (real),   row(m < 0) = Im T(n,+|m|)
+// are contracted with the sample x' = x * dv * exp(i k.path) (the band-independent Bloch phase now multiplies the
+// sample, exactly where projector.c:262 applies it): Q[row] = sum_pt U[row][pt] x'[pt] is 2 DMMA per k-step instead
+// of 4, and the channel values follow in the epilogue,
+//     P(+m) = Q(+m) - i Q(-m),    P(-m) = (-1)^m (Q(+m) + i Q(-m)),    P(0) = Q(0).
+// U does not depend on k (built once per table set); per k only the S phase factors are rebuilt.
+__global__ void __launch_bounds__(256)
+real_table_kernel(const SiteDev* __restrict__ sites, const int* __restrict__ chan_m,
+                  const double2* __restrict__ table, double* __restrict__ ureal) {
+  const SiteDev sd = sites[blockIdx.y];
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < sd.npts_pad; p += gridDim.x * blockDim.x)
+    for (int c = 0; c < sd.nlm; c++) {
+      const int m = chan_m[sd.lm_off + c];
+      const long o = sd.tab_off + (long)c * sd.npts_pad + p;
+      ureal[o] = m >= 0 ? table[o].x : table[o - 2L * m * sd.npts_pad].y;     // partner channel (n, +|m|) is c + 2|m|
+    }
+}
+
+// phk[pt] = dv * exp(i k_cart . path[pt])   [projector.c:259-263]
+__global__ void __launch_bounds__(256)
+phase_points_kernel(const double* __restrict__ path, long path_ld, long npts, double2* __restrict__ phk, double kx,
+                    double ky, double kz, double dv) {
+  for (long q = (long)blockIdx.x * blockDim.x + threadIdx.x; q < npts; q += (long)gridDim.x * blockDim.x) {
+    const double kr = kx * path[q] + ky * path[path_ld + q] + kz * path[2 * path_ld + q];
+    double s, c;
+    sincos(kr, &s, &c);
+    phk[q] = make_double2(dv * c, dv * s);
+  }
+}
+
+constexpr int PROJ_LDU = PROJ_KT + 4;   // double row stride of the real table tile (rows 0..3 cover all 32 banks)
+
+template <int MT>
+inline size_t sphere_project_real_smem() {
+  return (size_t)PROJ_STAGES * (sizeof(double2) * (PROJ_KT * PROJ_LDB + PROJ_KT) + sizeof(double) * 8 * MT * PROJ_LDU);
+}
+
+template <int MT>
+__global__ void __launch_bounds__(128)
+sphere_project_real_kernel(const SiteDev* __restrict__ sites, const int* __restrict__ site_list,
+                           const int* __restrict__ idx, const double* __restrict__ ureal,
+                           const double2* __restrict__ phk, const int* __restrict__ chan_m,
+                           const double2* __restrict__ X, long ngrid, int nslot, int ngroups,
+                           double2* __restrict__ P, long ldp, int slot0, int idx_cap) {
+  constexpr int IL = PROJ_IL;
+  const SiteDev sd = sites[site_list[blockIdx.y]];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double2* sB = reinterpret_cast<double2*>(smem_raw);                       // [ST][KT][LDB] samples
+  double2* sPh = sB + PROJ_STAGES * PROJ_KT * PROJ_LDB;                     // [ST][KT]      phase factors
+  double* sU = reinterpret_cast<double*>(sPh + PROJ_STAGES * PROJ_KT);      // [ST][8*MT][LDU] real table rows
+  int* sIdx = reinterpret_cast<int*>(sU + PROJ_STAGES * 8 * MT * PROJ_LDU); // [idx_cap] sphere index list
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int sbase = blockIdx.x * PROJ_NB;
+  const int nk = sd.npts_pad / PROJ_KT;
+  for (int e = tid; e < sd.npts_pad && e < idx_cap; e += 128) sIdx[e] = __ldg(idx + sd.pt_off + e);
+  for (int e = tid; e < PROJ_STAGES * 8 * MT * PROJ_LDU; e += 128) {
+    const int row = (e / PROJ_LDU) % (8 * MT);
+    if (row >= sd.nlm) sU[e] = 0.0;                 // channel padding rows, never overwritten
+  }
+  __syncthreads();
+  int grp = (sbase + lane) / IL;
+  if (grp >= ngroups) grp = ngroups - 1;          // tail CTA: duplicate the last group, discarded on store
+  const double2* xsrc = X + (long)grp * ngrid * IL + (lane & (IL - 1));
+
+  auto issue = [&](int kt, int st) {
+    if (kt < nk) {
+#pragma unroll
+      for (int q = 0; q < PROJ_KT / 4; q++) {
+        const int pt = warp + 4 * q;
+        const int ip = kt * PROJ_KT + pt;
+        const int g = ip < idx_cap ? sIdx[ip] : __ldg(idx + sd.pt_off + ip);   // warp-uniform -> broadcast
+        cp_async16(sB + (st * PROJ_KT + pt) * PROJ_LDB + lane, xsrc + (long)g * IL);
+      }
+      // real table tile: nlm rows x 32 points (16 chunks of 16 B per row); a warp covers two rows per pass
+      for (int row = 2 * warp + (lane >> 4); row < sd.nlm; row += 8)
+        cp_async16(sU + (st * 8 * MT + row) * PROJ_LDU + 2 * (lane & 15),
+                   ureal + sd.tab_off + (long)row * sd.npts_pad + kt * PROJ_KT + 2 * (lane & 15));
+      if (warp == 3) cp_async16(sPh + st * PROJ_KT + lane, phk + sd.pt_off + kt * PROJ_KT + lane);
+    }
+    cp_async_commit();
+  };
+
+  double qr[MT][2], qi[MT][2];
+#pragma unroll
+  for (int m = 0; m < MT; m++) qr[m][0] = qr[m][1] = qi[m][0] = qi[m][1] = 0;
+#pragma unroll
+  for (int s = 0; s < PROJ_STAGES - 1; s++) issue(s, s);
+  for (int kt = 0; kt < nk; kt++) {
+    cp_async_wait<PROJ_STAGES - 2>();
+    __syncthreads();
+    issue(kt + PROJ_STAGES - 1, (kt + PROJ_STAGES - 1) % PROJ_STAGES);
+    const int st = kt % PROJ_STAGES;
+    const double2* tB = sB + st * PROJ_KT * PROJ_LDB;
+    const double2* tP = sPh + st * PROJ_KT;
+    const double* tU = sU + st * 8 * MT * PROJ_LDU;
+#pragma unroll
+    for (int kk = 0; kk < PROJ_KT / 4; kk++) {
+      const double2 x = tB[(4 * kk + (lane & 3)) * PROJ_LDB + 8 * warp + (lane >> 2)];
+      const double2 ph = tP[4 * kk + (lane & 3)];
+      const double bx = x.x * ph.x - x.y * ph.y, by = x.x * ph.y + x.y * ph.x;     // x' = x dv e^{i k.r}
+#pragma unroll
+      for (int m = 0; m < MT; m++) {
+        const double u = tU[(8 * m + (lane >> 2)) * PROJ_LDU + 4 * kk + (lane & 3)];
+        dmma884(qr[m][0], qr[m][1], u, bx);
+        dmma884(qi[m][0], qi[m][1], u, by);
+      }
+    }
+  }
+  cp_async_wait<0>();
+  __syncthreads();                                 // every warp is done with the stage buffers: reuse sB for Q
+  // Q fragment: row (channel) = 8m + lane>>2, cols (slots) = 2*(lane&3)+{0,1}  ->  sQ[warp][channel][8 slots]
+  double2* sQ = sB + warp * (8 * MT * 8);
+#pragma unroll
+  for (int m = 0; m < MT; m++)
+#pragma unroll
+    for (int c = 0; c < 2; c++)
+      sQ[(8 * m + (lane >> 2)) * 8 + 2 * (lane & 3) + c] = make_double2(qr[m][c], qi[m][c]);
+  __syncwarp();
+#pragma unroll
+  for (int m = 0; m < MT; m++) {
+    const int ch = 8 * m + (lane >> 2);
+    if (ch < sd.nlm) {
+      const int mm = __ldg(chan_m + sd.lm_off + ch);
+#pragma unroll
+      for (int c = 0; c < 2; c++) {
+        const int col = 2 * (lane & 3) + c;
+        const int s = sbase + 8 * warp + col;
+        if (s >= nslot) continue;
+        const double2 q0 = sQ[ch * 8 + col];
+        double2 out = q0;
+        if (mm > 0) {                               // P(+m) = Q(+m) - i Q(-m)
+          const double2 qs = sQ[(ch - 2 * mm) * 8 + col];
+          out = make_double2(q0.x + qs.y, q0.y - qs.x);
+        } else if (mm < 0) {                        // P(-m) = (-1)^m (Q(+m) + i Q(-m))
+          const double2 qc = sQ[(ch - 2 * mm) * 8 + col];
+          const double sg = (mm & 1) ? -1.0 : 1.0;
+          out = make_double2(sg * (qc.x - q0.y), sg * (qc.y + q0.x));
+        }
+        P[(long)(slot0 + s) * ldp + sd.lm_off + ch] = out;
+      }
+    }
+  }
+}
+
 inline size_t sphere_project_smem(int MT) {
   return sizeof(double2) * PROJ_STAGES * (PROJ_KT * PROJ_LDB + 8 * MT * PROJ_LDA);
 }

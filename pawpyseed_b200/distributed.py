@@ -1,4 +1,5 @@
-"""One-process-per-GPU sharding of the band-projection path over (k,spin) blocks.
+"""One-process-per-GPU sharding of the band-projection path: (k,spin) blocks over ranks (level 1) and, for jobs
+with fewer blocks than GPUs, band blocks of one (k,spin) block over ranks (level 2).
 
 The overlap operator is block diagonal in k-point and spin (pseudoprojector.c:71-89,
 projector.c:872-887 loop over independent `kpt_num`), so rank r owns the blocks
@@ -129,6 +130,100 @@ def gather_projection_blocks(pr, own_kappas, nkappa: int, group=None, pinned_out
     else:
         host = valid.cpu().numpy()
     return host.view(np.complex128).reshape(nkappa, nS, nR)
+
+
+# --------------------------------------------------------------------------------------------
+# level 2: band blocks of ONE (k,spin) block over ranks (jobs with fewer blocks than GPUs)
+# --------------------------------------------------------------------------------------------
+def set_band_shard(rank: int, world: int):
+    """Wavefunctions read after this call hold only the bands [rank*per, (rank+1)*per), per = ceil(nband/world)."""
+    from . import _lib
+    _lib.lib().pawb200_set_band_shard(int(rank), int(world))
+
+
+class _DeviceRows:
+    """A row buffer inside the library (coefficients / projections of one (k,spin) block) viewed as a torch tensor."""
+
+    def __init__(self, wf, which, kappa):
+        import ctypes as C
+        import torch
+        from . import _lib
+        ld, rows, lo, hi = C.c_long(0), C.c_int(0), C.c_int(0), C.c_int(0)
+        ptr = _lib.lib().pawb200_get_device_buffer(wf.wf_ptr, int(which), int(kappa), C.byref(ld), C.byref(rows),
+                                                   C.byref(lo), C.byref(hi))
+        _lib.check()
+        self.rows, self.lo, self.hi = rows.value, lo.value, hi.value
+        elem = 8 if which == 0 else 16                     # complex64 / complex128
+        self.row_bytes = ld.value * elem
+        self.__cuda_array_interface__ = {"shape": (self.rows * self.row_bytes,), "typestr": "|u1",
+                                         "data": (int(ptr), False), "version": 2}
+        self.tensor = torch.as_tensor(self, device="cuda").view(self.rows, self.row_bytes)
+
+
+def exchange_rows(buf, per: int, group=None):
+    """In-place all-gather of equal row blocks: `buf` is [world * per, row_bytes] on every rank and rank r has
+    filled rows [r*per, (r+1)*per).  NCCL gathers in place (send = the own slice of the receive buffer)."""
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return buf
+    rank = dist.get_rank(group)
+    own = buf[rank * per:(rank + 1) * per]
+    if dist.get_backend(group) != "nccl":
+        own = own.clone()                                   # gloo: no aliasing between input and output
+    dist.all_gather_into_tensor(buf.view(-1), own.reshape(-1), group=group)
+    return buf
+
+
+def gather_band_blocks(wf, group=None, coefficients=True, projections=True):
+    """All-gather the band blocks of a band-sharded wavefunction in place over NVLink: afterwards every rank holds
+    all rows of C (plane-wave coefficients), P (projections) and W (wave projections, when present) of every
+    resident (k,spin) block.  This is the "allgather of the column blocks before the GEMM" of SURVEY 8e: the
+    basis side of a projection needs it, the wf side does not."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    NK = wf.nwk * wf.nspin
+    for kappa in range(NK):
+        todo = ([0] if coefficients else []) + ([1, 2] if projections else [])
+        for which in todo:
+            try:
+                rows = _DeviceRows(wf, which, kappa)
+            except Exception:
+                if which == 2:
+                    continue                                # no wave projections for this pair
+                raise
+            exchange_rows(rows.tensor, rows.rows // world, group)
+
+
+def band_sharded_projection_matrix(pr, group=None, pinned_out=None, want_host=True):
+    """PAW-corrected overlap matrix of a band-sharded pair: the basis rows are gathered, every rank multiplies the
+    rows of ITS wf bands against the whole basis (`pawb200_projection_matrix_dev` fills only those rows) and the
+    row blocks are all-gathered.  Call after Projector / CProjector._setup_overlap on every rank.
+    Returns [nkappa, nband_wf, nband_basis] complex128 (host array, or the device tensor when not want_host)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if world > 1 else 0
+    gather_band_blocks(pr.basis, group)
+    NK = pr.basis.nwk * pr.basis.nspin
+    nS, nR = pr.wf.nband, pr.basis.nband
+    per = -(-nS // world)
+    full = torch.zeros(NK, world * per, nR * 2, dtype=torch.float64, device="cuda")
+    blk = torch.empty(nS * nR * 2, dtype=torch.float64, device="cuda")
+    for kappa in range(NK):
+        pr._projection_matrix_dev(blk, kappa_range=(kappa, kappa + 1))
+        lo, hi = min(nS, rank * per), min(nS, (rank + 1) * per)
+        full[kappa, lo:hi] = blk.view(nS, nR * 2)[lo:hi]
+        exchange_rows(full[kappa], per, group)
+    out = full[:, :nS]
+    if not want_host:
+        return out
+    if pinned_out is not None:
+        dst = pinned_out[: out.numel()].view(NK, nS, nR * 2)
+        dst.copy_(out, non_blocking=False)
+        host = dst.numpy()
+    else:
+        host = out.cpu().numpy()
+    return np.ascontiguousarray(host).view(np.complex128).reshape(NK, nS, nR)
 
 
 def band_block(nband: int, rank: int, world: int):

@@ -48,12 +48,19 @@ def _worker(rank, world, port, nk, q):
     for j, k in enumerate(own):
         send[j * blk:(j + 1) * blk] = torch.from_numpy(np.ascontiguousarray(full[k]).reshape(-1).view(np.float64))
     got3 = pd.exchange_blocks(send, nk, blk).numpy().view(np.complex128).reshape(full.shape)
+    # level 2: in-place all-gather of band-row blocks (the C / P rows of a band-sharded wavefunction)
+    per_rows, width = 3, 10
+    rows = torch.zeros(world * per_rows, width, dtype=torch.uint8)
+    ref_rows = torch.arange(world * per_rows * width, dtype=torch.int64).remainder(251).to(torch.uint8).view(-1, width)
+    rows[rank * per_rows:(rank + 1) * per_rows] = ref_rows[rank * per_rows:(rank + 1) * per_rows]
+    pd.exchange_rows(rows, per_rows)
+    rows_ok = bool(torch.equal(rows, ref_rows))
     tmax = pd.max_over_ranks(float(rank + 1))
     fake = _FakeWavefunction()
     dens = pd.sharded_chg_density(fake)                       # bands split 4 + 3, one all-reduce
     dens_ok = bool(np.allclose(dens, fake._get_realspace_density(), rtol=0, atol=1e-12))
     q.put((rank, bool(np.array_equal(got, full) and np.array_equal(got2, full) and np.array_equal(got3, full)
-                      and dens_ok), tmax, own))
+                      and dens_ok and rows_ok), tmax, own))
     dist.destroy_process_group()
 
 

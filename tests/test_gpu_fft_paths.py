@@ -151,3 +151,50 @@ def test_chunked_side_stream_gemm_matches_single_gemm(tmp_path):
         outs.append(np.load(out))
     assert outs[0].shape == (2, 300, 300)
     assert rel(outs[1], outs[0]) < 1e-13
+
+
+@pytest.mark.parametrize("world,nband", [(2, 12), (3, 10)])
+def test_band_sharded_projection_equals_unsharded(world, nband):
+    """SURVEY 8e level 2: the bands of one (k,spin) block split over `world` ranks.  The ranks are emulated in one
+    process (pawb200_set_band_shard before each read); the NCCL all-gather of the basis rows is replaced by explicit
+    copies between the ranks' device buffers (the same buffers distributed.gather_band_blocks exchanges).  Every
+    rank's matrix holds only the rows of its wf bands; together they equal the unsharded matrix."""
+    from pawpyseed_b200 import distributed as pd
+    L = _lib.lib()
+    cR, cS = cases.small_case(seed=7, nband=nband), cases.small_case(seed=11, nband=nband, perturb=0.03)
+    cat = [[0, 1], [0, 1], [2, 3], [2, 3], [2, 3], [2, 3]]
+    L.pawb200_set_band_shard(0, 1)
+    R0, S0 = gpu(cR), gpu(cS)
+    pr0 = pawpyc.CProjector(S0, R0)
+    pr0._setup_overlap(cat, False)
+    want = pr0._projection_matrix()
+    try:
+        ranks = []
+        for r in range(world):
+            L.pawb200_set_band_shard(r, world)
+            R, S = gpu(cR), gpu(cS)
+            pr = pawpyc.CProjector(S, R)
+            pr._setup_overlap(cat, False)
+            ranks.append((R, S, pr))
+        NK = 4
+        per = -(-nband // world)
+        # "all-gather" of the basis rows: coefficients, projections, wave projections
+        for which in (0, 1, 2):
+            for kappa in range(NK):
+                views = [pd._DeviceRows(R, which, kappa) for R, _, _ in ranks]
+                assert all(v.rows == per * world * (1 if which == 0 else 1) for v in views)
+                for dst in views:
+                    for src in views:
+                        if src is not dst:
+                            dst.tensor[src.lo:src.hi].copy_(src.tensor[src.lo:src.hi])
+        total = np.zeros_like(want)
+        for r, (R, S, pr) in enumerate(ranks):
+            got = pr._projection_matrix()
+            lo, hi = min(nband, r * per), min(nband, (r + 1) * per)
+            outside = np.ones(nband, bool)
+            outside[lo:hi] = False
+            assert np.all(got[:, outside, :] == 0)          # rows of other ranks' bands stay zero
+            total += got
+        assert rel(total, want) < 1e-12
+    finally:
+        L.pawb200_set_band_shard(0, 1)
