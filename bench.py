@@ -982,6 +982,172 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+# --------------------------------------------------------------------------------------------
+# BASELINE configs 4 and 5: the spinor projection path and the real-space density path (own metrics)
+# --------------------------------------------------------------------------------------------
+def _device_timed(fn, steps, warmup):
+    import torch
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    e0.record()
+    for _ in range(steps):
+        out = fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps, out
+
+
+def run_aux(args):
+    """--config cfg4: noncollinear 128-site cell, 512 spinor bands x 2 k-points - one step = setup_projections
+    (two transforms + up/down projector overlaps per band, projector.c:372-418).
+    --config cfg5: ae_chg_density on a 400^3 grid, 256 bands (128 occupied), 64 sites - one step = the whole
+    density (density.c:158-179: realspace_state + |psi|^2 accumulation per occupied band, grid to the host)."""
+    import torch
+    from pawpyseed_b200 import _lib, pawpyc
+    from oracle import ref_driver as rd
+    torch.cuda.set_device(0)
+    L = _lib.lib()
+    if L.pawb200_device_check() != 0:
+        raise SystemExit("pawpyseed_b200: " + L.pawb200_last_error().decode())
+    L.pawb200_set_host_threads(os.cpu_count() or 1)
+    hbm_peak, hbm_src = load_peaks()
+    threads = os.cpu_count() or 1
+    if args.config == "cfg4":
+        nband = args.nband or 512
+        lat, frac, lab = synth.wurtzite_supercell((4, 2, 2))            # 128 sites
+        lab = lab.astype(np.int32)
+        encut, kpts, kws = 400.0, np.array([[0.0, 0.0, 0.0], [0.5, 0.0, 0.0]]), np.array([0.5, 0.5])
+        gv = [synth.enumerate_gvectors(lat, encut, k) for k in kpts]
+        dim = synth.fft_grid_for(gv)
+        ge = synth.grid_encut(dim, lat)
+        pps = synth.synthetic_pps(["Ga", "N"])
+        img = synth.wavecar_image(lat, encut, kpts, 1, nband, synth.random_coeffs(4, nband), ncl=True, gvecs=gv)
+
+        def read():
+            return pawpyc.CNCLWavefunction(pawpyc.PWFPointer.from_arrays(img, kpts, kws))
+
+        def setup(wf):
+            wf.projector_owner = 0
+            wf._c_projector_setup(len(pps), len(lab), ge, lab, frac, dim, pps)
+            return wf._get_projections(0, 0, 1)
+        wf = read()
+        _lib.reset_timers()
+        ms, _ = _device_timed(lambda: setup(wf), args.steps, args.warmup)
+        tm = _lib.timers()
+        n = args.steps + args.warmup
+        units = nband * len(kpts)
+        e2e_ms, _ = _device_timed(lambda: setup(read()), max(1, min(args.steps, 3)), 1)
+        t0 = time.perf_counter()
+        wf._get_realspace_state(0, 1, 0)
+        first_state = time.perf_counter() - t0
+        st_ms, _ = _device_timed(lambda: wf._get_realspace_state(1, 1, 0), 4, 1)
+        ngrid, npw = int(np.prod(dim)), float(np.mean([len(g) for g in gv]))
+        per_box = 12.0 * npw + 48.0 * ngrid
+        cpu = None
+        if not args.no_cpu and rd.available():
+            nb_s = 32
+            simg = synth.wavecar_image(lat, encut, kpts, 1, nb_s, synth.random_coeffs(4, nb_s), ncl=True, gvecs=gv)
+            os.environ["OMP_NUM_THREADS"] = str(threads)
+            with _Quiet():
+                R = rd.RefWavefunction(simg, kws)
+                t0 = time.perf_counter()
+                R.setup_projections(pps, lab, frac, dim, ge)
+                t_all = time.perf_counter() - t0
+                t_site = R.time_projector_values()
+                R.free()
+            full = t_site + (t_all - t_site) * nband / nb_s
+            cpu = {"value": units / full, "unit": "spinor bands/s", "cores": threads, "kind": "reference",
+                   "sample": "unmodified reference C setup_projections on %d of %d spinor bands x 2 k-points, all 128 "
+                             "sites: %.2f s of which the serial setup_site %.2f s; band part scaled by %d/%d"
+                             % (nb_s, nband, t_all, t_site, nband, nb_s)}
+        line = {"metric": "ncl_spinor_band_projections_per_sec", "value": units / (ms * 1e-3), "unit": "spinor bands/s",
+                "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "noncollinear GaN 128-site cell, ENCUT 400, %d spinor bands, 2 k-points, grid %s"
+                                       % (nband, [int(x) for x in dim]), "npw_per_spinor_half": [len(g) for g in gv],
+                           "l2": "FFT boxes of a launch (8 groups x 16 slots) exceed the 126 MB L2"},
+                "e2e": {"value": units / (e2e_ms * 1e-3), "unit": "spinor bands/s", "h2d_bytes_per_step": int(img.nbytes),
+                        "d2h_bytes_per_step": 16 * int(L.pawb200_num_projections(wf.wf_ptr, 1)), "ms_per_step": e2e_ms},
+                "gpu_launches": int(tm["launches"]),
+                "roofline": {"kernel": "pruned fft3d (pass Z + Y + X), two transforms per spinor band", "bound": "hbm",
+                             "achieved": per_box * tm["boxes_fft"] / (tm["fft_ms"] * 1e-3) / 1e9, "peak": hbm_peak,
+                             "unit": "GB/s", "traffic": None, "peak_source": hbm_src,
+                             "share_of_step": tm["fft_ms"] / n / ms},
+                "stage_ms_per_step": {k: v / n for k, v in tm.items() if k.endswith("_ms")},
+                "ncl_realspace_state": {"first_call_ms": first_state * 1e3, "ms_per_state": st_ms,
+                                        "bytes_to_host_per_state": 2 * 16 * ngrid},
+                "cpu_baseline": cpu}
+        line["roofline"]["frac"] = line["roofline"]["achieved"] / hbm_peak
+        print(json.dumps(line))
+        return
+    # ---- cfg5 ----
+    nband = args.nband or 256
+    dim = np.array([args.grid // 2] * 3, np.int32)                        # fine grid = 2 * dim (pawpyc.pyx:455-461)
+    lat, coords = synth.diamond_supercell(5.43, 2)                        # 64 Si sites
+    encut, kpts, kws = 300.0, np.array([[0.0, 0.0, 0.0]]), np.array([1.0])
+    gv = [synth.enumerate_gvectors(lat, encut, kpts[0])]
+    pps = synth.synthetic_pps(["Si"])
+    labels = np.zeros(len(coords), np.int32)
+    ge = synth.grid_encut(dim, lat)
+    img = synth.wavecar_image(lat, encut, kpts, 1, nband, synth.random_coeffs(5, nband), gvecs=gv)
+    nocc = (nband + 1) // 2
+
+    def make():
+        wf = pawpyc.CWavefunction(pawpyc.PWFPointer.from_arrays(img, kpts, kws))
+        wf.projector_owner = 0
+        wf._c_projector_setup(1, len(coords), ge, labels, coords, dim, pps)
+        return wf
+    wf = make()
+    t0 = time.perf_counter()
+    wf._get_realspace_density()
+    first = time.perf_counter() - t0                                      # builds the AE partial-wave tables
+    _lib.reset_timers()
+    ms, rho = _device_timed(wf._get_realspace_density, args.steps, min(args.warmup, 1))
+    tm = _lib.timers()
+    n = args.steps + min(args.warmup, 1)
+    e2e_ms, _ = _device_timed(lambda: make()._get_realspace_density(), 1, 0)
+    ngrid, npw = int(rho.size), len(gv[0])
+    per_state = 12.0 * npw + 48.0 * ngrid + 32.0 * ngrid                  # SURVEY 8d: scatter + FFT + density RMW
+    vol = abs(np.linalg.det(lat))
+    cpu = None
+    if not args.no_cpu and rd.available():
+        nb_s = 4                                                          # 2 occupied bands
+        simg = synth.wavecar_image(lat, encut, kpts, 1, nb_s, synth.random_coeffs(5, nb_s), gvecs=gv)
+        os.environ["OMP_NUM_THREADS"] = str(threads)
+        with _Quiet():
+            R = rd.RefWavefunction(simg, kws)
+            R.setup_projections(pps, labels, coords, dim, ge)
+            t0 = time.perf_counter()
+            R.chg_density()
+            t_ref = time.perf_counter() - t0
+            R.free()
+        cpu = {"value": 2 / t_ref, "unit": "AE states/s", "cores": threads, "kind": "reference",
+               "sample": "unmodified reference C ae_chg_density on the same cell and %d^3 grid with 2 occupied bands: "
+                         "%.1f s (serial over bands, density.c:158-179)" % (args.grid, t_ref)}
+    line = {"metric": "ae_states_per_sec", "value": nocc / (ms * 1e-3), "unit": "AE states/s", "n_gpus": 1,
+            "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "ae_chg_density (write_density path) on a %d^3 grid, %d bands (%d occupied), "
+                                   "64 Si sites, ENCUT 300, Gamma" % (args.grid, nband, nocc), "npw": npw,
+                       "l2": "every box (%.2f GB) exceeds the 126 MB L2" % (16 * ngrid / 1e9)},
+            "e2e": {"value": nocc / (e2e_ms * 1e-3), "unit": "AE states/s", "h2d_bytes_per_step": int(img.nbytes),
+                    "d2h_bytes_per_step": 8 * ngrid, "ms_per_step": e2e_ms,
+                    "note": "read_wavefunctions + setup_projections + AE tables + density, grid on the host"},
+            "gpu_launches": int(tm["launches"]),
+            "roofline": {"kernel": "pruned fft3d + Bloch phase + augmentation + |psi|^2 accumulation per state",
+                         "bound": "hbm", "achieved": per_state * nocc / (ms * 1e-3) / 1e9, "peak": hbm_peak,
+                         "unit": "GB/s", "traffic": None, "peak_source": hbm_src,
+                         "algorithmic_bytes_per_state": per_state},
+            "stage_ms_per_step": {k: v / n for k, v in tm.items() if k.endswith("_ms")},
+            "first_call_ms": first * 1e3,
+            "density_integral": float(rho.sum() * vol / rho.size),
+            "cpu_baseline": cpu}
+    line["roofline"]["frac"] = line["roofline"]["achieved"] / hbm_peak
+    print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -998,8 +1164,16 @@ def main():
                     help="config 2 only: N GPUs = N k-points of the config's shape (weak scaling over (k,spin) blocks)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the config-2 secondary measurement")
+    ap.add_argument("--grid", type=int, default=400, help="cfg5: fine grid points per axis")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.config in ("cfg4", "cfg5"):
+        if int(os.environ.get("RANK", 0)) == 0:
+            if args.impl == "reference":
+                print(json.dumps({"impl": "reference", "unavailable": "configs 4/5 report their CPU leg inside the "
+                                  "b200 line (cpu_baseline)"}))
+            else:
+                run_aux(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_b200(args)

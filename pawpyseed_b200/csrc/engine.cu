@@ -1110,6 +1110,7 @@ DevBuf g_grid;   // FFT box batch, reused across calls
 struct PrunedPlan {
   bool ok = false;
   FftGeom g;
+  int max_plane_cols = 0;
   DevBuf col_start, col_cnt, zpos, col_run, plane_run, ysrc, xsrc, tw[3];
 };
 
@@ -1208,6 +1209,7 @@ std::shared_ptr<PrunedPlan> build_pruned_plan(const pawb200_pswf* wf, int kap, c
     plane_run[p] = gap < 0 ? make_int4(c0, cnt, col_ypos[c0], cnt)
                            : make_int4(c0, cnt, col_ypos[c0 + gap + 1], cnt - (gap + 1));
   }
+  for (int p = 0; p < g.nplane; p++) P->max_plane_cols = std::max(P->max_plane_cols, plane_ncol[p]);
   if (planes_ok) P->plane_run = upload(plane_run);
   g.plane_run = planes_ok ? P->plane_run.as<int4>() : nullptr;
   P->col_start = upload(col_start); P->col_cnt = upload(col_cnt); P->zpos = upload(zpos);
@@ -1289,7 +1291,7 @@ void pruned_fft(const pawb200_pswf* wf, int kap, const PrunedPlan& P, int slot0,
     const int ns = std::min(nslot - g0 * FFT_B, ng * FFT_B);
     wait_coeffs(wf, kap, s0 / h, (s0 + ns + h - 1) / h);
     count_launch(launch_pruned_passes(g, in, s0, ns, ng, scale, w, &yx, X + (long)g0 * ngrid * FFT_B, g_num_sms,
-                                      g_stream));
+                                      g_stream, P.max_plane_cols));
     trace_mark("fft done slots " + std::to_string(s0) + "+" + std::to_string(ns), g_stream);
   }
   check_launch();
@@ -2006,10 +2008,23 @@ void state_to_host(pawb200_c128* out, int band, int kap, pawb200_pswf* wf, const
   require_device();
   check_kpoint(wf, band, kap);
   SiteTables& T = ae_tables(wf, fftg, labels, coords);
-  DevBuf inv = build_inverse_map(wf, kap, fftg);
   const int h = wf->halves();
-  realspace_boxes(wf, kap, band * h, h, fftg, T, inv);
   const long ngrid = (long)fftg[0] * fftg[1] * fftg[2];
+  std::shared_ptr<PrunedPlan> plan = get_pruned_plan(wf, kap, fftg);
+  if (plan->ok && !getenv("PAWB200_DENSITY_GENERIC")) {
+    // hand-written pruned transform (one interleave group; the other 15 slots are zero columns), Bloch phase and
+    // augmentation on the interleaved box, then the state's slot(s) are copied out in the caller's layout
+    realspace_boxes_il(wf, kap, *plan, band * h, h, fftg, T);
+    DevBuf planar((size_t)h * ngrid * sizeof(double2));
+    const long blocks = std::min<long>((ngrid * h + 255) / 256, (long)g_num_sms * 16);
+    extract_il_kernel<<<(unsigned)blocks, 256, 0, g_stream>>>(g_grid.as<double2>(), ngrid, 0, h, planar.as<double2>());
+    count_launch();
+    check_launch();
+    d2h_pipelined(out, planar.p, (size_t)h * ngrid * sizeof(double2), false);
+    return;
+  }
+  DevBuf inv = build_inverse_map(wf, kap, fftg);
+  realspace_boxes(wf, kap, band * h, h, fftg, T, inv);
   d2h_pipelined(out, g_grid.p, (size_t)h * ngrid * sizeof(double2), false);
 }
 
@@ -2430,6 +2445,65 @@ void compute_aug_freqs(pawb200_pswf* wf, const int* site_list, int nlist, const 
     wf->CA[kap].zero((size_t)wf->nband * wf->ldc[kap] * sizeof(float2));
     double kc[3] = {wf->kp[kap].k[0], wf->kp[kap].k[1], wf->kp[kap].k[2]};
     frac_to_cart(kc, wf->reclattice);                                           // projector.c:288-292
+    std::shared_ptr<PrunedPlan> plan = get_pruned_plan(wf, kap, fftg);
+    const bool pruned = plan->ok && plan->g.col_run && !getenv("PAWB200_DENSITY_GENERIC");
+    // one site per launch, no atomics: sums over overlapping spheres are formed in site order (deterministic)
+    auto add_sites = [&](double2* x, int b_first, int nbx, int interleaved) {
+      for (int c0 = 0; c0 < nbx && T->total_pts; c0 += NBMAX) {
+        const int nc = std::min(NBMAX, nbx - c0);
+        for (int s = 0; s < nlist; s++) {
+          const int npts = T->host[s].npts;
+          if (!npts) continue;
+          aug_freq_add_site_kernel<<<(npts + 255) / 256, 256, sizeof(double2) * nc * maxlm, g_stream>>>(
+              T->sites.as<SiteDev>(), s, full_off[s], T->idx.as<int>(), T->path.as<double>(), T->total_pts,
+              T->table.as<double2>(), wf->P[kap].as<double2>() + (long)(b_first + c0) * wf->ldp, wf->ldp, nc,
+              interleaved ? x + (long)(c0 / FFT_B) * ngrid * FFT_B : x + (long)c0 * ngrid, ngrid, kc[0], kc[1], kc[2],
+              interleaved);
+          count_launch();
+        }
+        check_launch();
+      }
+    };
+    if (pruned) {
+      // hand-written forward transform, pruned on the output side (fft_fwd_pass_*): augmentation built straight in
+      // the interleaved box layout, coefficients come back interleaved and are transposed into band rows
+      const FftGeom& g = plan->g;
+      const size_t grp_box = (size_t)FFT_B * ngrid * sizeof(double2);
+      const int gmax = (int)std::max<size_t>(1, std::min<size_t>(8, fft_budget_bytes() / grp_box));
+      const size_t t1_grp = (size_t)g.ncol * g.n3 * FFT_B * sizeof(double2);
+      const size_t t2_grp = (size_t)g.nplane * g.n2 * g.n3 * FFT_B * sizeof(double2);
+      const long ldil = ((long)npw + 1) / 2 * 2;
+      DevBuf cil((size_t)gmax * ldil * FFT_B * sizeof(float2));
+      const int ngroups = (wf->nband + FFT_B - 1) / FFT_B;
+      for (int g0 = 0; g0 < ngroups; g0 += gmax) {
+        const int ng = std::min(gmax, ngroups - g0);
+        const int b0 = g0 * FFT_B, nb = std::min(wf->nband - b0, ng * FFT_B);
+        g_grid.ensure((size_t)ng * grp_box);
+        g_fft_t1.ensure(t1_grp * ng);
+        g_fft_t2.ensure(t2_grp * ng);
+        double2* x = g_grid.as<double2>();
+        {
+          ScopedStage tm(ST_AUGMENT);
+          CUDA_OK(cudaMemsetAsync(x, 0, (size_t)ng * grp_box, g_stream));
+          add_sites(x, b0, nb, 1);
+        }
+        FftWork w;
+        w.T1 = g_fft_t1.as<double2>();
+        w.T2 = g_fft_t2.as<double2>();
+        {
+          ScopedStage tm(ST_FFT);
+          g_boxes_fft += nb;
+          count_launch(launch_pruned_forward(g, ng, x, w, cil.as<float2>(), ldil, scale, g_num_sms, g_stream));
+        }
+        ScopedStage tm(ST_SCATTER);
+        dim3 grid((npw + 127) / 128, ng);
+        deinterleave_coeff_kernel<<<grid, 256, 0, g_stream>>>(cil.as<float2>(), ldil, npw, b0, nb,
+                                                             wf->CA[kap].as<float2>(), wf->ldc[kap]);
+        count_launch();
+        check_launch();
+      }
+      continue;
+    }
     for (int b0 = 0; b0 < wf->nband; b0 += batch) {
       const int nb = std::min(batch, wf->nband - b0);
       g_grid.ensure((size_t)nb * ngrid * sizeof(double2));
@@ -2437,16 +2511,7 @@ void compute_aug_freqs(pawb200_pswf* wf, const int* site_list, int nlist, const 
       {
         ScopedStage tm(ST_AUGMENT);
         CUDA_OK(cudaMemsetAsync(x, 0, (size_t)nb * ngrid * sizeof(double2), g_stream));
-        for (int c0 = 0; c0 < nb && T->total_pts; c0 += NBMAX) {
-          const int nc = std::min(NBMAX, nb - c0);
-          dim3 grid(std::max(1, (maxpts + 255) / 256), nlist);
-          aug_freq_add_kernel<<<grid, 256, sizeof(double2) * nc * maxlm, g_stream>>>(
-              T->sites.as<SiteDev>(), doff.as<int>(), T->idx.as<int>(), T->path.as<double>(), T->total_pts,
-              T->table.as<double2>(), wf->P[kap].as<double2>() + (long)(b0 + c0) * wf->ldp, wf->ldp, nc,
-              x + (long)c0 * ngrid, ngrid, kc[0], kc[1], kc[2]);
-          count_launch();
-          check_launch();
-        }
+        add_sites(x, b0, nb, 0);
       }
       launch_fft(x, fftg, nb, CUFFT_FORWARD);
       ScopedStage tm(ST_SCATTER);

@@ -12,6 +12,7 @@
 // (batch fastest -> conflict-free), with a two-factor Cooley-Tukey n = R1*R2 (R <= 20, radices 2,3,5,7 and
 // their products <= 20 evaluated in registers; n <= 400).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -391,6 +392,19 @@ __device__ __forceinline__ void wait_count(const unsigned* p, unsigned target) {
   while (ld_acquire_u32(p) < target) __nanosleep(64);
 }
 
+// decoded work item (thread 0 decodes the ticket once - the integer divisions would otherwise be repeated by every
+// thread - and publishes it through shared memory together with the ticket prefetch)
+struct YxItem {
+  int kind;                 // 0: past the end, 1: no-op (void / padded), 2: Y line, 3: X line; bit 2 set: counts on completion
+  int c;                    // chunk
+  int row;                  // X: y;  Y: plane
+  int zz, z, grp, slot;
+  int dep;                  // index of the counter this item waits on (into ydone/xdone), -1: none
+  unsigned target;          // value the counter must reach
+  int done;                 // index of the counter it increments on completion, -1: none
+  int pad[2];
+};
+
 template <int RMAX>
 __global__ void __launch_bounds__(FftLaunch<RMAX>::THREADS, FftLaunch<RMAX>::MINB)
 fft_pass_yx_kernel(FftGeom g, YxArgs a, const double2* __restrict__ T1, double2* T2c, double2* __restrict__ X) {
@@ -400,8 +414,8 @@ fft_pass_yx_kernel(FftGeom g, YxArgs a, const double2* __restrict__ T1, double2*
   double2* twy = bufs + 2 * nmax * FFT_B;                    // [n2]
   double2* twx = twy + g.n2;                                 // [n1]
   int4* srun = reinterpret_cast<int4*>(twx + g.n1);          // [nplane] y-run of every active x-plane
-  int* sxsrc = reinterpret_cast<int*>(srun + g.nplane);      // [n1] plane holding each x row (or -1)
-  unsigned* sticket = reinterpret_cast<unsigned*>(sxsrc + g.n1);   // [2]
+  YxItem* sitem = reinterpret_cast<YxItem*>(srun + g.nplane);   // [2]
+  int* sxsrc = reinterpret_cast<int*>(sitem + 2);            // [n1] plane holding each x row (or -1)
   const int tid = threadIdx.x, q = tid / FFT_B, b = tid % FFT_B, lane = tid & 31;
   const unsigned nwarps = (blockDim.x + 31) >> 5;             // the last warp may be half full (16-thread q slots)
   for (int i = tid; i < g.n2; i += blockDim.x) twy[i] = g.tw[1][i];
@@ -410,69 +424,65 @@ fft_pass_yx_kernel(FftGeom g, YxArgs a, const double2* __restrict__ T1, double2*
     sxsrc[i] = g.xsrc[i];
   }
   for (int i = tid; i < g.nplane; i += blockDim.x) srun[i] = g.plane_run[i];
-  if (tid == 0) sticket[0] = atomicAdd(a.ticket, 1u);
-  __syncthreads();
   const unsigned items_x = (unsigned)g.n2 * a.zch, items_y = (unsigned)g.nplane * a.zch;
   const unsigned per_step = items_x + items_y;
   const unsigned total = (unsigned)(a.nchunks + a.lead) * per_step;
+  unsigned* counters = a.ydone;                               // ydone[nchunks] followed by xdone[nchunks]
+  auto fetch = [&](YxItem* it) {                              // thread 0 only
+    const unsigned t = atomicAdd(a.ticket, 1u);
+    YxItem d;
+    d.kind = 0; d.c = 0; d.row = 0; d.zz = 0; d.z = 0; d.grp = 0; d.slot = 0; d.dep = -1; d.target = 0; d.done = -1;
+    if (t < total) {
+      const int step = (int)(t / per_step);
+      unsigned r = t - (unsigned)step * per_step;
+      const bool isx = r < items_x;
+      const int c = isx ? step - a.lead : step;
+      const bool valid = isx ? (c >= 0) : (c < a.nchunks);
+      if (!isx) r -= items_x;
+      d.kind = 1;
+      if (valid) {
+        d.c = c;
+        d.row = (int)(r / a.zch);
+        d.zz = (int)(r - (unsigned)d.row * a.zch);
+        d.grp = c / a.nzc;
+        d.z = (c - d.grp * a.nzc) * a.zch + d.zz;
+        d.slot = c % a.ring;
+        d.done = isx ? a.nchunks + c : c;
+        if (d.z < g.n3) {
+          d.kind = isx ? 3 : 2;
+          if (isx) { d.dep = c; d.target = items_y * nwarps; }
+          else if (c >= a.ring) { d.dep = a.nchunks + c - a.ring; d.target = items_x * nwarps; }
+        }
+      }
+    }
+    *it = d;
+  };
+  if (tid == 0) fetch(sitem);
+  __syncthreads();
   const long plane = (long)g.n2 * g.n3;
   const long slot_elems = (long)g.nplane * g.n2 * a.zch * FFT_B;
-  unsigned cur = sticket[0];
-  // what item `t` must wait for: (counter, target), counter == nullptr when nothing
-  auto dependency = [&](unsigned t, const unsigned*& ctr, unsigned& target) {
-    ctr = nullptr;
-    target = 0;
-    if (t >= total) return;
-    const int step = (int)(t / per_step);
-    const unsigned r = t % per_step;
-    if (r < items_x) {
-      const int c = step - a.lead;
-      if (c >= 0) { ctr = a.ydone + c; target = items_y * nwarps; }
-    } else {
-      const int c = step;
-      if (c < a.nchunks && c >= a.ring) { ctr = a.xdone + (c - a.ring); target = items_x * nwarps; }
-    }
-  };
-  // lane 0 of every warp: value of the dependency counter of the CURRENT item, sampled during the previous item
-  unsigned seen = 0;
-  {
-    const unsigned* ctr; unsigned target;
-    dependency(cur, ctr, target);
-    if (lane == 0 && ctr) seen = ld_acquire_u32(ctr);
-  }
-  unsigned* pending = nullptr;      // completion of the previous item, not yet published (lane 0)
+  YxItem cur = sitem[0];
+  // lane 0 of every warp: value of the current item's dependency counter, sampled during the previous item
+  unsigned seen = (lane == 0 && cur.dep >= 0) ? ld_acquire_u32(counters + cur.dep) : 0u;
+  int pending = -1;                 // completion of the previous item, not yet published
   auto publish = [&]() {
-    if (lane == 0 && pending) red_release_add(pending, 1u);
-    pending = nullptr;
+    if (lane == 0 && pending >= 0) red_release_add(counters + pending, 1u);
+    pending = -1;
   };
-  for (int it = 0; cur < total; it++) {
-    if (tid == 0) sticket[(it + 1) & 1] = atomicAdd(a.ticket, 1u);     // next item, off the critical path
-    const int step = (int)(cur / per_step);
-    unsigned r = cur % per_step;
-    const bool isx = r < items_x;
-    const int c = isx ? step - a.lead : step;
-    const bool valid = isx ? (c >= 0) : (c < a.nchunks);
-    if (!isx) r -= items_x;
-    const int row = (int)(r / a.zch), zz = (int)(r % a.zch);           // X: row = y;  Y: row = plane
-    int grp = 0, z = 0;
-    if (valid) {
-      grp = c / a.nzc;
-      z = (c % a.nzc) * a.zch + zz;
-    }
-    const bool work = valid && z < g.n3;
+  for (int it = 0; cur.kind != 0; it++) {
+    if (tid == 0) fetch(sitem + ((it + 1) & 1));               // next item, off the critical path
+    const bool isx = cur.kind == 3, work = cur.kind >= 2;
     double2* buf = bufs + (it & 1) * nmax * FFT_B;
-    double2* ring = T2c + (long)(valid ? c % a.ring : 0) * slot_elems;
+    double2* ring = T2c + (long)cur.slot * slot_elems;
     if (work) {
-      const unsigned* ctr; unsigned target;
-      dependency(cur, ctr, target);
-      if (lane == 0 && ctr && seen < target) {
+      if (lane == 0 && cur.dep >= 0 && seen < cur.target) {
         publish();                 // never wait while holding an unpublished completion
-        wait_count(ctr, target);
+        wait_count(counters + cur.dep, cur.target);
       }
       __syncwarp();
       if (isx) {
         if (q < g.r2[0]) {
-          const double2* in = ring + ((long)row * a.zch + zz) * FFT_B + b;
+          const double2* in = ring + ((long)cur.row * a.zch + cur.zz) * FFT_B + b;
           const long pstride = (long)g.n2 * a.zch * FFT_B;
           auto load = [&](int x) {
             const int p = sxsrc[x];
@@ -485,8 +495,8 @@ fft_pass_yx_kernel(FftGeom g, YxArgs a, const double2* __restrict__ T1, double2*
         }
       } else {
         if (q < g.r2[1]) {
-          const int4 run = srun[row];
-          const double2* in = T1 + ((long)grp * g.ncol * g.n3 + z) * FFT_B + b;
+          const int4 run = srun[cur.row];
+          const double2* in = T1 + ((long)cur.grp * g.ncol * g.n3 + cur.z) * FFT_B + b;
           const long cstride = (long)g.n3 * FFT_B;
           const int n2 = g.n2;
           auto load = [&](int y) {
@@ -504,19 +514,15 @@ fft_pass_yx_kernel(FftGeom g, YxArgs a, const double2* __restrict__ T1, double2*
       }
     }
     __syncthreads();
-    const unsigned nxt = sticket[(it + 1) & 1];
+    const YxItem nxt = sitem[(it + 1) & 1];
     // The previous item's stores were issued a whole phase ago: publishing them now costs a short fence.  The
     // next item's dependency counter is sampled here too, so that its value is in a register when the item starts.
     publish();
-    {
-      const unsigned* ctr; unsigned target;
-      dependency(nxt, ctr, target);
-      seen = (lane == 0 && ctr) ? ld_acquire_u32(ctr) : 0u;
-    }
+    seen = (lane == 0 && nxt.dep >= 0) ? ld_acquire_u32(counters + nxt.dep) : 0u;
     if (work) {
       if (isx) {
         if (q < g.r1[0]) {
-          double2* out = X + ((long)grp * g.n1 * plane + (long)row * g.n3 + z) * FFT_B + b;
+          double2* out = X + ((long)cur.grp * g.n1 * plane + (long)cur.row * g.n3 + cur.z) * FFT_B + b;
           auto store = [&](int x, double2 v) { out[(long)x * plane * FFT_B] = v; };
           const int R1 = g.r1[0];
 #define P2(R) line_phase2<R>(buf, R1, q, b, store)
@@ -525,7 +531,7 @@ fft_pass_yx_kernel(FftGeom g, YxArgs a, const double2* __restrict__ T1, double2*
         }
       } else {
         if (q < g.r1[1]) {
-          double2* out = ring + ((long)row * g.n2 * a.zch + zz) * FFT_B + b;
+          double2* out = ring + ((long)cur.row * g.n2 * a.zch + cur.zz) * FFT_B + b;
           const long ystride = (long)a.zch * FFT_B;
           auto store = [&](int y, double2 v) { __stcg(out + (long)y * ystride, v); };
           const int R1 = g.r1[1];
@@ -535,13 +541,330 @@ fft_pass_yx_kernel(FftGeom g, YxArgs a, const double2* __restrict__ T1, double2*
         }
       }
     }
-    if (valid) {        // padded z (z >= n3) items only count
+    if (cur.done >= 0) {        // padded z (z >= n3) items only count
       __syncwarp();
-      pending = isx ? a.xdone + c : a.ydone + c;
+      pending = cur.done;
     }
     cur = nxt;
   }
   publish();
+}
+
+// ---- TMA-fed passes Y and X -----------------------------------------------------------------------------------
+// The register-direct passes above keep only as many bytes in flight as their ~20 resident warps per SM have loads
+// outstanding (ncu: long_scoreboard-bound at 47-60 % of DRAM peak).  Here the inputs of a whole work unit - ZL
+// lines - are fetched by the TMA engine (cp.async.bulk.tensor, one elected thread, completion on an mbarrier) into a
+// ring of shared-memory stages, several units ahead of the arithmetic, so the bytes in flight no longer depend on
+// how many warps are waiting:
+//   pass X unit = ZL consecutive (y,z) lines of a group: ONE 3-D box {256 B, ZL, nplane} of T2[grp][plane][yz][16];
+//   pass Y unit = (group, plane, ZL consecutive z): boxes {256 B, ZL, 16 columns} of T1[grp][col][z][16] covering the
+//                 plane's column run (the tail box over-fetches the next plane's first columns; they are ignored).
+// A stage is laid out like the box, [row][ZL][16] (row = plane / column).  The compute side is the unchanged
+// two-phase line transform (thread = (radix slot, band)); phase 1 reads the stage instead of global memory, phase 2
+// stores straight to global.  Stage reuse needs no second barrier array: a stage is refilled only after the
+// __syncthreads that ends the phase-1 reads of its last line.
+struct TmaPassArgs {
+  int zl;                   // lines per unit
+  int stages;               // ring depth
+  int stage_rows;           // rows (planes / padded columns) a stage holds
+  int dbl;                  // exchange buffer double-buffered (one barrier per line) or single (two)
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(void* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(void* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const void* tmap, int c0, int c1, int c2, void* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(smem_u32(dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
+}
+
+constexpr int FFT_TMA_COLBOX = 16;     // columns per box of pass Y
+
+// PASS: 0 = X (T2 -> X), 1 = Y (T1 -> T2)
+template <int RMAX, int PASS>
+__global__ void __launch_bounds__(FftLaunch<RMAX>::THREADS, FftLaunch<RMAX>::MINB)
+fft_pass_tma_kernel(const __grid_constant__ CUtensorMap tmap, FftGeom g, TmaPassArgs a, double2* __restrict__ out_base,
+                    int ngroups) {
+  extern __shared__ __align__(128) unsigned char fft_smem[];
+  const int n = PASS == 0 ? g.n1 : g.n2;
+  const int R1 = g.r1[PASS == 0 ? 0 : 1], R2 = g.r2[PASS == 0 ? 0 : 1];
+  const int zl = a.zl, S = a.stages;
+  const int stage_elems = a.stage_rows * zl * FFT_B;                     // double2 per stage
+  double2* stage0 = reinterpret_cast<double2*>(fft_smem);                // [S][stage_rows][zl][16]
+  double2* bufs = stage0 + (long)S * stage_elems;                        // [1 or 2][n][16] exchange
+  double2* tw = bufs + (a.dbl ? 2 : 1) * n * FFT_B;                      // [n]
+  int4* srun = reinterpret_cast<int4*>(tw + n);                          // Y: [nplane] runs
+  int* ssrc = reinterpret_cast<int*>(srun + (PASS == 1 ? g.nplane : 0));  // X: [n1] plane of each x row
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(
+      (reinterpret_cast<uintptr_t>(ssrc + (PASS == 0 ? g.n1 : 0)) + 7) & ~(uintptr_t)7);   // [S] mbarriers
+  const int tid = threadIdx.x, q = tid / FFT_B, b = tid % FFT_B;
+  for (int i = tid; i < n; i += blockDim.x) tw[i] = g.tw[PASS == 0 ? 0 : 1][i];
+  if (PASS == 0) {
+    for (int i = tid; i < g.n1; i += blockDim.x) ssrc[i] = g.xsrc[i];
+  } else {
+    for (int i = tid; i < g.nplane; i += blockDim.x) srun[i] = g.plane_run[i];
+  }
+  if (tid == 0) {
+    for (int s = 0; s < S; s++) mbar_init(full + s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // work units
+  const long plane = (long)g.n2 * g.n3;
+  const long upg = PASS == 0 ? (plane + zl - 1) / zl : (long)g.nplane * ((g.n3 + zl - 1) / zl);   // units per group
+  const long nunits = (long)ngroups * upg;
+  const int nzc = (g.n3 + zl - 1) / zl;
+
+  auto issue = [&](long unit, int s) {          // elected thread: fetch the inputs of `unit` into stage s
+    const int grp = (int)(unit / upg);
+    const long u = unit % upg;
+    double2* dst = stage0 + (long)s * stage_elems;
+    if (PASS == 0) {
+      const long yz0 = u * zl;
+      const int nbox = (g.nplane + 255) / 256;
+      mbar_expect_tx(full + s, (unsigned)(stage_elems * sizeof(double2)));
+      for (int j = 0; j < nbox; j++)
+        tma_load_3d(dst + (long)j * 256 * zl * FFT_B, &tmap, 0, (int)yz0, grp * g.nplane + j * 256, full + s);
+    } else {
+      const int p = (int)(u / nzc), z0 = (int)(u % nzc) * zl;
+      const int4 run = srun[p];
+      const int nbox = (run.y + FFT_TMA_COLBOX - 1) / FFT_TMA_COLBOX;
+      mbar_expect_tx(full + s, (unsigned)(nbox * FFT_TMA_COLBOX * zl * FFT_B * sizeof(double2)));
+      for (int j = 0; j < nbox; j++)
+        tma_load_3d(dst + (long)j * FFT_TMA_COLBOX * zl * FFT_B, &tmap, 0, z0,
+                    grp * g.ncol + run.x + j * FFT_TMA_COLBOX, full + s);
+    }
+  };
+
+  long nmine = 0;
+  if ((long)blockIdx.x < nunits) nmine = (nunits - blockIdx.x + gridDim.x - 1) / gridDim.x;
+  if (tid == 0)
+    for (int s = 0; s < S - 1 && s < nmine; s++) issue(blockIdx.x + (long)s * gridDim.x, s);
+  int lineno = 0;
+  for (long i = 0; i < nmine; i++) {
+    const int s = (int)(i % S);
+    const unsigned parity = (unsigned)((i / S) & 1);
+    // the stage of unit i-1 was consumed before the barrier that ended its last phase 1: refill it
+    if (tid == 0 && i + S - 1 < nmine) issue(blockIdx.x + (i + S - 1) * gridDim.x, (int)((i + S - 1) % S));
+    mbar_wait(full + s, parity);
+    const long unit = blockIdx.x + i * gridDim.x;
+    const int grp = (int)(unit / upg);
+    const long u = unit % upg;
+    const double2* st = stage0 + (long)s * stage_elems;
+    for (int l = 0; l < zl; l++, lineno++) {
+      double2* buf = bufs + (a.dbl ? (lineno & 1) : 0) * n * FFT_B;
+      bool live;
+      long yz = 0;
+      int p = 0, z = 0;
+      if (PASS == 0) {
+        yz = u * zl + l;
+        live = yz < plane;
+      } else {
+        p = (int)(u / nzc);
+        z = (int)(u % nzc) * zl + l;
+        live = z < g.n3;
+      }
+      if (live && q < R2) {
+        const double2* in = st + (long)l * FFT_B + b;
+        const long rstride = (long)zl * FFT_B;
+        if (PASS == 0) {
+          auto load = [&](int x) {
+            const int pl = ssrc[x];
+            return pl >= 0 ? in[(long)pl * rstride] : make_double2(0, 0);
+          };
+#define P1(R) line_phase1<R>(buf, tw, R2, q, b, load)
+          PAWB200_RADIX_SWITCH(R1, P1)
+#undef P1
+        } else {
+          const int4 run = srun[p];
+          const int n2 = g.n2;
+          auto load = [&](int y) {
+            int d = y - run.z;
+            if (d < 0) d += n2;
+            if (d >= run.y) return make_double2(0, 0);
+            const int j = d < run.w ? run.y - run.w + d : d - run.w;
+            return in[(long)j * rstride];
+          };
+#define P1(R) line_phase1<R>(buf, tw, R2, q, b, load)
+          PAWB200_RADIX_SWITCH(R1, P1)
+#undef P1
+        }
+      }
+      __syncthreads();
+      if (live && q < R1) {
+        if (PASS == 0) {
+          double2* out = out_base + ((long)grp * g.n1 * plane + yz) * FFT_B + b;
+          auto store = [&](int x, double2 v) { out[(long)x * plane * FFT_B] = v; };
+#define P2(R) line_phase2<R>(buf, R1, q, b, store)
+          PAWB200_RADIX_SWITCH(R2, P2)
+#undef P2
+        } else {
+          double2* out = out_base + ((((long)grp * g.nplane + p) * g.n2) * g.n3 + z) * FFT_B + b;
+          const long ystride = (long)g.n3 * FFT_B;
+          auto store = [&](int y, double2 v) { out[(long)y * ystride] = v; };
+#define P2(R) line_phase2<R>(buf, R1, q, b, store)
+          PAWB200_RADIX_SWITCH(R2, P2)
+#undef P2
+        }
+      }
+      if (!a.dbl) __syncthreads();
+    }
+  }
+}
+
+// ---- forward transform, pruned on the OUTPUT side: X -> T2 -> T1 -> interleaved plane-wave coefficients ------------
+// fwd_fft3d + gather (linalg.c:47-79) for whole band groups: F[G] = scale * sum_r x[r] e^{-2 pi i G.r/N} is evaluated
+// as conj(inverse transform of conj(x)), so the line transforms above are reused unchanged; the data stays conjugated
+// between the passes and is conjugated back (and narrowed to complex64, like the reference's store) by pass Z.
+// Pruning mirrors the inverse transform: pass X keeps only the x-planes that hold plane waves, pass Y only the
+// active columns, pass Z only each column's z-run.
+template <int RMAX>
+__global__ void __launch_bounds__(FftLaunch<RMAX>::THREADS, FftLaunch<RMAX>::MINB)
+fft_fwd_pass_x_kernel(FftGeom g, const double2* __restrict__ X, double2* __restrict__ T2, int ngroups) {
+  extern __shared__ __align__(16) unsigned char fft_smem[];
+  double2* bufs = reinterpret_cast<double2*>(fft_smem);      // [2][n1][FFT_B]
+  double2* tw = bufs + 2 * g.n1 * FFT_B;
+  int* sxsrc = reinterpret_cast<int*>(tw + g.n1);
+  const int tid = threadIdx.x, q = tid / FFT_B, b = tid % FFT_B;
+  const int R1 = g.r1[0], R2 = g.r2[0];
+  for (int i = tid; i < g.n1; i += blockDim.x) {
+    tw[i] = g.tw[0][i];
+    sxsrc[i] = g.xsrc[i];
+  }
+  __syncthreads();
+  const long plane = (long)g.n2 * g.n3;
+  const long nlines = (long)ngroups * plane;
+  int it = 0;
+  for (long line = blockIdx.x; line < nlines; line += gridDim.x, it++) {
+    const long yz = line % plane;
+    const int grp = (int)(line / plane);
+    double2* buf = bufs + (it & 1) * g.n1 * FFT_B;
+    if (q < R2) {
+      const double2* in = X + ((long)grp * g.n1 * plane + yz) * FFT_B + b;
+      auto load = [&](int row) {
+        const double2 v = in[(long)row * plane * FFT_B];
+        return make_double2(v.x, -v.y);
+      };
+#define P1(R) line_phase1<R>(buf, tw, R2, q, b, load)
+      PAWB200_RADIX_SWITCH(R1, P1)
+#undef P1
+    }
+    __syncthreads();
+    if (q < R1) {
+      double2* out = T2 + ((long)grp * g.nplane * plane + yz) * FFT_B + b;
+      auto store = [&](int row, double2 v) {
+        const int p = sxsrc[row];
+        if (p >= 0) out[(long)p * plane * FFT_B] = v;
+      };
+#define P2(R) line_phase2<R>(buf, R1, q, b, store)
+      PAWB200_RADIX_SWITCH(R2, P2)
+#undef P2
+    }
+  }
+}
+
+template <int RMAX>
+__global__ void __launch_bounds__(FftLaunch<RMAX>::THREADS, FftLaunch<RMAX>::MINB)
+fft_fwd_pass_y_kernel(FftGeom g, const double2* __restrict__ T2, double2* __restrict__ T1, int ngroups) {
+  extern __shared__ __align__(16) unsigned char fft_smem[];
+  double2* bufs = reinterpret_cast<double2*>(fft_smem);      // [2][n2][FFT_B]
+  double2* tw = bufs + 2 * g.n2 * FFT_B;
+  int* ssrc = reinterpret_cast<int*>(tw + g.n2);             // [n2] column of each y row of the current plane
+  const int tid = threadIdx.x, q = tid / FFT_B, b = tid % FFT_B;
+  const int R1 = g.r1[1], R2 = g.r2[1];
+  for (int i = tid; i < g.n2; i += blockDim.x) tw[i] = g.tw[1][i];
+  const int nzc = (g.n3 + FFT_ZC - 1) / FFT_ZC;
+  const long nunits = (long)ngroups * g.nplane * nzc;
+  int it = 0;
+  for (long unit = blockIdx.x; unit < nunits; unit += gridDim.x) {
+    const int zc = (int)(unit % nzc);
+    const int p = (int)((unit / nzc) % g.nplane);
+    const int grp = (int)(unit / ((long)nzc * g.nplane));
+    __syncthreads();
+    for (int i = tid; i < g.n2; i += blockDim.x) ssrc[i] = g.ysrc[p * g.n2 + i];
+    __syncthreads();
+    const int z1 = min(g.n3, (zc + 1) * FFT_ZC);
+    for (int z = zc * FFT_ZC; z < z1; z++, it++) {
+      double2* buf = bufs + (it & 1) * g.n2 * FFT_B;
+      if (q < R2) {
+        const double2* in = T2 + ((((long)grp * g.nplane + p) * g.n2) * g.n3 + z) * FFT_B + b;
+        auto load = [&](int row) { return in[(long)row * g.n3 * FFT_B]; };
+#define P1(R) line_phase1<R>(buf, tw, R2, q, b, load)
+        PAWB200_RADIX_SWITCH(R1, P1)
+#undef P1
+      }
+      __syncthreads();
+      if (q < R1) {
+        double2* out = T1 + ((long)grp * g.ncol * g.n3 + z) * FFT_B + b;
+        auto store = [&](int row, double2 v) {
+          const int c = ssrc[row];
+          if (c >= 0) out[(long)c * g.n3 * FFT_B] = v;
+        };
+#define P2(R) line_phase2<R>(buf, R1, q, b, store)
+        PAWB200_RADIX_SWITCH(R2, P2)
+#undef P2
+      }
+    }
+  }
+}
+
+// pass Z: T1 -> Cil-layout coefficients out[group][ldil][FFT_B] (complex64, box order), scaled and conjugated back
+template <int RMAX>
+__global__ void __launch_bounds__(FftLaunch<RMAX>::THREADS, FftLaunch<RMAX>::MINB)
+fft_fwd_pass_z_kernel(FftGeom g, const double2* __restrict__ T1, float2* __restrict__ out_il, long ldil, double scale,
+                      int ngroups) {
+  extern __shared__ __align__(16) unsigned char fft_smem[];
+  double2* bufs = reinterpret_cast<double2*>(fft_smem);      // [2][n3][FFT_B]
+  double2* tw = bufs + 2 * g.n3 * FFT_B;
+  const int tid = threadIdx.x, q = tid / FFT_B, b = tid % FFT_B;
+  const int R1 = g.r1[2], R2 = g.r2[2], n3 = g.n3;
+  for (int i = tid; i < n3; i += blockDim.x) tw[i] = g.tw[2][i];
+  __syncthreads();
+  const long nlines = (long)ngroups * g.ncol;
+  int it = 0;
+  for (long line = blockIdx.x; line < nlines; line += gridDim.x, it++) {
+    const int grp = (int)(line / g.ncol), col = (int)(line % g.ncol);
+    const int4 run = __ldg(g.col_run + col);
+    double2* buf = bufs + (it & 1) * n3 * FFT_B;
+    if (q < R2) {
+      const double2* in = T1 + (((long)grp * g.ncol + col) * n3) * FFT_B + b;
+      auto load = [&](int row) { return in[(long)row * FFT_B]; };
+#define P1(R) line_phase1<R>(buf, tw, R2, q, b, load)
+      PAWB200_RADIX_SWITCH(R1, P1)
+#undef P1
+    }
+    __syncthreads();
+    if (q < R1) {
+      float2* out = out_il + ((long)grp * ldil + run.x) * FFT_B + b;
+      auto store = [&](int row, double2 v) {
+        int d = row - run.z;
+        if (d < 0) d += n3;
+        if (d >= run.y) return;
+        const int j = d < run.w ? run.y - run.w + d : d - run.w;
+        out[(long)j * FFT_B] = make_float2((float)(v.x * scale), (float)(-v.y * scale));
+      };
+#define P2(R) line_phase2<R>(buf, R1, q, b, store)
+      PAWB200_RADIX_SWITCH(R2, P2)
+#undef P2
+    }
+  }
 }
 
 }  // namespace pawb200

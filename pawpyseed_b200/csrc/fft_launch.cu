@@ -96,7 +96,7 @@ inline int yx_threads(const FftGeom& g) {
 inline size_t yx_smem(const FftGeom& g) {
   const int nmax = std::max(g.n1, g.n2);
   return (size_t)(2 * nmax * FFT_B + g.n1 + g.n2) * sizeof(double2) + (size_t)g.nplane * sizeof(int4) +
-         (size_t)g.n1 * sizeof(int) + 2 * sizeof(unsigned) + 16;
+         (size_t)g.n1 * sizeof(int) + 2 * sizeof(YxItem) + 16;
 }
 
 template <int RMAX>
@@ -115,6 +115,107 @@ void launch_pass_yx(const FftGeom& g, const YxConfig& yx, int ng, const double2*
   a.xdone = flags + 8 + a.nchunks;
   FFT_CUDA_OK(cudaMemsetAsync(flags, 0, yx.flag_words(ng) * sizeof(unsigned), st));
   fft_pass_yx_kernel<RMAX><<<yx.grid, yx_threads(g), yx_smem(g), st>>>(g, a, T1, ring, X);
+}
+
+// ---- TMA-fed passes (fft_pass_tma_kernel) ------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn tensor_map_encoder() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+    else
+      cudaGetLastError();
+  }
+  return fn;
+}
+
+// rows x inner rank-3 view of an interleaved scratch array: [outer][mid][16 bands] of complex128, i.e.
+// dims (fastest first) {32 doubles, mid, outer}, box {32, zl, box_rows}
+bool make_tensor_map(CUtensorMap* m, const void* base, long mid, long outer, int zl, int box_rows) {
+  EncodeTiledFn enc = tensor_map_encoder();
+  if (!enc) return false;
+  const cuuint64_t dims[3] = {32, (cuuint64_t)mid, (cuuint64_t)outer};
+  const cuuint64_t strides[2] = {256, (cuuint64_t)mid * 256};
+  const cuuint32_t box[3] = {32, (cuuint32_t)zl, (cuuint32_t)box_rows};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<void*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
+struct TmaPlan {
+  bool ok = false;
+  TmaPassArgs a;
+  int box_rows = 0, threads = 0;
+  size_t smem = 0;
+};
+
+// Stage / exchange-buffer configuration of a TMA-fed pass (pass 0 = X, 1 = Y): the deepest ring that still leaves
+// two CTAs per SM; PAWB200_TMA_ZL / _STAGES / _DBL override (tuning).
+TmaPlan plan_tma_pass(const FftGeom& g, int pass, int max_plane_cols) {
+  TmaPlan p;
+  // Opt-in (PAWB200_FFT_TMA=1).  Measured on config 2 (fft ms/step): register-direct passes 10.4; TMA-fed, two
+  // CTAs/SM with a 3-stage ring 12.9, ZL=2 12.0, single exchange buffer (three CTAs/SM) 10.9 - the passes are bound by
+  // resident warps (issue / FP64 latency between the two phases of a line), not by bytes in flight, so shared memory
+  // spent on stages costs more than the prefetch returns.
+  if (env_int("PAWB200_FFT_TMA", 0) == 0 || !tensor_map_encoder()) return p;
+  if (pass == 1 && !g.plane_run) return p;
+  const int n = pass == 0 ? g.n1 : g.n2;
+  const int zl = std::max(1, std::min(8, env_int("PAWB200_TMA_ZL", 1)));
+  int rows;
+  if (pass == 0) {
+    p.box_rows = std::min(g.nplane, 256);
+    rows = (g.nplane + p.box_rows - 1) / p.box_rows * p.box_rows;
+  } else {
+    p.box_rows = FFT_TMA_COLBOX;
+    rows = (max_plane_cols + FFT_TMA_COLBOX - 1) / FFT_TMA_COLBOX * FFT_TMA_COLBOX;
+  }
+  const size_t stage = (size_t)rows * zl * FFT_B * sizeof(double2);
+  auto smem_of = [&](int S, int dbl) {
+    return (size_t)S * stage + (size_t)(dbl ? 2 : 1) * n * FFT_B * sizeof(double2) + (size_t)n * sizeof(double2) +
+           (pass == 1 ? (size_t)g.nplane * sizeof(int4) : (size_t)g.n1 * sizeof(int)) + (size_t)S * 8 + 32;
+  };
+  const int prefs[][2] = {{3, 1}, {2, 1}, {3, 0}, {2, 0}};
+  int S = 2, dbl = 0;
+  bool found = false;
+  for (auto& pr : prefs)
+    if (!found && smem_of(pr[0], pr[1]) <= (size_t)kFftSmemOptIn / 2) { S = pr[0]; dbl = pr[1]; found = true; }
+  S = std::max(2, env_int("PAWB200_TMA_STAGES", S));
+  dbl = env_int("PAWB200_TMA_DBL", dbl) ? 1 : 0;
+  p.smem = smem_of(S, dbl);
+  if (p.smem > (size_t)kFftSmemOptIn) return p;
+  p.a.zl = zl; p.a.stages = S; p.a.stage_rows = rows; p.a.dbl = dbl;
+  p.threads = std::max(g.r1[pass == 0 ? 0 : 1], g.r2[pass == 0 ? 0 : 1]) * FFT_B;
+  p.ok = true;
+  return p;
+}
+
+template <int RMAX, int PASS>
+bool launch_pass_tma(const FftGeom& g, const TmaPlan& p, int ng, const double2* in, double2* out, int num_sms,
+                     cudaStream_t st) {
+  CUtensorMap tmap;
+  const long plane = (long)g.n2 * g.n3;
+  const bool ok = PASS == 0 ? make_tensor_map(&tmap, in, plane, (long)g.nplane * ng, p.a.zl, p.box_rows)
+                            : make_tensor_map(&tmap, in, g.n3, (long)g.ncol * ng, p.a.zl, p.box_rows);
+  if (!ok) return false;
+  const int occ = cached_occupancy(fft_pass_tma_kernel<RMAX, PASS>, p.threads, p.smem);
+  const long upg = PASS == 0 ? (plane + p.a.zl - 1) / p.a.zl : (long)g.nplane * ((g.n3 + p.a.zl - 1) / p.a.zl);
+  fft_pass_tma_kernel<RMAX, PASS><<<fft_grid_dim((long)ng * upg, occ, num_sms), p.threads, p.smem, st>>>(
+      tmap, g, p.a, out, ng);
+  return true;
 }
 
 }  // namespace
@@ -179,8 +280,46 @@ YxConfig plan_fused_yx(const FftGeom& g, int num_sms, size_t l2_budget_bytes) {
   return c;
 }
 
+int launch_pruned_forward(const FftGeom& g, int ng, const double2* X, const FftWork& w, float2* out_il, long ldil,
+                          double scale, int num_sms, cudaStream_t st) {
+  if (!g.col_run) throw std::runtime_error("forward pruned transform needs single-run columns");
+  const int rz = std::max(g.r1[2], g.r2[2]), ry = std::max(g.r1[1], g.r2[1]), rx = std::max(g.r1[0], g.r2[0]);
+#define FWD_X(R)                                                                                                    \
+  {                                                                                                                 \
+    const int threads = rx * FFT_B;                                                                                 \
+    const size_t smem = (size_t)(2 * g.n1 * FFT_B + g.n1) * sizeof(double2) + g.n1 * sizeof(int);                  \
+    const int occ = cached_occupancy(fft_fwd_pass_x_kernel<R>, threads, smem);                                      \
+    fft_fwd_pass_x_kernel<R><<<fft_grid_dim((long)ng * g.n2 * g.n3, occ, num_sms), threads, smem, st>>>(g, X, w.T2, ng); \
+  }
+#define FWD_Y(R)                                                                                                    \
+  {                                                                                                                 \
+    const int threads = ry * FFT_B;                                                                                 \
+    const size_t smem = (size_t)(2 * g.n2 * FFT_B + g.n2) * sizeof(double2) + g.n2 * sizeof(int);                  \
+    const int occ = cached_occupancy(fft_fwd_pass_y_kernel<R>, threads, smem);                                      \
+    fft_fwd_pass_y_kernel<R><<<fft_grid_dim((long)ng * g.nplane * ((g.n3 + FFT_ZC - 1) / FFT_ZC), occ, num_sms),    \
+                               threads, smem, st>>>(g, w.T2, w.T1, ng);                                             \
+  }
+#define FWD_Z(R)                                                                                                    \
+  {                                                                                                                 \
+    const int threads = rz * FFT_B;                                                                                 \
+    const size_t smem = (size_t)(2 * g.n3 * FFT_B + g.n3) * sizeof(double2);                                        \
+    const int occ = cached_occupancy(fft_fwd_pass_z_kernel<R>, threads, smem);                                      \
+    fft_fwd_pass_z_kernel<R><<<fft_grid_dim((long)ng * g.ncol, occ, num_sms), threads, smem, st>>>(                 \
+        g, w.T1, out_il, ldil, scale, ng);                                                                          \
+  }
+  PAWB200_AXIS_SWITCH(rx, FWD_X);
+  PAWB200_AXIS_SWITCH(ry, FWD_Y);
+  PAWB200_AXIS_SWITCH(rz, FWD_Z);
+#undef FWD_X
+#undef FWD_Y
+#undef FWD_Z
+  FFT_CUDA_OK(cudaGetLastError());
+  return 3;
+}
+
 int launch_pruned_passes(const FftGeom& g, const FftInput& in, int s0, int ns, int ng, double scale,
-                         const FftWork& w, const YxConfig* yx, double2* X, int num_sms, cudaStream_t st) {
+                         const FftWork& w, const YxConfig* yx, double2* X, int num_sms, cudaStream_t st,
+                         int max_plane_cols) {
   const int rz = std::max(g.r1[2], g.r2[2]), ry = std::max(g.r1[1], g.r2[1]), rx = std::max(g.r1[0], g.r2[0]);
 #define PASS_Z(R) launch_pass_z<R>(g, in, s0, ns, ng, scale, w.T1, num_sms, st)
   PAWB200_AXIS_SWITCH(rz, PASS_Z);
@@ -193,12 +332,20 @@ int launch_pruned_passes(const FftGeom& g, const FftInput& in, int s0, int ns, i
     FFT_CUDA_OK(cudaGetLastError());
     return 2;
   }
+  const TmaPlan ty = plan_tma_pass(g, 1, max_plane_cols), tx = plan_tma_pass(g, 0, max_plane_cols);
+  bool done_y = false, done_x = false;
+#define PASS_Y_TMA(R) done_y = launch_pass_tma<R, 1>(g, ty, ng, w.T1, w.T2, num_sms, st)
+#define PASS_X_TMA(R) done_x = launch_pass_tma<R, 0>(g, tx, ng, w.T2, X, num_sms, st)
 #define PASS_Y(R) launch_pass_y<R>(g, ng, w.T1, w.T2, num_sms, st)
 #define PASS_X(R) launch_pass_x<R>(g, ng, w.T2, X, num_sms, st)
-  PAWB200_AXIS_SWITCH(ry, PASS_Y);
-  PAWB200_AXIS_SWITCH(rx, PASS_X);
+  if (ty.ok) PAWB200_AXIS_SWITCH(ry, PASS_Y_TMA);
+  if (!done_y) PAWB200_AXIS_SWITCH(ry, PASS_Y);
+  if (tx.ok) PAWB200_AXIS_SWITCH(rx, PASS_X_TMA);
+  if (!done_x) PAWB200_AXIS_SWITCH(rx, PASS_X);
 #undef PASS_Y
 #undef PASS_X
+#undef PASS_Y_TMA
+#undef PASS_X_TMA
   FFT_CUDA_OK(cudaGetLastError());
   return 3;
 }

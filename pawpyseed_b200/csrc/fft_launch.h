@@ -59,7 +59,15 @@ void init_small_twiddles();
 // would not fit `l2_budget_bytes`, or PAWB200_FFT_FUSED=0.
 YxConfig plan_fused_yx(const FftGeom& g, int num_sms, size_t l2_budget_bytes);
 // Transforms `ng` groups (slots s0 .. s0+ns) into X[ng][n1][n2][n3][16]; returns the number of kernels launched.
+// max_plane_cols: largest number of active columns in one x-plane (stage size of the TMA-fed pass Y).
 int launch_pruned_passes(const FftGeom& g, const FftInput& in, int s0, int ns, int ng, double scale,
-                         const FftWork& w, const YxConfig* yx, double2* X, int num_sms, cudaStream_t st);
+                         const FftWork& w, const YxConfig* yx, double2* X, int num_sms, cudaStream_t st,
+                         int max_plane_cols);
+
+// Forward transform + gather of `ng` interleaved boxes X[ng][n1][n2][n3][16] (fwd_fft3d, linalg.c:47-79): the result
+// is written as complex64 coefficients in the interleaved layout out_il[ng][ldil][16] (box order), multiplied by
+// `scale`.  Uses w.T1 / w.T2 as full-size scratch ([ng][ncol][n3][16], [ng][nplane][n2][n3][16]).
+int launch_pruned_forward(const FftGeom& g, int ng, const double2* X, const FftWork& w, float2* out_il, long ldil,
+                          double scale, int num_sms, cudaStream_t st);
 
 }  // namespace pawb200

@@ -97,6 +97,27 @@ interleave_coeff_kernel(const float2* __restrict__ C, long ldc, int halves, int 
   }
 }
 
+// inverse of interleave_coeff_kernel for whole groups: rows[band0 + grp*16 + r][j] = il[grp][j][r]
+// (the forward pruned transform leaves its coefficients in the interleaved layout; the GEMM wants band rows)
+__global__ void __launch_bounds__(256)
+deinterleave_coeff_kernel(const float2* __restrict__ il, long ldil, int npw, int band0, int nband,
+                          float2* __restrict__ rows, long ldc) {
+  __shared__ float2 tile[16][129];
+  const int grp = blockIdx.y;
+  const int j0 = blockIdx.x * 128;
+  for (int e = threadIdx.x; e < 16 * 128; e += 256) {
+    const int jj = e >> 4, r = e & 15;
+    const int j = j0 + jj;
+    tile[r][jj] = j < npw ? il[((long)grp * ldil + j) * 16 + r] : make_float2(0.f, 0.f);
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < 16 * 128; e += 256) {
+    const int r = e >> 7, jj = e & 127;
+    const int band = grp * 16 + r, j = j0 + jj;
+    if (band < nband && j < npw) rows[(long)(band0 + band) * ldc + j] = tile[r][jj];
+  }
+}
+
 // (f2) k-point desymmetrisation  [utils.c:1070-1081]: Cnew[b][j] = fac[j] * Cold[b][src[j]] (conjugated under
 // time reversal), in single precision without FMA contraction so it rounds like the reference's complex float
 // multiply.
@@ -818,6 +839,41 @@ aug_freq_add_kernel(const SiteDev* __restrict__ sites, const int* __restrict__ f
   }
 }
 
+// Deterministic variants: ONE site per launch (the launches of a site list run back to back on the stream), so every
+// grid point is touched by exactly one thread of a launch and the sums over overlapping spheres are formed in site
+// order without atomics.  `planar`: boxes x[b][g];  interleaved: x[group][g][16] for the pruned forward transform.
+__global__ void __launch_bounds__(256)
+aug_freq_add_site_kernel(const SiteDev* __restrict__ sites, int site, int full_off, const int* __restrict__ idx,
+                         const double* __restrict__ path, long path_ld, const double2* __restrict__ table,
+                         const double2* __restrict__ P, long ldp, int nbox, double2* __restrict__ x, long ngrid,
+                         double kx, double ky, double kz, int interleaved) {
+  const SiteDev sd = sites[site];
+  extern __shared__ double2 sP[];    // [nbox][nlm]
+  for (int e = threadIdx.x; e < nbox * sd.nlm; e += blockDim.x)
+    sP[e] = P[(long)(e / sd.nlm) * ldp + full_off + (e % sd.nlm)];
+  __syncthreads();
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < sd.npts; p += gridDim.x * blockDim.x) {
+    const long q = sd.pt_off + p;
+    const double kr = -(kx * path[q] + ky * path[path_ld + q] + kz * path[2 * path_ld + q]);
+    double s, c;
+    sincos(kr, &s, &c);
+    const int g = idx[q];
+    for (int b = 0; b < nbox; b++) {
+      double2 acc = make_double2(0, 0);
+      for (int ch = 0; ch < sd.nlm; ch++) {
+        const double2 t = cmul(sP[b * sd.nlm + ch], table[sd.tab_off + (long)ch * sd.npts_pad + p]);
+        acc.x += t.x;
+        acc.y += t.y;
+      }
+      double2* dst = interleaved ? x + ((long)(b >> 4) * ngrid + g) * 16 + (b & 15) : x + (long)b * ngrid + g;
+      double2 v = *dst;
+      v.x += acc.x * c - acc.y * s;
+      v.y += acc.x * s + acc.y * c;
+      *dst = v;
+    }
+  }
+}
+
 // batched (a3): Cout[b][w] = (complex64) scale * x[b][gidx[w]]
 __global__ void __launch_bounds__(256)
 gather_pw_batch_kernel(const double2* __restrict__ x, long ngrid, const int* __restrict__ gidx,
@@ -917,6 +973,19 @@ density_accum_il_kernel(const double2* __restrict__ x, long ngrid, int ngroups, 
     a += __shfl_xor_sync(0xffffffffu, a, 2);
     a += __shfl_xor_sync(0xffffffffu, a, 1);
     if (b == 0 && g < ngrid) rho[g] += a;
+  }
+}
+
+// planar boxes out[j][g] (j < nslots) from the interleaved group layout x[group][g][16], slots slot0 .. slot0+nslots-1
+// (slot0 is relative to the first slot of x): the caller-layout copy of single real-space states
+__global__ void __launch_bounds__(256)
+extract_il_kernel(const double2* __restrict__ x, long ngrid, int slot0, int nslots, double2* __restrict__ out) {
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < ngrid * nslots; e += stride) {
+    const int j = (int)(e / ngrid);
+    const long g = e % ngrid;
+    const int slot = slot0 + j;
+    out[e] = x[((long)(slot >> 4) * ngrid + g) * 16 + (slot & 15)];
   }
 }
 
