@@ -910,6 +910,7 @@ def run_b200(args):
                         "e2e": {"value": m2["e2e_value"], "unit": UNIT, "h2d_bytes_per_step": m2["h2d_bytes"],
                                 "d2h_bytes_per_step": m2["d2h_bytes"], "ms_per_step": m2["e2e_ms"]},
                         "roofline": roof2, "kernels": kern2, "stage_ms_per_step": m2["stage"],
+                        "checksum": m2["checksum"], "mean_abs_diagonal": m2["mean_abs_diagonal"],
                         "cpu_baseline": cpu2, "parity": par2}
     print(json.dumps(line))
     if parity is not None and not parity["ok"]:

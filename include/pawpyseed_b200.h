@@ -23,6 +23,10 @@
  *     cblas_cdotc_sub, pseudoprojector.c:86);
  *   - there is NO CPU fallback: every compute entry point fails with an error if no
  *     CUDA device is usable.
+ * Threading: like the reference (one caller thread, pswf_t mutated by overlap_setup_*), the
+ *   library is not re-entrant - one main CUDA stream, shared scratch buffers, stream-ordered
+ *   pools.  Every entry point that touches device state takes one process-wide lock, so
+ *   concurrent callers are serialised.  One process drives one GPU (the current device).
  */
 #ifndef PAWPYSEED_B200_H
 #define PAWPYSEED_B200_H

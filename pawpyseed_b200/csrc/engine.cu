@@ -657,6 +657,10 @@ struct pawb200_pswf {
   std::vector<DevBuf> P;               // per kappa: double2 [nslot][ldp]
   long ldp = 0;
   bool has_projections = false;
+  // setup_projections could not keep the FFT boxes resident: the transform + projection of the bands is deferred
+  // to the first consumer, so that overlap_setup_real can project its partial-wave tables in the SAME pass over
+  // the boxes instead of transforming every band a second time (see require_projections)
+  bool lazy_proj = false;
   // overlap_setup state (this wf's bands projected on the other structure's filtered partial waves)
   std::vector<DevBuf> W;               // per kappa: double2 [nslot][ldw]
   long ldw = 0;
@@ -1070,6 +1074,7 @@ void launch_project_mt(const SiteTables& T, const double2* x, long ngrid, int ns
 
 void launch_project(const SiteTables& T, const double2* x, long ngrid, int nslot, double2* P, long ldp,
                     int slot0) {
+  if (T.nsites == 0 || T.total_pts == 0) return;
   ScopedStage tm(ST_PROJECT);
   g_slots_projected += nslot;
   for (auto& sd : T.host) g_sphere_samples += (long long)nslot * sd.npts;
@@ -1129,15 +1134,13 @@ bool factor_pair(int n, int& r1, int& r2) {
   return found;
 }
 
-std::shared_ptr<PrunedPlan> build_pruned_plan(const pawb200_pswf* wf, int kap, const int* fftg) {
+std::shared_ptr<PrunedPlan> build_pruned_plan_kp(const KPointInfo& kp, int npw, const int* fftg) {
   auto P = std::make_shared<PrunedPlan>();
   if (getenv("PAWB200_FFT") && std::string(getenv("PAWB200_FFT")) == "cufft") return P;
   FftGeom& g = P->g;
   g.n1 = fftg[0]; g.n2 = fftg[1]; g.n3 = fftg[2];
   for (int d = 0; d < 3; d++)
     if (!factor_pair(fftg[d], g.r1[d], g.r2[d])) return P;
-  const KPointInfo& kp = wf->kp[kap];
-  const int npw = wf->npw_half(kap);
   if (npw == 0) return P;
   std::vector<int> col_start, col_cnt, col_ypos, zpos(npw), plane_col0, plane_ncol, plane_xpos;
   int last1 = -1, last2 = -1, lastz = -1;
@@ -1228,6 +1231,10 @@ std::shared_ptr<PrunedPlan> build_pruned_plan(const pawb200_pswf* wf, int kap, c
   init_small_twiddles();
   P->ok = true;
   return P;
+}
+
+std::shared_ptr<PrunedPlan> build_pruned_plan(const pawb200_pswf* wf, int kap, const int* fftg) {
+  return build_pruned_plan_kp(wf->kp[kap], wf->npw_half(kap), fftg);
 }
 
 std::shared_ptr<PrunedPlan> get_pruned_plan(pawb200_pswf* wf, int kap, const int* fftg) {
@@ -1335,6 +1342,7 @@ void launch_project_il_mt(const SiteTables& T, const double2* X, long ngrid, int
 
 void launch_project_il(const SiteTables& T, const double2* X, long ngrid, int nslot, double2* P, long ldp,
                        int slot0) {
+  if (T.nsites == 0 || T.total_pts == 0) return;
   ScopedStage tm(ST_PROJECT);
   g_slots_projected += nslot;
   for (auto& sd : T.host) g_sphere_samples += (long long)nslot * sd.npts;
@@ -1387,14 +1395,22 @@ bool prefft_all_bands(pawb200_pswf* wf, const int* fftg) {
 
 // All bands of all resident (k,spin) blocks of `wf` -> <table|psi~>, written to out[kap] [nslot][ld].
 // main_pass: this is setup_projections (boxes may be kept); otherwise kept boxes are reused when present.
+// T2 / out2 / ld2 (optional): a second table set projected from the same boxes in the same pass.
 void project_all_bands(pawb200_pswf* wf, SiteTables& T, const int* fftg, std::vector<DevBuf>& out,
-                       long& ld, bool main_pass) {
+                       long& ld, bool main_pass, SiteTables* T2 = nullptr, std::vector<DevBuf>* out2 = nullptr,
+                       long* ld2 = nullptr) {
   HostSection hs_("project_all_bands");
   const int NK = wf->nkappa();
   const long ngrid = (long)fftg[0] * fftg[1] * fftg[2];
   ld = ((long)std::max(T.nproj, 1) + 7) / 8 * 8;
   out.clear();
   out.resize(NK);
+  const bool two = T2 && out2 && ld2 && T2->nsites > 0;
+  if (T2 && out2 && ld2) {
+    *ld2 = ((long)std::max(T2->nproj, 1) + 7) / 8 * 8;
+    out2->clear();
+    out2->resize(NK);
+  }
   const int nslot = wf->slot_own(), slo = wf->slot_lo();   // own band block (all bands unless band-sharded)
   const size_t out_rows = (size_t)wf->band_rows * wf->halves();
   long batch = (long)(fft_budget_bytes() / (sizeof(double2) * ngrid));
@@ -1421,19 +1437,32 @@ void project_all_bands(pawb200_pswf* wf, SiteTables& T, const int* fftg, std::ve
     if (!wf->resident[kap]) continue;
     out[kap].alloc(out_rows * ld * sizeof(double2));
     out[kap].zero();
-    if (T.nsites == 0 || nslot == 0) continue;
+    if (T2 && out2 && ld2) {
+      (*out2)[kap].alloc(out_rows * *ld2 * sizeof(double2));
+      (*out2)[kap].zero();
+    }
+    if ((T.nsites == 0 && !two) || nslot == 0) continue;
     const bool reuse = !main_pass && same_grid && (int)wf->boxes.size() == NK && wf->boxes[kap].p;
     std::shared_ptr<PrunedPlan> plan = reuse ? nullptr : get_pruned_plan(wf, kap, fftg);
     make_phase_table(T, wf, kap, fftg, reuse ? wf->boxes_interleaved : plan->ok);
+    if (two) make_phase_table(*T2, wf, kap, fftg, reuse ? wf->boxes_interleaved : plan->ok);
+    auto second_il = [&](const double2* x, int nb, int slot) {
+      if (two) launch_project_il(*T2, x, ngrid, nb, (*out2)[kap].as<double2>(), *ld2, slot);
+    };
+    auto second_planar = [&](const double2* x, int nb, int slot) {
+      if (two) launch_project(*T2, x, ngrid, nb, (*out2)[kap].as<double2>(), *ld2, slot);
+    };
     if (reuse) {
       for (int s0 = 0; s0 < nslot; s0 += 2048) {
         const int nb = std::min(2048, nslot - s0);
-        if (wf->boxes_interleaved)
-          launch_project_il(T, wf->boxes[kap].as<double2>() + (long)s0 * ngrid, ngrid, nb, out[kap].as<double2>(), ld,
-                            slo + s0);
-        else
-          launch_project(T, wf->boxes[kap].as<double2>() + (long)s0 * ngrid, ngrid, nb, out[kap].as<double2>(), ld,
-                         slo + s0);
+        const double2* xb = wf->boxes[kap].as<double2>() + (long)s0 * ngrid;
+        if (wf->boxes_interleaved) {
+          launch_project_il(T, xb, ngrid, nb, out[kap].as<double2>(), ld, slo + s0);
+          second_il(xb, nb, slo + s0);
+        } else {
+          launch_project(T, xb, ngrid, nb, out[kap].as<double2>(), ld, slo + s0);
+          second_planar(xb, nb, slo + s0);
+        }
       }
       continue;
     }
@@ -1454,6 +1483,7 @@ void project_all_bands(pawb200_pswf* wf, SiteTables& T, const int* fftg, std::ve
         double2* x = keep ? base + (long)s0 * ngrid : base;
         pruned_fft(wf, kap, *plan, slo + s0, nb, x);
         launch_project_il(T, x, ngrid, nb, out[kap].as<double2>(), ld, slo + s0);
+        second_il(x, nb, slo + s0);
       }
       continue;
     }
@@ -1473,9 +1503,25 @@ void project_all_bands(pawb200_pswf* wf, SiteTables& T, const int* fftg, std::ve
       launch_scatter(wf, kap, slo + s0, nb, inv, x, fftg);
       launch_fft(x, fftg, nb, CUFFT_INVERSE);
       launch_project(T, x, ngrid, nb, out[kap].as<double2>(), ld, slo + s0);
+      second_planar(x, nb, slo + s0);
     }
   }
 }
+
+// Projections are valid on return: a wavefunction whose setup_projections deferred the work (lazy_proj) is
+// transformed and projected now - together with a second table set when the caller has one for the same bands.
+void require_projections(pawb200_pswf* wf, SiteTables* T2 = nullptr, std::vector<DevBuf>* out2 = nullptr,
+                         long* ld2 = nullptr) {
+  if (!wf || !wf->has_projections) throw std::runtime_error("setup_projections has not been run");
+  if (wf->lazy_proj) {
+    wf->lazy_proj = false;
+    project_all_bands(wf, *wf->proj_sites, wf->fftg, wf->P, wf->ldp, true, T2, out2, ld2);
+  } else if (T2 && out2 && ld2) {
+    // boxes (if kept) are reused; otherwise the bands are transformed again for the second table set alone
+    project_all_bands(wf, *T2, wf->fftg, *out2, *ld2, false);
+  }
+}
+
 
 // ---- GEMM driver ------------------------------------------------------------------------------
 DevBuf g_zg_ws;
@@ -1659,6 +1705,8 @@ AugPlan plan_aug(const pawb200_pswf* S, const pawb200_pswf* R, const SiteLists& 
   HostSection hs_("plan_aug");
   if (!S->has_projections || !R->has_projections)
     throw std::runtime_error("setup_projections has not been run on both wavefunctions");
+  require_projections(const_cast<pawb200_pswf*>(S));
+  require_projections(const_cast<pawb200_pswf*>(R));
   const auto& elsR = R->pps->list.el;
   const auto& elsS = S->pps->list.el;
   AugPlan A;
@@ -1869,7 +1917,7 @@ void overlap_matrix(pawb200_pswf* S, pawb200_pswf* R, const SiteLists* L, int fl
 
 // ---- real-space states -----------------------------------------------------------------------
 SiteTables& ae_tables(pawb200_pswf* wf, const int* fftg, const int* labels, const double* coords) {
-  if (!wf->has_projections) throw std::runtime_error("setup_projections has not been run");
+  require_projections(wf);
   const size_t h = hash_bytes(coords, sizeof(double) * 3 * wf->num_sites, hash_bytes(labels, sizeof(int) * wf->num_sites));
   if (!wf->ae_sites || wf->ae_sites->fftg[0] != fftg[0] || wf->ae_sites->fftg[1] != fftg[1] ||
       wf->ae_sites->fftg[2] != fftg[2] || wf->ae_sites->coord_hash != h) {
@@ -2150,6 +2198,7 @@ void* pawb200_get_device_buffer(pawb200_pswf_t* wf, int which, int kappa, long* 
     wait_coeffs(wf, kappa, 0, wf->nband);
     p = wf->C[kappa].p; l = wf->ldc[kappa]; r = wf->band_rows; lo = wf->band_lo; hi = wf->band_hi;
   } else if (which == 1 || which == 2) {   // projections / wave projections: one row per slot
+    require_projections(wf);
     std::vector<DevBuf>& v = which == 1 ? wf->P : wf->W;
     if (kappa >= (int)v.size() || !v[kappa].p) throw std::runtime_error("projections have not been set up");
     p = v[kappa].p; l = which == 1 ? wf->ldp : wf->ldw; r = wf->band_rows * h; lo = wf->band_lo * h; hi = wf->band_hi * h;
@@ -2274,8 +2323,22 @@ void pawb200_setup_projections(pawb200_pswf_t* wf, pawb200_ppot_t* pps, int num_
   for (int i = 0; i < num_sites; i++) all[i] = i;
   const bool pre = prefft_all_bands(wf, fftg);     // queue the transforms first; the host work below overlaps them
   wf->proj_sites = build_site_tables(pps->list.el, all.data(), num_sites, labels, coords, wf->lattice, fftg, 0, true);
-  project_all_bands(wf, *wf->proj_sites, fftg, wf->P, wf->ldp, !pre);
   wf->has_projections = true;
+  wf->lazy_proj = false;
+  int nres = 0;
+  for (int kap = 0; kap < wf->nkappa(); kap++) nres += wf->resident[kap] ? 1 : 0;
+  const size_t box_bytes = (size_t)wf->slot_own() * fftg[0] * fftg[1] * fftg[2] * sizeof(double2);
+  static const bool lazy_ok = !(getenv("PAWB200_LAZY") && atoi(getenv("PAWB200_LAZY")) == 0);
+  if (!pre && lazy_ok && box_bytes * (size_t)std::max(nres, 1) > keep_boxes_budget()) {
+    // The boxes cannot stay resident, so a later overlap_setup_real would have to transform every band again.
+    // Defer: the first consumer of the projections runs the pass (require_projections), and overlap_setup_real
+    // adds its own table set to that same pass.
+    wf->P.clear();
+    wf->boxes.clear();
+    wf->lazy_proj = true;
+  } else {
+    project_all_bands(wf, *wf->proj_sites, fftg, wf->P, wf->ldp, !pre);
+  }
   API_END_VOID
 }
 
@@ -2548,14 +2611,16 @@ void pawb200_overlap_setup_real(pawb200_pswf_t* wf_R, pawb200_pswf_t* wf_S, cons
   if (num_N_R > 0) {
     auto T = build_site_tables(elsR, N_R, num_N_R, labels_R, coords_R, wf_S->lattice, wf_S->fftg, 1, false);
     for (auto& sd : T->host) wf_S->wp_nlm.push_back(sd.nlm);
-    project_all_bands(wf_S, *T, wf_S->fftg, wf_S->W, wf_S->ldw, false);
+    require_projections(wf_S, T.get(), &wf_S->W, &wf_S->ldw);     // one pass over the boxes for P (if deferred) and W
   }
   // part 2 (:649-671)
   if (num_N_S > 0) {
     auto T = build_site_tables(elsS, N_S, num_N_S, labels_S, coords_S, wf_R->lattice, wf_R->fftg, 1, false);
     for (auto& sd : T->host) wf_R->wp_nlm.push_back(sd.nlm);
-    project_all_bands(wf_R, *T, wf_R->fftg, wf_R->W, wf_R->ldw, false);
+    require_projections(wf_R, T.get(), &wf_R->W, &wf_R->ldw);
   }
+  require_projections(wf_R);
+  require_projections(wf_S);
   setup_offsite(wf_R, wf_S, labels_R, labels_S, coords_R, coords_S, N_RS_R, N_RS_S, num_N_RS);
   wf_R->recip_setup = wf_S->recip_setup = false;
   wf_R->CA.clear(); wf_S->CA.clear();
@@ -2609,6 +2674,8 @@ void pawb200_overlap_setup_recip(pawb200_pswf_t* wf_R, pawb200_pswf_t* wf_S, con
   wf_R->CA.clear(); wf_S->CA.clear();
   if (wf_R->band_sharded() || wf_S->band_sharded())
     throw std::runtime_error("method aug_recip is not available on band-sharded wavefunctions (use aug_real)");
+  require_projections(wf_R);
+  require_projections(wf_S);
   if (num_N_R > 0) compute_aug_freqs(wf_R, N_R, num_N_R, labels_R, coords_R);   // part 1 (:748-767)
   if (num_N_S > 0) compute_aug_freqs(wf_S, N_S, num_N_S, labels_S, coords_S);   // part 2 (:770-792)
   setup_offsite(wf_R, wf_S, labels_R, labels_S, coords_R, coords_S, N_RS_R, N_RS_S, num_N_RS);
@@ -2867,6 +2934,32 @@ void pawb200_project_realspace_state(pawb200_c128* projs, int BAND_NUM, pawb200_
       for (int b = 0; b < nR; b++) out[(size_t)b * NK + kap] = cdouble(0, 0);
       continue;
     }
+    std::shared_ptr<PrunedPlan> planS = get_pruned_plan(wf, kap, fftg), planR = get_pruned_plan(wf_R, kap, fftg);
+    if (planS->ok && planR->ok && !getenv("PAWB200_DENSITY_GENERIC")) {
+      // both sides through the hand-written pruned transform; the basis states stay in the interleaved layout
+      realspace_boxes_il(wf, kap, *planS, BAND_NUM, 1, fftg, TS);
+      extract_il_kernel<<<(unsigned)std::min<long>((ngrid + 255) / 256, (long)g_num_sms * 16), 256, 0, g_stream>>>(
+          g_grid.as<double2>(), ngrid, 0, 1, state.as<double2>());
+      count_launch();
+      check_launch();
+      const int gbatch = (int)std::max<long>(1, std::min<long>(4, batch / FFT_B));
+      DevBuf partial_il((size_t)gbatch * FFT_B * nchunk * sizeof(double2));
+      for (int b0 = 0; b0 < nR; b0 += gbatch * FFT_B) {
+        const int nb = std::min(gbatch * FFT_B, nR - b0), ng = (nb + FFT_B - 1) / FFT_B;
+        realspace_boxes_il(wf_R, kap, *planR, b0, nb, fftg, TR);
+        ScopedStage tm(ST_AUGMENT);
+        grid_dot_partial_il_kernel<<<dim3(nchunk, ng), 256, 0, g_stream>>>(g_grid.as<double2>(), state.as<double2>(),
+                                                                           ngrid, nchunk, partial_il.as<double2>());
+        grid_dot_final_kernel<<<(nb + 127) / 128, 128, 0, g_stream>>>(partial_il.as<double2>(), nchunk, nb, scale,
+                                                                      dres.as<double2>() + b0);
+        count_launch(2);
+        check_launch();
+      }
+      CUDA_OK(cudaMemcpyAsync(host.data(), dres.p, (size_t)nR * sizeof(double2), cudaMemcpyDeviceToHost, g_stream));
+      stream_sync();
+      for (int b = 0; b < nR; b++) out[(size_t)b * NK + kap] = host[b];
+      continue;
+    }
     {
       DevBuf inv = build_inverse_map(wf, kap, fftg);
       realspace_boxes(wf, kap, BAND_NUM, 1, fftg, TS, inv);
@@ -2911,11 +3004,63 @@ void pawb200_write_volumetric(const char* filename, const double* x, const int* 
 }
 
 // ---- single-band FFT entry points ---------------------------------------------------------------
+namespace {
+// Plan of a caller-supplied G list (the single-band fft3d / fwd_fft3d entry points): box-order permutation + pruned
+// geometry.  ok == false -> the caller falls back to scatter + cuFFT (unsupported radix, aliased grid, or a grid too
+// large for a whole 16-slot interleave group).
+std::shared_ptr<PrunedPlan> plan_for_g_list(const int* Gs, int num_waves, const int* fftg, KPointInfo& kp) {
+  const long ngrid = (long)fftg[0] * fftg[1] * fftg[2];
+  if (num_waves <= 0 || (size_t)ngrid * FFT_B * sizeof(double2) > ((size_t)2 << 30)) return std::make_shared<PrunedPlan>();
+  kp.nplane = num_waves;
+  kp.G.assign(Gs, Gs + 3 * (size_t)num_waves);
+  box_order(kp);
+  return build_pruned_plan_kp(kp, num_waves, fftg);
+}
+void ensure_group_scratch(const FftGeom& g) {
+  g_fft_t1.ensure((size_t)g.ncol * g.n3 * FFT_B * sizeof(double2));
+  g_fft_t2.ensure((size_t)g.nplane * g.n2 * g.n3 * FFT_B * sizeof(double2));
+}
+}  // namespace
+
 void pawb200_fft3d(pawb200_c128* x, const int*, const double* lattice, const double*, const int* Gs,
                    const pawb200_c64* Cs, int num_waves, const int* fftg) {
   API_BEGIN
   require_device();
   const long ngrid = (long)fftg[0] * fftg[1] * fftg[2];
+  {
+    KPointInfo kp;
+    std::shared_ptr<PrunedPlan> plan = plan_for_g_list(Gs, num_waves, fftg, kp);
+    if (plan->ok && plan->g.col_run) {
+      // slot 0 of one interleave group carries the band; the hand-written pruned transform does the rest
+      const long ldil = ((long)num_waves + 1) / 2 * 2;
+      std::vector<float2> il((size_t)ldil * FFT_B, make_float2(0.f, 0.f));
+      const float2* C = reinterpret_cast<const float2*>(Cs);
+      for (int j = 0; j < num_waves; j++) il[(size_t)j * FFT_B] = C[kp.perm[j]];
+      DevBuf dil = upload(il);
+      const FftGeom& g = plan->g;
+      ensure_group_scratch(g);
+      g_grid.ensure((size_t)ngrid * FFT_B * sizeof(double2));
+      FftInput in;
+      in.Cil = dil.as<float2>(); in.ldil = ldil; in.C = nullptr; in.ldc = 0; in.halves = 1; in.half_len = num_waves;
+      FftWork w;
+      w.T1 = g_fft_t1.as<double2>(); w.T2 = g_fft_t2.as<double2>();
+      const double scale = std::pow(determinant3(lattice), -0.5);
+      {
+        ScopedStage tm(ST_FFT);
+        g_boxes_fft += 1;
+        count_launch(launch_pruned_passes(g, in, 0, 1, 1, scale, w, nullptr, g_grid.as<double2>(), g_num_sms, g_stream,
+                                          plan->max_plane_cols));
+      }
+      DevBuf planar((size_t)ngrid * sizeof(double2));
+      extract_il_kernel<<<(unsigned)std::min<long>((ngrid + 255) / 256, (long)g_num_sms * 16), 256, 0, g_stream>>>(
+          g_grid.as<double2>(), ngrid, 0, 1, planar.as<double2>());
+      count_launch();
+      check_launch();
+      CUDA_OK(cudaMemcpyAsync(x, planar.p, ngrid * sizeof(double2), cudaMemcpyDeviceToHost, g_stream));
+      stream_sync();
+      return;
+    }
+  }
   std::vector<int> inv(ngrid, -1);
   for (int w = 0; w < num_waves; w++) {
     const long g1 = (Gs[3 * w] + fftg[0]) % fftg[0], g2 = (Gs[3 * w + 1] + fftg[1]) % fftg[1],
@@ -2944,6 +3089,40 @@ void pawb200_fwd_fft3d(pawb200_c128* x, const int*, const double* lattice, const
   API_BEGIN
   require_device();
   const long ngrid = (long)fftg[0] * fftg[1] * fftg[2];
+  {
+    KPointInfo kp;
+    std::shared_ptr<PrunedPlan> plan = plan_for_g_list(Gs, num_waves, fftg, kp);
+    if (plan->ok && plan->g.col_run) {
+      // forward transform pruned on the output side (fft_fwd_pass_*): the box goes into slot 0 of an interleave group
+      const FftGeom& g = plan->g;
+      ensure_group_scratch(g);
+      g_grid.ensure((size_t)ngrid * FFT_B * sizeof(double2));
+      DevBuf planar((size_t)ngrid * sizeof(double2));
+      CUDA_OK(cudaMemcpyAsync(planar.p, x, ngrid * sizeof(double2), cudaMemcpyHostToDevice, g_stream));
+      CUDA_OK(cudaMemsetAsync(g_grid.p, 0, (size_t)ngrid * FFT_B * sizeof(double2), g_stream));
+      insert_il_kernel<<<(unsigned)std::min<long>((ngrid + 255) / 256, (long)g_num_sms * 16), 256, 0, g_stream>>>(
+          planar.as<double2>(), ngrid, 0, 1, g_grid.as<double2>());
+      count_launch();
+      check_launch();
+      const long ldil = ((long)num_waves + 1) / 2 * 2;
+      DevBuf dil((size_t)ldil * FFT_B * sizeof(float2));
+      FftWork w;
+      w.T1 = g_fft_t1.as<double2>(); w.T2 = g_fft_t2.as<double2>();
+      const double scale = std::pow(determinant3(lattice), 0.5) / fftg[0] / fftg[1] / fftg[2];   // linalg.c:64-65
+      {
+        ScopedStage tm(ST_FFT);
+        g_boxes_fft += 1;
+        count_launch(launch_pruned_forward(g, 1, g_grid.as<double2>(), w, dil.as<float2>(), ldil, scale, g_num_sms,
+                                           g_stream));
+      }
+      std::vector<float2> il((size_t)ldil * FFT_B);
+      CUDA_OK(cudaMemcpyAsync(il.data(), dil.p, il.size() * sizeof(float2), cudaMemcpyDeviceToHost, g_stream));
+      stream_sync();
+      float2* C = reinterpret_cast<float2*>(Cs);
+      for (int j = 0; j < num_waves; j++) C[kp.perm[j]] = il[(size_t)j * FFT_B];
+      return;
+    }
+  }
   std::vector<int> gi(num_waves);
   for (int w = 0; w < num_waves; w++) {
     const long g1 = (Gs[3 * w] + fftg[0]) % fftg[0], g2 = (Gs[3 * w + 1] + fftg[1]) % fftg[1],
@@ -3051,6 +3230,7 @@ int pawb200_num_projections(pawb200_pswf_t* wf, int which) {
 int pawb200_get_projections(pawb200_pswf_t* wf, int band, int kappa, int which, pawb200_c128* out) {
   API_BEGIN
   check_kpoint(wf, band, kappa);
+  require_projections(wf);
   const int n = pawb200_num_projections(wf, which);
   const std::vector<DevBuf>& src = which == 3 ? wf->W : wf->P;
   const long ld = which == 3 ? wf->ldw : wf->ldp;
@@ -3176,6 +3356,7 @@ BoxMap build_box_map(const pawb200_pswf* wf, int kap) {
 }
 
 std::vector<cdouble> fetch_projection_row(pawb200_pswf* wf, int kap, int band) {
+  require_projections(wf);
   const int np = wf->proj_sites ? wf->proj_sites->nproj : 0;
   std::vector<cdouble> row(std::max(np, 1));
   CUDA_OK(cudaMemcpyAsync(row.data(), wf->P[kap].as<double2>() + (long)band * wf->ldp,

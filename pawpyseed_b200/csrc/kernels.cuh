@@ -989,6 +989,18 @@ extract_il_kernel(const double2* __restrict__ x, long ngrid, int slot0, int nslo
   }
 }
 
+// the reverse: planar boxes in[j][g] into slots slot0 .. of the (pre-zeroed) interleaved layout
+__global__ void __launch_bounds__(256)
+insert_il_kernel(const double2* __restrict__ in, long ngrid, int slot0, int nslots, double2* __restrict__ x) {
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < ngrid * nslots; e += stride) {
+    const int j = (int)(e / ngrid);
+    const long g = e % ngrid;
+    const int slot = slot0 + j;
+    x[((long)(slot >> 4) * ngrid + g) * 16 + (slot & 15)] = in[e];
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // (f4) momentum matrix elements  [momentum.c]
 // ---------------------------------------------------------------------------------------
@@ -1152,6 +1164,33 @@ grid_dot_partial_kernel(const double2* __restrict__ xR, const double2* __restric
     __syncthreads();
   }
   if (threadIdx.x == 0) partial[(long)b * nchunk + c] = make_double2(sr[0], si[0]);
+}
+// same partial sums on interleaved boxes xR[group][g][16]: block = (chunk, group), thread = (point, band)
+__global__ void __launch_bounds__(256)
+grid_dot_partial_il_kernel(const double2* __restrict__ xR, const double2* __restrict__ x, long ngrid, int nchunk,
+                           double2* __restrict__ partial) {
+  const int grp = blockIdx.y, c = blockIdx.x;
+  const int b = threadIdx.x & 15, pt = threadIdx.x >> 4;
+  const long per = (ngrid + nchunk - 1) / nchunk;
+  const long g0 = (long)c * per, g1 = min(ngrid, g0 + per);
+  double re = 0, im = 0;
+  for (long g = g0 + pt; g < g1; g += 16) {
+    const double2 a = xR[((long)grp * ngrid + g) * 16 + b], v = x[g];
+    re += a.x * v.x + a.y * v.y;
+    im += a.x * v.y - a.y * v.x;
+  }
+  __shared__ double sr[256], si[256];
+  sr[threadIdx.x] = re;
+  si[threadIdx.x] = im;
+  __syncthreads();
+  for (int s = 128; s >= 16; s >>= 1) {          // fixed tree over the 16 point slots of each band
+    if (threadIdx.x < s) {
+      sr[threadIdx.x] += sr[threadIdx.x + s];
+      si[threadIdx.x] += si[threadIdx.x + s];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x < 16) partial[(long)(grp * 16 + threadIdx.x) * nchunk + c] = make_double2(sr[threadIdx.x], si[threadIdx.x]);
 }
 __global__ void grid_dot_final_kernel(const double2* __restrict__ partial, int nchunk, int nb, double scale,
                                       double2* __restrict__ out) {

@@ -1,5 +1,11 @@
 """pawpyseed/core/projector.py on the GPU engine: `Projector(wf, basis)` with
-`single_band_projection`, `proportion_conduction`, `defect_band_analysis`."""
+`single_band_projection`, `proportion_conduction`, `defect_band_analysis`.
+
+This module restates the Python API layer of pawpyseed (pawpyseed/core/projector.py, Copyright (c) 2017 Kyle Bystrom,
+BSD 3-clause licence - see the upstream LICENSE) on top of the B200 engine: class / method names, argument
+meaning and the bookkeeping code around the compute calls follow the reference so that user code switches by
+import path only.  It is the drop-in surface required by the integration boundary, not an independent design.
+"""
 from __future__ import annotations
 
 import time

@@ -5,6 +5,11 @@ arguments and method names (file:line cited per method) so user code switches by
 path only.  pymatgen is optional: `from_files` / `from_directory` need it (they parse
 POSCAR / POTCAR / vasprun.xml exactly like the reference); everything else accepts either
 pymatgen objects or the light `structure.Structure`.
+
+This module restates the Python API layer of pawpyseed (pawpyseed/core/wavefunction.py, Copyright (c) 2017 Kyle Bystrom,
+BSD 3-clause licence - see the upstream LICENSE) on top of the B200 engine: class / method names, argument
+meaning and the bookkeeping code around the compute calls follow the reference so that user code switches by
+import path only.  It is the drop-in surface required by the integration boundary, not an independent design.
 """
 from __future__ import annotations
 
