@@ -2608,19 +2608,21 @@ void pawb200_overlap_setup_real(pawb200_pswf_t* wf_R, pawb200_pswf_t* wf_S, cons
   const auto& elsR = wf_R->pps->list.el;
   const auto& elsS = wf_S->pps->list.el;
   // part 1 (projector.c:625-646): filtered partial waves of R's N_R sites on S's grid, all S bands
+  std::unique_ptr<SiteTables> T_NR, T_NS;
   if (num_N_R > 0) {
-    auto T = build_site_tables(elsR, N_R, num_N_R, labels_R, coords_R, wf_S->lattice, wf_S->fftg, 1, false);
-    for (auto& sd : T->host) wf_S->wp_nlm.push_back(sd.nlm);
-    require_projections(wf_S, T.get(), &wf_S->W, &wf_S->ldw);     // one pass over the boxes for P (if deferred) and W
+    T_NR = build_site_tables(elsR, N_R, num_N_R, labels_R, coords_R, wf_S->lattice, wf_S->fftg, 1, false);
+    for (auto& sd : T_NR->host) wf_S->wp_nlm.push_back(sd.nlm);
   }
-  // part 2 (:649-671)
-  if (num_N_S > 0) {
-    auto T = build_site_tables(elsS, N_S, num_N_S, labels_S, coords_S, wf_R->lattice, wf_R->fftg, 1, false);
-    for (auto& sd : T->host) wf_R->wp_nlm.push_back(sd.nlm);
-    require_projections(wf_R, T.get(), &wf_R->W, &wf_R->ldw);
+  if (num_N_S > 0) {     // part 2 (:649-671)
+    T_NS = build_site_tables(elsS, N_S, num_N_S, labels_S, coords_S, wf_R->lattice, wf_R->fftg, 1, false);
+    for (auto& sd : T_NS->host) wf_R->wp_nlm.push_back(sd.nlm);
   }
-  require_projections(wf_R);
-  require_projections(wf_S);
+  // One pass over the boxes of each wavefunction for P (if deferred) and W.  The wavefunction that was read first
+  // goes first: with asynchronous ingest its coefficients are the ones already arriving, the other one's copies
+  // are queued behind them.
+  auto pass_S = [&] { require_projections(wf_S, T_NR.get(), T_NR ? &wf_S->W : nullptr, T_NR ? &wf_S->ldw : nullptr); };
+  auto pass_R = [&] { require_projections(wf_R, T_NS.get(), T_NS ? &wf_R->W : nullptr, T_NS ? &wf_R->ldw : nullptr); };
+  if (wf_R->id <= wf_S->id) { pass_R(); pass_S(); } else { pass_S(); pass_R(); }
   setup_offsite(wf_R, wf_S, labels_R, labels_S, coords_R, coords_S, N_RS_R, N_RS_S, num_N_RS);
   wf_R->recip_setup = wf_S->recip_setup = false;
   wf_R->CA.clear(); wf_S->CA.clear();

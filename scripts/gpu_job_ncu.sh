@@ -13,3 +13,10 @@ tail -1 gpurun_out/ncu_fft.log | cut -c1-200
 timeout 600 ncu --set full --clock-control none -k regex:"fft_pass|sphere_project_real|zgemm_abh_kernel<float2" -s 6 -c 5 -o gpurun_out/r02_cfg2_kernels python bench.py --config cfg2 --steps 1 --warmup 0 --no-cpu > gpurun_out/ncu_cfg2.log 2>&1
 tail -1 gpurun_out/ncu_cfg2.log | cut -c1-200
 ls -la gpurun_out/*.ncu-rep
+# e2e of the default workload after the read-order fix, with the host profile
+PAWB200_PROFILE=1 timeout 600 python bench.py --steps 3 --warmup 1 --no-cpu --no-secondary > gpurun_out/bench_g.json 2> gpurun_out/bench_g.err
+python - <<PY
+import json
+d=json.loads(open("gpurun_out/bench_g.json").read().strip().splitlines()[-1])
+print("cfg3 N=1", d["ms_per_step"], "e2e", d["e2e"]["ms_per_step"], d["checksum"])
+PY
