@@ -1139,6 +1139,7 @@ std::shared_ptr<PrunedPlan> build_pruned_plan_kp(const KPointInfo& kp, int npw, 
   if (getenv("PAWB200_FFT") && std::string(getenv("PAWB200_FFT")) == "cufft") return P;
   FftGeom& g = P->g;
   g.n1 = fftg[0]; g.n2 = fftg[1]; g.n3 = fftg[2];
+  g.pf = getenv("PAWB200_FFT_PF") ? atoi(getenv("PAWB200_FFT_PF")) : 1;
   for (int d = 0; d < 3; d++)
     if (!factor_pair(fftg[d], g.r1[d], g.r2[d])) return P;
   if (npw == 0) return P;
@@ -1253,7 +1254,8 @@ DevBuf g_fft_t1, g_fft_t2, g_fft_flags;
 size_t fused_l2_budget() {
   // ring of the fused pass Y+X: must stay L2-resident next to the streams that pass through (126 MB L2)
   if (const char* e = getenv("PAWB200_FFT_RING_BYTES")) return (size_t)atoll(e);
-  return (size_t)40 << 20;
+  const char* f = getenv("PAWB200_FFT_FUSED");
+  return (size_t)((f && atoi(f) == 2) ? 60 : 40) << 20;      // phased variant: 3 slots, two of them live
 }
 
 // Inverse transform of slots [slot0, slot0 + nslot) of kappa into X (interleaved groups of FFT_B slots).
@@ -1320,7 +1322,7 @@ void launch_project_il_mt(const SiteTables& T, const double2* X, long ngrid, int
       CUDA_OK(cudaFuncSetAttribute(sphere_project_real_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       configured_r = smem;
     }
-    sphere_project_real_kernel<MT><<<grid, 128, smem, g_stream>>>(
+    sphere_project_real_kernel<MT><<<grid, PROJ_THREADS, smem, g_stream>>>(
         T.sites.as<SiteDev>(), T.by_mt_dev[MT].as<int>(), T.idx.as<int>(), T.ureal.as<double>(),
         T.phk.as<double2>(), T.chan_m.as<int>(), X, ngrid, nslot, (nslot + FFT_B - 1) / FFT_B, P, ldp, slot0, idx_cap);
     count_launch();

@@ -159,11 +159,25 @@ __device__ __forceinline__ void line_phase2(const double2* __restrict__ buf, int
   for (int k2 = 0; k2 < R; k2++) store(k1 + R1 * k2, v[k2]);
 }
 
+// L2 prefetch of a contiguous byte range (multiple of 16 B, 16-B aligned): the passes below ask for the inputs of
+// their NEXT work item while they transform the current one, so the demand loads of phase 1 find their lines in L2
+// instead of waiting a DRAM round trip with only ~20 resident warps per SM to cover it.
+__device__ __forceinline__ void l2_prefetch(const void* p, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void l2_prefetch_line(const void* p) {      // the 128-byte line holding p
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
 template <int RMAX> struct FftLaunch {
   static constexpr int THREADS = RMAX * FFT_B;          // q-slots x 16 bands
   // resident CTAs per SM the register budget is tuned for (10: 160 thr x 5, 12: 192 x 3, 14: 224 x 2, 16: 256 x 2,
   // 20: 320 x 1 - lines up to 400 points fill the shared memory of an SM on their own)
-  static constexpr int MINB = RMAX <= 10 ? 5 : RMAX <= 12 ? 3 : RMAX <= 16 ? 2 : 1;
+#ifndef PAWB200_FFT_MINB10
+#define PAWB200_FFT_MINB10 5
+#endif
+  static constexpr int MINB = RMAX <= 10 ? PAWB200_FFT_MINB10 : RMAX <= 12 ? 3 : RMAX <= 16 ? 2 : 1;
 };
 
 // ---- pass Z: coefficients -> T1[group][col][z][FFT_B] ---------------------------------------------
@@ -190,6 +204,11 @@ fft_pass_z_kernel(FftGeom g, const float2* __restrict__ Cil, long ldil, int slot
     const int4 cur = run;
     const long nxt = line + gridDim.x;
     if (nxt < nlines) run = __ldg(g.col_run + (int)(nxt % g.ncol));     // next column's run, off the critical path
+    if (g.pf && tid == 0 && nxt < nlines && run.y > 0) {
+      // the next line's plane waves are one contiguous run of 128-byte rows of the interleaved coefficients
+      const int gs = (slot0 >> 4) + (int)(nxt / g.ncol);
+      l2_prefetch(Cil + ((long)gs * ldil + run.x) * FFT_B, (unsigned)run.y * (FFT_B * sizeof(float2)));
+    }
     double2* buf = bufs + (it & 1) * n3 * FFT_B;
     if (q < R2) {
       const int slot = slot0 + grp * FFT_B + b;
@@ -289,10 +308,29 @@ fft_pass_y_kernel(FftGeom g, const double2* __restrict__ T1, double2* __restrict
     const int grp = (int)(unit / ((long)nzc * g.nplane));
     __syncthreads();                                         // previous unit no longer reads ssrc
     for (int i = tid; i < g.n2; i += blockDim.x) ssrc[i] = g.ysrc[p * g.n2 + i];
+    // first line of the next unit of this CTA (one line ahead only: a whole unit ahead is 80 MB in flight GPU-wide and
+    // was evicted before use - ncu showed pass Y reading T1 twice)
+    long nu_base = -1;
+    int nu_plane = 0;
+    if (g.pf && unit + gridDim.x < nunits) {
+      const long nu = unit + gridDim.x;
+      nu_plane = (int)((nu / nzc) % g.nplane);
+      nu_base = ((long)(nu / ((long)nzc * g.nplane)) * g.ncol * g.n3 + (int)(nu % nzc) * FFT_ZC) * FFT_B;
+    }
     __syncthreads();
     const int z1 = min(g.n3, (zc + 1) * FFT_ZC);
     for (int z = zc * FFT_ZC; z < z1; z++, it++) {
       double2* buf = bufs + (it & 1) * g.n2 * FFT_B;
+      if (g.pf) {               // inputs of the next line: z + 1 of this unit, else the first line of the next unit
+        const bool last = z + 1 >= z1;
+        if (!last || nu_base >= 0) {
+          const double2* nin = last ? T1 + nu_base : T1 + ((long)grp * g.ncol * g.n3 + z + 1) * FFT_B;
+          for (int i = tid; i < 2 * g.n2; i += blockDim.x) {
+            const int c = last ? __ldg(g.ysrc + nu_plane * g.n2 + (i >> 1)) : ssrc[i >> 1];
+            if (c >= 0) l2_prefetch_line(reinterpret_cast<const char*>(nin + (long)c * g.n3 * FFT_B) + (i & 1) * 128);
+          }
+        }
+      }
       if (q < R2) {
         const double2* in = T1 + ((long)grp * g.ncol * g.n3 + z) * FFT_B + b;
         auto load = [&](int row) {
@@ -337,6 +375,12 @@ fft_pass_x_kernel(FftGeom g, const double2* __restrict__ T2, double2* __restrict
     const long yz = line % plane;
     const int grp = (int)(line / plane);
     double2* buf = bufs + (it & 1) * g.n1 * FFT_B;
+    if (g.pf && line + gridDim.x < nlines) {
+      const long nl = line + gridDim.x;
+      const double2* nin = T2 + ((nl / plane) * g.nplane * plane + nl % plane) * FFT_B;
+      for (int i = tid; i < 2 * g.nplane; i += blockDim.x)
+        l2_prefetch_line(reinterpret_cast<const char*>(nin + (long)(i >> 1) * plane * FFT_B) + (i & 1) * 128);
+    }
     if (q < R2) {
       const double2* in = T2 + ((long)grp * g.nplane * plane + yz) * FFT_B + b;
       auto load = [&](int row) {
@@ -546,6 +590,163 @@ fft_pass_yx_kernel(FftGeom g, YxArgs a, const double2* __restrict__ T1, double2*
       pending = cur.done;
     }
     cur = nxt;
+  }
+  publish();
+}
+
+// ---- fused pass Y + X, phased variant (PAWB200_FFT_FUSED=2) --------------------------------------------------------
+// Same idea as fft_pass_yx_kernel - T2 only ever exists as a few chunks in an L2-resident ring - but without any
+// per-line synchronisation.  The items of the whole launch form one static list, phase p = [Y lines of chunk p,
+// X lines of chunk p - 1], and CTA i simply takes items i, i + G, i + 2G, ...  A CTA talks to the others only
+// when its item moves on to another (chunk, kind) group: it publishes how many items of the old group it completed
+// (one barrier, one fence, one atomic) and checks that the new group's dependency - all Y lines of the chunk for
+// an X line, all X lines of the chunk that used the ring slot before for a Y line (ring = 3 slots) - is complete.
+// Both dependencies were produced at least LX (or LY) items earlier in the list, so in steady state the check is a
+// single load.  All CTAs must be co-resident (cooperative launch): a waiting CTA depends on CTAs with SMALLER
+// and LARGER indices alike.
+struct Yx2Args {
+  int zch, nzc, ring, nchunks;
+  unsigned* ydone;          // [nchunks] Y items of the chunk that are complete
+  unsigned* xdone;          // [nchunks]
+};
+
+template <int RMAX>
+__global__ void __launch_bounds__(FftLaunch<RMAX>::THREADS, FftLaunch<RMAX>::MINB)
+fft_pass_yx2_kernel(FftGeom g, Yx2Args a, const double2* __restrict__ T1, double2* T2c, double2* __restrict__ X) {
+  extern __shared__ __align__(16) unsigned char fft_smem[];
+  const int nmax = max(g.n1, g.n2);
+  double2* bufs = reinterpret_cast<double2*>(fft_smem);      // [2][nmax][FFT_B] exchange buffers
+  double2* twy = bufs + 2 * nmax * FFT_B;                    // [n2]
+  double2* twx = twy + g.n2;                                 // [n1]
+  int4* srun = reinterpret_cast<int4*>(twx + g.n1);          // [nplane] y-run of every active x-plane
+  int* sxsrc = reinterpret_cast<int*>(srun + g.nplane);      // [n1] plane holding each x row (or -1)
+  const int tid = threadIdx.x, q = tid / FFT_B, b = tid % FFT_B;
+  for (int i = tid; i < g.n2; i += blockDim.x) twy[i] = g.tw[1][i];
+  for (int i = tid; i < g.n1; i += blockDim.x) {
+    twx[i] = g.tw[0][i];
+    sxsrc[i] = g.xsrc[i];
+  }
+  for (int i = tid; i < g.nplane; i += blockDim.x) srun[i] = g.plane_run[i];
+  __syncthreads();
+  const unsigned LY = (unsigned)g.nplane * a.zch, LX = (unsigned)g.n2 * a.zch, per = LY + LX;
+  const long plane = (long)g.n2 * g.n3;
+  const long slot_elems = (long)g.nplane * g.n2 * a.zch * FFT_B;
+  const long cstride = (long)g.n3 * FFT_B;                   // T1: column stride
+  const long pstride = (long)g.n2 * a.zch * FFT_B;           // ring: plane stride
+  const long ystride = (long)a.zch * FFT_B;                  // ring: y stride
+  unsigned phase = 0, r = blockIdx.x;
+  while (r >= per) { r -= per; phase++; }
+  int key = -1;               // (chunk, kind) group of the items in progress: 2 * chunk + kind
+  unsigned cnt = 0;           // items of that group this CTA has completed
+  int it = 0;
+  auto publish = [&]() {
+    if (key < 0) return;
+    __syncthreads();          // every thread's stores of the group are issued
+    if (tid == 0) {
+      __threadfence();
+      atomicAdd(((key & 1) ? a.xdone : a.ydone) + (key >> 1), cnt);
+    }
+  };
+  while (phase <= (unsigned)a.nchunks) {
+    const bool isx = r >= LY;
+    const int c = isx ? (int)phase - 1 : (int)phase;
+    const bool valid = isx ? phase >= 1 : phase < (unsigned)a.nchunks;
+    // the next item of this CTA (for the L2 prefetch of a Y line's inputs)
+    unsigned nphase = phase, nr = r + gridDim.x;
+    while (nr >= per) { nr -= per; nphase++; }
+    if (valid) {
+      const int k = 2 * c + (isx ? 1 : 0);
+      if (k != key) {
+        publish();
+        key = k;
+        cnt = 0;
+        if (tid == 0) {
+          const unsigned* dep = nullptr;
+          unsigned target = 0;
+          if (isx) { dep = a.ydone + c; target = LY; }
+          else if (c >= a.ring) { dep = a.xdone + (c - a.ring); target = LX; }
+          if (dep) {
+            while (ld_acquire_u32(dep) < target) __nanosleep(40);
+            __threadfence();
+          }
+        }
+        __syncthreads();
+      }
+      cnt++;
+      const unsigned rr = isx ? r - LY : r;
+      const int row = (int)(rr / (unsigned)a.zch), zz = (int)(rr - (unsigned)row * a.zch);
+      const int grp = c / a.nzc;
+      const int z = (c - grp * a.nzc) * a.zch + zz;
+      if (z < g.n3) {
+        double2* buf = bufs + (it & 1) * nmax * FFT_B;
+        it++;
+        double2* ring = T2c + (long)(c % a.ring) * slot_elems;
+        if (g.pf && nphase < (unsigned)a.nchunks && nr < LY) {
+          // inputs of this CTA's next Y line: one 256-byte segment per active column of its plane
+          const int nrow = (int)(nr / (unsigned)a.zch), nzz = (int)(nr - (unsigned)nrow * a.zch);
+          const int ngrp = (int)nphase / a.nzc;
+          const int nz = ((int)nphase - ngrp * a.nzc) * a.zch + nzz;
+          const int4 nrun = srun[nrow];
+          if (nz < g.n3 && tid < nrun.y) {
+            const char* pp = reinterpret_cast<const char*>(T1 + (((long)ngrp * g.ncol + nrun.x + tid) * g.n3 + nz) * FFT_B);
+            l2_prefetch_line(pp);
+            l2_prefetch_line(pp + 128);
+          }
+        }
+        if (isx) {
+          if (q < g.r2[0]) {
+            const double2* in = ring + ((long)row * a.zch + zz) * FFT_B + b;
+            auto load = [&](int x) {
+              const int p = sxsrc[x];
+              return p >= 0 ? __ldcg(in + (long)p * pstride) : make_double2(0, 0);
+            };
+            const int R2 = g.r2[0];
+#define P1(R) line_phase1<R>(buf, twx, R2, q, b, load)
+            PAWB200_RADIX_SWITCH(g.r1[0], P1)
+#undef P1
+          }
+        } else {
+          if (q < g.r2[1]) {
+            const int4 run = srun[row];
+            const double2* in = T1 + ((long)grp * g.ncol * g.n3 + z) * FFT_B + b;
+            const int n2 = g.n2;
+            auto load = [&](int y) {
+              int d = y - run.z;
+              if (d < 0) d += n2;
+              if (d >= run.y) return make_double2(0, 0);
+              const int col = run.x + (d < run.w ? run.y - run.w + d : d - run.w);
+              return __ldg(in + (long)col * cstride);
+            };
+            const int R2 = g.r2[1];
+#define P1(R) line_phase1<R>(buf, twy, R2, q, b, load)
+            PAWB200_RADIX_SWITCH(g.r1[1], P1)
+#undef P1
+          }
+        }
+        __syncthreads();
+        if (isx) {
+          if (q < g.r1[0]) {
+            double2* out = X + ((long)grp * g.n1 * plane + (long)row * g.n3 + z) * FFT_B + b;
+            auto store = [&](int x, double2 v) { out[(long)x * plane * FFT_B] = v; };
+            const int R1 = g.r1[0];
+#define P2(R) line_phase2<R>(buf, R1, q, b, store)
+            PAWB200_RADIX_SWITCH(g.r2[0], P2)
+#undef P2
+          }
+        } else {
+          if (q < g.r1[1]) {
+            double2* out = ring + ((long)row * g.n2 * a.zch + zz) * FFT_B + b;
+            auto store = [&](int y, double2 v) { __stcg(out + (long)y * ystride, v); };
+            const int R1 = g.r1[1];
+#define P2(R) line_phase2<R>(buf, R1, q, b, store)
+            PAWB200_RADIX_SWITCH(g.r2[1], P2)
+#undef P2
+          }
+        }
+      }
+    }
+    phase = nphase;
+    r = nr;
   }
   publish();
 }

@@ -117,6 +117,35 @@ void launch_pass_yx(const FftGeom& g, const YxConfig& yx, int ng, const double2*
   fft_pass_yx_kernel<RMAX><<<yx.grid, yx_threads(g), yx_smem(g), st>>>(g, a, T1, ring, X);
 }
 
+inline size_t yx2_smem(const FftGeom& g) {
+  const int nmax = std::max(g.n1, g.n2);
+  return (size_t)(2 * nmax * FFT_B + g.n1 + g.n2) * sizeof(double2) + (size_t)g.nplane * sizeof(int4) +
+         (size_t)g.n1 * sizeof(int) + 16;
+}
+
+template <int RMAX>
+int yx2_occupancy(const FftGeom& g) {
+  return cached_occupancy(fft_pass_yx2_kernel<RMAX>, yx_threads(g), yx2_smem(g));
+}
+
+// phased fused pass: cooperative launch (every CTA must be resident, see fft_pass_yx2_kernel)
+template <int RMAX>
+void launch_pass_yx2(const FftGeom& g, const YxConfig& yx, int ng, const double2* T1, double2* ring, unsigned* flags,
+                     double2* X, cudaStream_t st) {
+  FftGeom gg = g;
+  Yx2Args a;
+  a.zch = yx.zch; a.nzc = yx.nzc; a.ring = yx.ring;
+  a.nchunks = ng * yx.nzc;
+  a.ydone = flags;
+  a.xdone = flags + a.nchunks;
+  FFT_CUDA_OK(cudaMemsetAsync(flags, 0, yx.flag_words(ng) * sizeof(unsigned), st));
+  const long items = (long)(a.nchunks + 1) * (long)(g.nplane + g.n2) * yx.zch;
+  const unsigned grid = (unsigned)std::min<long>(yx.grid, items);
+  void* args[] = {&gg, &a, &T1, &ring, &X};
+  FFT_CUDA_OK(cudaLaunchCooperativeKernel((const void*)fft_pass_yx2_kernel<RMAX>, dim3(grid), dim3(yx_threads(g)), args,
+                                          yx2_smem(g), st));
+}
+
 // ---- TMA-fed passes (fft_pass_tma_kernel) ------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -254,6 +283,31 @@ YxConfig plan_fused_yx(const FftGeom& g, int num_sms, size_t l2_budget_bytes) {
   if (yx_smem(g) > (size_t)kFftSmemOptIn) return c;
   const int ryx = std::max(std::max(g.r1[0], g.r2[0]), std::max(g.r1[1], g.r2[1]));
   int occ = 1;
+  if (atoi(e) == 2) {
+    // phased variant: ring of 3 chunk slots, chunk = zch z values of one band group
+    int coop = 0, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    if (!coop) return c;
+#define OCC2(R) occ = yx2_occupancy<R>(g)
+    PAWB200_AXIS_SWITCH(ryx, OCC2);
+#undef OCC2
+    const size_t per_z = (size_t)g.nplane * g.n2 * FFT_B * sizeof(double2);
+    int zmax = (int)std::min<size_t>((size_t)g.n3, l2_budget_bytes / (3 * per_z));
+    if (zmax < 1) return c;
+    int zch = zmax;
+    for (int z = zmax; z >= std::max(1, (2 * zmax + 2) / 3); z--)      // prefer a divisor of n3 close to the budget
+      if (g.n3 % z == 0) { zch = z; break; }
+    c.mode = 2;
+    c.zch = zch;
+    c.nzc = (g.n3 + zch - 1) / zch;
+    c.ring = 3;
+    c.lead = 1;
+    c.grid = num_sms * occ;
+    c.ring_bytes = (size_t)c.ring * per_z * zch;
+    c.ok = true;
+    return c;
+  }
 #define OCC(R) occ = yx_occupancy<R>(g)
   PAWB200_AXIS_SWITCH(ryx, OCC);
 #undef OCC
@@ -327,8 +381,11 @@ int launch_pruned_passes(const FftGeom& g, const FftInput& in, int s0, int ns, i
   if (yx && yx->ok) {
     const int ryx = std::max(ry, rx);
 #define PASS_YX(R) launch_pass_yx<R>(g, *yx, ng, w.T1, w.T2, w.flags, X, st)
-    PAWB200_AXIS_SWITCH(ryx, PASS_YX);
+#define PASS_YX2(R) launch_pass_yx2<R>(g, *yx, ng, w.T1, w.T2, w.flags, X, st)
+    if (yx->mode == 2) PAWB200_AXIS_SWITCH(ryx, PASS_YX2);
+    else PAWB200_AXIS_SWITCH(ryx, PASS_YX);
 #undef PASS_YX
+#undef PASS_YX2
     FFT_CUDA_OK(cudaGetLastError());
     return 2;
   }

@@ -25,6 +25,7 @@ struct FftGeom {            // device-side description of one (k-point, grid) pr
   const int* ysrc;          // [nplane][n2] column index holding (plane, y) or -1
   const int* xsrc;          // [n1] plane index holding x or -1
   const double2* tw[3];     // exp(+2 pi i m / n_d), m < n_d
+  int pf;                   // passes prefetch the inputs of their next work item into L2 (PAWB200_FFT_PF, default on)
 };
 
 struct FftInput {           // coefficient source of pass Z
@@ -39,6 +40,7 @@ struct FftInput {           // coefficient source of pass Z
 // L2, so the intermediate T2 never travels to HBM (see fft_pass_yx_kernel).
 struct YxConfig {
   bool ok = false;
+  int mode = 1;             // 1: in-order ticket queue with per-line dependencies; 2: static phases (cooperative launch)
   int zch = 0;              // z values per chunk
   int nzc = 0;              // chunks per band group
   int ring = 0;             // chunk slots in the ring

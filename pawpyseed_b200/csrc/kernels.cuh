@@ -601,8 +601,13 @@ inline size_t sphere_project_real_smem() {
   return (size_t)PROJ_STAGES * (sizeof(double2) * (PROJ_KT * PROJ_LDB + PROJ_KT) + sizeof(double) * 8 * MT * PROJ_LDU);
 }
 
+// 8 warps per CTA: warps w and w + 4 work on the same 8 slots and split the k-steps of every stage between them
+// (even / odd), so an SM holds twice the warps for the same shared memory - the 4-warp version left the DMMA pipe idle
+// between the dependent issue slots of its two warps per scheduler (ncu r02: "wait" 44 % of the stall samples).
+constexpr int PROJ_THREADS = 256;
+
 template <int MT>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(PROJ_THREADS)
 sphere_project_real_kernel(const SiteDev* __restrict__ sites, const int* __restrict__ site_list,
                            const int* __restrict__ idx, const double* __restrict__ ureal,
                            const double2* __restrict__ phk, const int* __restrict__ chan_m,
@@ -616,10 +621,12 @@ sphere_project_real_kernel(const SiteDev* __restrict__ sites, const int* __restr
   double* sU = reinterpret_cast<double*>(sPh + PROJ_STAGES * PROJ_KT);      // [ST][8*MT][LDU] real table rows
   int* sIdx = reinterpret_cast<int*>(sU + PROJ_STAGES * 8 * MT * PROJ_LDU); // [idx_cap] sphere index list
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wq = warp & 3;                          // slot octet of this warp
+  const int wh = warp >> 2;                         // which half of the k-steps of a stage
   const int sbase = blockIdx.x * PROJ_NB;
   const int nk = sd.npts_pad / PROJ_KT;
-  for (int e = tid; e < sd.npts_pad && e < idx_cap; e += 128) sIdx[e] = __ldg(idx + sd.pt_off + e);
-  for (int e = tid; e < PROJ_STAGES * 8 * MT * PROJ_LDU; e += 128) {
+  for (int e = tid; e < sd.npts_pad && e < idx_cap; e += PROJ_THREADS) sIdx[e] = __ldg(idx + sd.pt_off + e);
+  for (int e = tid; e < PROJ_STAGES * 8 * MT * PROJ_LDU; e += PROJ_THREADS) {
     const int row = (e / PROJ_LDU) % (8 * MT);
     if (row >= sd.nlm) sU[e] = 0.0;                 // channel padding rows, never overwritten
   }
@@ -631,17 +638,17 @@ sphere_project_real_kernel(const SiteDev* __restrict__ sites, const int* __restr
   auto issue = [&](int kt, int st) {
     if (kt < nk) {
 #pragma unroll
-      for (int q = 0; q < PROJ_KT / 4; q++) {
-        const int pt = warp + 4 * q;
+      for (int q = 0; q < PROJ_KT / 8; q++) {
+        const int pt = warp + 8 * q;
         const int ip = kt * PROJ_KT + pt;
         const int g = ip < idx_cap ? sIdx[ip] : __ldg(idx + sd.pt_off + ip);   // warp-uniform -> broadcast
         cp_async16(sB + (st * PROJ_KT + pt) * PROJ_LDB + lane, xsrc + (long)g * IL);
       }
       // real table tile: nlm rows x 32 points (16 chunks of 16 B per row); a warp covers two rows per pass
-      for (int row = 2 * warp + (lane >> 4); row < sd.nlm; row += 8)
+      for (int row = 2 * warp + (lane >> 4); row < sd.nlm; row += 16)
         cp_async16(sU + (st * 8 * MT + row) * PROJ_LDU + 2 * (lane & 15),
                    ureal + sd.tab_off + (long)row * sd.npts_pad + kt * PROJ_KT + 2 * (lane & 15));
-      if (warp == 3) cp_async16(sPh + st * PROJ_KT + lane, phk + sd.pt_off + kt * PROJ_KT + lane);
+      if (warp == 7) cp_async16(sPh + st * PROJ_KT + lane, phk + sd.pt_off + kt * PROJ_KT + lane);
     }
     cp_async_commit();
   };
@@ -660,8 +667,9 @@ sphere_project_real_kernel(const SiteDev* __restrict__ sites, const int* __restr
     const double2* tP = sPh + st * PROJ_KT;
     const double* tU = sU + st * 8 * MT * PROJ_LDU;
 #pragma unroll
-    for (int kk = 0; kk < PROJ_KT / 4; kk++) {
-      const double2 x = tB[(4 * kk + (lane & 3)) * PROJ_LDB + 8 * warp + (lane >> 2)];
+    for (int k2 = 0; k2 < PROJ_KT / 8; k2++) {
+      const int kk = 2 * k2 + wh;
+      const double2 x = tB[(4 * kk + (lane & 3)) * PROJ_LDB + 8 * wq + (lane >> 2)];
       const double2 ph = tP[4 * kk + (lane & 3)];
       const double bx = x.x * ph.x - x.y * ph.y, by = x.x * ph.y + x.y * ph.x;     // x' = x dv e^{i k.r}
 #pragma unroll
@@ -674,13 +682,24 @@ sphere_project_real_kernel(const SiteDev* __restrict__ sites, const int* __restr
   }
   cp_async_wait<0>();
   __syncthreads();                                 // every warp is done with the stage buffers: reuse sB for Q
-  // Q fragment: row (channel) = 8m + lane>>2, cols (slots) = 2*(lane&3)+{0,1}  ->  sQ[warp][channel][8 slots]
-  double2* sQ = sB + warp * (8 * MT * 8);
+  // Q fragment: row (channel) = 8m + lane>>2, cols (slots) = 2*(lane&3)+{0,1}  ->  sQ[octet][channel][8 slots]
+  double2* sQ = sB + wq * (8 * MT * 8);
+  if (wh == 1) {
+#pragma unroll
+    for (int m = 0; m < MT; m++)
+#pragma unroll
+      for (int c = 0; c < 2; c++)
+        sQ[(8 * m + (lane >> 2)) * 8 + 2 * (lane & 3) + c] = make_double2(qr[m][c], qi[m][c]);
+  }
+  __syncthreads();
+  if (wh == 1) return;
 #pragma unroll
   for (int m = 0; m < MT; m++)
 #pragma unroll
-    for (int c = 0; c < 2; c++)
-      sQ[(8 * m + (lane >> 2)) * 8 + 2 * (lane & 3) + c] = make_double2(qr[m][c], qi[m][c]);
+    for (int c = 0; c < 2; c++) {
+      double2& e = sQ[(8 * m + (lane >> 2)) * 8 + 2 * (lane & 3) + c];      // same thread wrote / reads this element
+      e = make_double2(e.x + qr[m][c], e.y + qi[m][c]);
+    }
   __syncwarp();
 #pragma unroll
   for (int m = 0; m < MT; m++) {
@@ -690,7 +709,7 @@ sphere_project_real_kernel(const SiteDev* __restrict__ sites, const int* __restr
 #pragma unroll
       for (int c = 0; c < 2; c++) {
         const int col = 2 * (lane & 3) + c;
-        const int s = sbase + 8 * warp + col;
+        const int s = sbase + 8 * wq + col;
         if (s >= nslot) continue;
         const double2 q0 = sQ[ch * 8 + col];
         double2 out = q0;
