@@ -51,9 +51,11 @@ UNIT = "pairs/s"
 # --------------------------------------------------------------------------------------------
 # workloads
 # --------------------------------------------------------------------------------------------
-def workload(name, nk=1, nband=None):
+def workload(name, nk=1, nband=None, blocks=None):
     """Returns dict(lattice, encut, kpts, nspin, nband, basis/wf coords+labels, elements, site_cat, dim).
-    nk is only used by config 2's weak-scaling variant (nk Gamma-like k-points, one per GPU)."""
+    nk is only used by config 2's weak-scaling variant (nk Gamma-like k-points, one per GPU).
+    blocks (debug): keep only the first `blocks` (k,spin) blocks of a multi-k workload (1 = what one rank of an
+    8-GPU config-3 job holds)."""
     if name == "cfg2":      # Si216 bulk vs Si215 vacancy, ENCUT 520, Gamma (full sphere), 600 bands
         lat, bulk = synth.diamond_supercell(5.43, 3)
         _, defect = synth.diamond_supercell(5.43, 3, vacancy=107)
@@ -81,6 +83,11 @@ def workload(name, nk=1, nband=None):
         raise SystemExit("unknown config %s" % name)
     if nband:
         w["nband"] = int(nband)
+    if blocks and "kpt_list" in w:
+        if blocks < len(w["kpt_list"]):
+            w["nspin"] = 1
+        w["kpt_list"] = w["kpt_list"][:max(1, min(blocks, len(w["kpt_list"])))]
+        w["name"] += " [debug: first %d block(s)]" % (len(w["kpt_list"]) * w["nspin"])
     w["key"] = name
     if "kpt_list" in w:
         w["kpts"] = np.array(w["kpt_list"])
@@ -859,7 +866,7 @@ def run_b200(args):
 
     weak = args.weak and world > 1      # --weak: config 2 replicated over N k-points, one per GPU (round-1 curve)
     scaling = "weak" if weak else "strong"
-    w = workload(args.config, nk=world if weak else 1, nband=args.nband)
+    w = workload(args.config, nk=world if weak else 1, nband=args.nband, blocks=args.blocks)
     e2e_steps = max(1, min(args.steps, 3))
     m = measure_b200(args, w, rank, world, local, args.steps, args.warmup, scaling, e2e_steps)
     if rank != 0:
@@ -1157,6 +1164,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="cfg3")
     ap.add_argument("--nband", type=int, default=None, help="override the band count (debug)")
+    ap.add_argument("--blocks", type=int, default=None, help="keep only the first n (k,spin) blocks (debug)")
     ap.add_argument("--cpu-bands", type=int, default=0, help="bands per structure in the CPU sample")
     ap.add_argument("--cpu-sites", type=int, default=0, help="sites per element in the CPU sample")
     ap.add_argument("--cpu-pair-bands", type=int, default=0, help="wf bands whose pair rows the CPU sample computes")

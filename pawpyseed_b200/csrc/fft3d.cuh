@@ -145,7 +145,7 @@ __device__ __forceinline__ void line_phase1(double2* __restrict__ buf, const dou
 #pragma unroll
   for (int k1 = 0; k1 < R; k1++) {
     double2 x = v[k1];
-    if (k1 > 0 && j2 > 0) x = cmulf(x, tw[j2 * k1]);
+    if (k1 > 0) x = cmulf(x, tw[j2 * k1]);          // tw[0] = (1, 0) exactly: no per-thread branch for j2 == 0
     buf[(k1 * R2 + j2) * FFT_B + b] = x;
   }
 }
@@ -168,6 +168,23 @@ __device__ __forceinline__ void l2_prefetch(const void* p, unsigned bytes) {
 
 __device__ __forceinline__ void l2_prefetch_line(const void* p) {      // the 128-byte line holding p
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
+// phase 2 with the common store pattern out[(k1 + R1 * k2) * stride]: one running pointer instead of R offsets
+template <int R>
+__device__ __forceinline__ void line_phase2_strided(const double2* __restrict__ buf, int R1, int k1, int b,
+                                                    double2* __restrict__ out, int stride) {
+  double2 v[R];
+#pragma unroll
+  for (int j2 = 0; j2 < R; j2++) v[j2] = buf[(k1 * R + j2) * FFT_B + b];
+  SmallDFT<R, 1>::run(v);
+  double2* po = out + k1 * stride;
+  const long inc = (long)R1 * stride;
+#pragma unroll
+  for (int k2 = 0; k2 < R; k2++) {
+    *po = v[k2];
+    po += inc;
+  }
 }
 
 template <int RMAX> struct FftLaunch {
@@ -195,19 +212,20 @@ fft_pass_z_kernel(FftGeom g, const float2* __restrict__ Cil, long ldil, int slot
   const int tid = threadIdx.x, q = tid / FFT_B, b = tid % FFT_B;
   const int R1 = g.r1[2], R2 = g.r2[2], n3 = g.n3;
   for (int i = tid; i < n3; i += blockDim.x) tw[i] = g.tw[2][i];
-  const long nlines = (long)ngroups * g.ncol;
-  long line = blockIdx.x;
-  int4 run = line < nlines ? __ldg(g.col_run + (int)(line % g.ncol)) : make_int4(0, 0, 0, 0);
+  // (group, column) of this CTA's line, advanced incrementally: no 64-bit divisions in the line loop
+  const int ncol = g.ncol, step = (int)gridDim.x;
+  int grp = (int)blockIdx.x / ncol, col = (int)blockIdx.x % ncol;
+  int4 run = grp < ngroups ? __ldg(g.col_run + col) : make_int4(0, 0, 0, 0);
   __syncthreads();
-  for (int it = 0; line < nlines; line += gridDim.x, it++) {
-    const int grp = (int)(line / g.ncol), col = (int)(line % g.ncol);
+  for (int it = 0; grp < ngroups; it++) {
     const int4 cur = run;
-    const long nxt = line + gridDim.x;
-    if (nxt < nlines) run = __ldg(g.col_run + (int)(nxt % g.ncol));     // next column's run, off the critical path
-    if (g.pf && tid == 0 && nxt < nlines && run.y > 0) {
+    int ngrp = grp, ncl = col + step;
+    while (ncl >= ncol) { ncl -= ncol; ngrp++; }
+    const bool more = ngrp < ngroups;
+    if (more) run = __ldg(g.col_run + ncl);                    // next column's run, off the critical path
+    if (g.pf && tid == 0 && more && run.y > 0) {
       // the next line's plane waves are one contiguous run of 128-byte rows of the interleaved coefficients
-      const int gs = (slot0 >> 4) + (int)(nxt / g.ncol);
-      l2_prefetch(Cil + ((long)gs * ldil + run.x) * FFT_B, (unsigned)run.y * (FFT_B * sizeof(float2)));
+      l2_prefetch(Cil + ((long)((slot0 >> 4) + ngrp) * ldil + run.x) * FFT_B, (unsigned)run.y * (FFT_B * sizeof(float2)));
     }
     double2* buf = bufs + (it & 1) * n3 * FFT_B;
     if (q < R2) {
@@ -229,11 +247,12 @@ fft_pass_z_kernel(FftGeom g, const float2* __restrict__ Cil, long ldil, int slot
     __syncthreads();
     if (q < R1) {
       double2* out = T1 + (((long)grp * g.ncol + col) * n3) * FFT_B + b;
-      auto store = [&](int row, double2 v) { out[(long)row * FFT_B] = v; };
-#define P2(R) line_phase2<R>(buf, R1, q, b, store)
+#define P2(R) line_phase2_strided<R>(buf, R1, q, b, out, FFT_B)
       PAWB200_RADIX_SWITCH(R2, P2)
 #undef P2
     }
+    grp = ngrp;
+    col = ncl;
   }
 }
 
@@ -300,22 +319,27 @@ fft_pass_y_kernel(FftGeom g, const double2* __restrict__ T1, double2* __restrict
   const int R1 = g.r1[1], R2 = g.r2[1];
   for (int i = tid; i < g.n2; i += blockDim.x) tw[i] = g.tw[1][i];
   const int nzc = (g.n3 + FFT_ZC - 1) / FFT_ZC;
-  const long nunits = (long)ngroups * g.nplane * nzc;
+  const int nunits = ngroups * g.nplane * nzc;                // 32-bit: <= 8 groups x 400 planes x 45 chunks
   int it = 0;
-  for (long unit = blockIdx.x; unit < nunits; unit += gridDim.x) {
-    const int zc = (int)(unit % nzc);
-    const int p = (int)((unit / nzc) % g.nplane);
-    const int grp = (int)(unit / ((long)nzc * g.nplane));
+  for (int unit = blockIdx.x; unit < nunits; unit += gridDim.x) {
+    const int zc = unit % nzc;
+    const int p = (unit / nzc) % g.nplane;
+    const int grp = unit / (nzc * g.nplane);
     __syncthreads();                                         // previous unit no longer reads ssrc
-    for (int i = tid; i < g.n2; i += blockDim.x) ssrc[i] = g.ysrc[p * g.n2 + i];
+    // element offset of the column holding each y row, premultiplied (32-bit: ncol * n3 * 16 < 2^31 for n <= 400)
+    const int colstride = g.n3 * FFT_B;
+    for (int i = tid; i < g.n2; i += blockDim.x) {
+      const int c = g.ysrc[p * g.n2 + i];
+      ssrc[i] = c >= 0 ? c * colstride : -1;
+    }
     // first line of the next unit of this CTA (one line ahead only: a whole unit ahead is 80 MB in flight GPU-wide and
     // was evicted before use - ncu showed pass Y reading T1 twice)
     long nu_base = -1;
     int nu_plane = 0;
-    if (g.pf && unit + gridDim.x < nunits) {
-      const long nu = unit + gridDim.x;
-      nu_plane = (int)((nu / nzc) % g.nplane);
-      nu_base = ((long)(nu / ((long)nzc * g.nplane)) * g.ncol * g.n3 + (int)(nu % nzc) * FFT_ZC) * FFT_B;
+    if (g.pf && unit + (int)gridDim.x < nunits) {
+      const int nu = unit + (int)gridDim.x;
+      nu_plane = (nu / nzc) % g.nplane;
+      nu_base = ((long)(nu / (nzc * g.nplane)) * g.ncol * g.n3 + (nu % nzc) * FFT_ZC) * FFT_B;
     }
     __syncthreads();
     const int z1 = min(g.n3, (zc + 1) * FFT_ZC);
@@ -326,16 +350,16 @@ fft_pass_y_kernel(FftGeom g, const double2* __restrict__ T1, double2* __restrict
         if (!last || nu_base >= 0) {
           const double2* nin = last ? T1 + nu_base : T1 + ((long)grp * g.ncol * g.n3 + z + 1) * FFT_B;
           for (int i = tid; i < 2 * g.n2; i += blockDim.x) {
-            const int c = last ? __ldg(g.ysrc + nu_plane * g.n2 + (i >> 1)) : ssrc[i >> 1];
-            if (c >= 0) l2_prefetch_line(reinterpret_cast<const char*>(nin + (long)c * g.n3 * FFT_B) + (i & 1) * 128);
+            const int o = last ? __ldg(g.ysrc + nu_plane * g.n2 + (i >> 1)) * colstride : ssrc[i >> 1];
+            if (o >= 0) l2_prefetch_line(reinterpret_cast<const char*>(nin + o) + (i & 1) * 128);
           }
         }
       }
       if (q < R2) {
         const double2* in = T1 + ((long)grp * g.ncol * g.n3 + z) * FFT_B + b;
         auto load = [&](int row) {
-          const int c = ssrc[row];
-          return c >= 0 ? in[(long)c * g.n3 * FFT_B] : make_double2(0, 0);
+          const int o = ssrc[row];
+          return o >= 0 ? in[o] : make_double2(0, 0);
         };
 #define P1(R) line_phase1<R>(buf, tw, R2, q, b, load)
         PAWB200_RADIX_SWITCH(R1, P1)
@@ -344,8 +368,7 @@ fft_pass_y_kernel(FftGeom g, const double2* __restrict__ T1, double2* __restrict
       __syncthreads();
       if (q < R1) {
         double2* out = T2 + ((((long)grp * g.nplane + p) * g.n2) * g.n3 + z) * FFT_B + b;
-        auto store = [&](int row, double2 v) { out[(long)row * g.n3 * FFT_B] = v; };
-#define P2(R) line_phase2<R>(buf, R1, q, b, store)
+#define P2(R) line_phase2_strided<R>(buf, R1, q, b, out, colstride)
         PAWB200_RADIX_SWITCH(R2, P2)
 #undef P2
       }
@@ -363,42 +386,45 @@ fft_pass_x_kernel(FftGeom g, const double2* __restrict__ T2, double2* __restrict
   int* sxsrc = reinterpret_cast<int*>(tw + g.n1);            // [n1] plane holding each x row (or -1)
   const int tid = threadIdx.x, q = tid / FFT_B, b = tid % FFT_B;
   const int R1 = g.r1[0], R2 = g.r2[0];
+  const long plane = (long)g.n2 * g.n3;
   for (int i = tid; i < g.n1; i += blockDim.x) {
     tw[i] = g.tw[0][i];
-    sxsrc[i] = g.xsrc[i];
+    const int p = g.xsrc[i];
+    sxsrc[i] = p >= 0 ? p * (int)(plane * FFT_B) : -1;     // premultiplied element offset (nplane * plane * 16 < 2^31)
   }
   __syncthreads();
-  const long plane = (long)g.n2 * g.n3;
-  const long nlines = (long)ngroups * plane;
-  int it = 0;
-  for (long line = blockIdx.x; line < nlines; line += gridDim.x, it++) {
-    const long yz = line % plane;
-    const int grp = (int)(line / plane);
+  const int iplane = (int)plane, step = (int)gridDim.x;
+  int grp = (int)blockIdx.x / iplane, yz = (int)blockIdx.x % iplane;       // advanced incrementally: no divisions per line
+  for (int it = 0; grp < ngroups; it++) {
     double2* buf = bufs + (it & 1) * g.n1 * FFT_B;
-    if (g.pf && line + gridDim.x < nlines) {
-      const long nl = line + gridDim.x;
-      const double2* nin = T2 + ((nl / plane) * g.nplane * plane + nl % plane) * FFT_B;
-      for (int i = tid; i < 2 * g.nplane; i += blockDim.x)
-        l2_prefetch_line(reinterpret_cast<const char*>(nin + (long)(i >> 1) * plane * FFT_B) + (i & 1) * 128);
-    }
     if (q < R2) {
       const double2* in = T2 + ((long)grp * g.nplane * plane + yz) * FFT_B + b;
       auto load = [&](int row) {
-        const int p = sxsrc[row];
-        return p >= 0 ? in[(long)p * plane * FFT_B] : make_double2(0, 0);
+        const int o = sxsrc[row];
+        return o >= 0 ? in[o] : make_double2(0, 0);
       };
 #define P1(R) line_phase1<R>(buf, tw, R2, q, b, load)
       PAWB200_RADIX_SWITCH(R1, P1)
 #undef P1
     }
     __syncthreads();
+    // next line of this CTA; its inputs are requested now (phase 1's registers are dead, phase 2 covers the latency)
+    int ngrp = grp, nyz = yz + step;
+    while (nyz >= iplane) { nyz -= iplane; ngrp++; }
+    if (g.pf && ngrp < ngroups) {
+      const double2* nin = T2 + ((long)ngrp * g.nplane * plane + nyz) * FFT_B;
+      for (int i = tid; i < 2 * g.nplane; i += blockDim.x)
+        l2_prefetch_line(reinterpret_cast<const char*>(nin + (i >> 1) * (int)(plane * FFT_B)) + (i & 1) * 128);
+    }
     if (q < R1) {
       double2* out = X + ((long)grp * g.n1 * plane + yz) * FFT_B + b;
-      auto store = [&](int row, double2 v) { out[(long)row * plane * FFT_B] = v; };
-#define P2(R) line_phase2<R>(buf, R1, q, b, store)
+      const int xstride = (int)(plane * FFT_B);                 // n1 * plane * 16 < 2^31 for n <= 400
+#define P2(R) line_phase2_strided<R>(buf, R1, q, b, out, xstride)
       PAWB200_RADIX_SWITCH(R2, P2)
 #undef P2
     }
+    grp = ngrp;
+    yz = nyz;
   }
 }
 

@@ -1,5 +1,6 @@
-"""Host-side timeline of one end-to-end step (config 2): when each API call returns on the host, and when the
-device is done.  Usage on the GPU box: python scripts/e2e_timeline.py [steps]"""
+"""Host-side timeline of one end-to-end step: when each API call returns on the host, and when the device is done.
+Usage on the GPU box: python scripts/e2e_timeline.py [steps] [config=cfg2] [blocks] [host threads]
+(cfg3 with blocks=1 and 2 host threads is what one rank of the 8-GPU job does)."""
 import os
 import sys
 import time
@@ -12,9 +13,11 @@ import bench  # noqa: E402
 from pawpyseed_b200 import _lib, pawpyc  # noqa: E402
 
 L = _lib.lib()
-w = bench.workload("cfg2")
+cfg = sys.argv[2] if len(sys.argv) > 2 else "cfg2"
+blocks = int(sys.argv[3]) if len(sys.argv) > 3 else None
+w = bench.workload(cfg, blocks=blocks)
 imgs = bench.make_images(w, pinned=True)
-L.pawb200_set_host_threads(os.cpu_count())
+L.pawb200_set_host_threads(int(sys.argv[4]) if len(sys.argv) > 4 else os.cpu_count())
 L.pawb200_set_async_ingest(1)
 
 
