@@ -1316,7 +1316,7 @@ void launch_project_il_mt(const SiteTables& T, const double2* X, long ngrid, int
   dim3 grid((nslot + PROJ_NB - 1) / PROJ_NB, (unsigned)T.by_mt[MT].size());
   if (T.ureal.p && T.phk.p) {
     // real tables + phase on the samples: 2 DMMA per k-step and channel tile instead of 4
-    const size_t smem = sphere_project_real_smem<MT>() + (size_t)idx_cap * sizeof(int);
+    const size_t smem = sphere_project_real_smem<MT>();
     static size_t configured_r = 0;
     if (smem > configured_r) {
       CUDA_OK(cudaFuncSetAttribute(sphere_project_real_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -971,22 +971,22 @@ fft_fwd_pass_x_kernel(FftGeom g, const double2* __restrict__ X, double2* __restr
   int* sxsrc = reinterpret_cast<int*>(tw + g.n1);
   const int tid = threadIdx.x, q = tid / FFT_B, b = tid % FFT_B;
   const int R1 = g.r1[0], R2 = g.r2[0];
+  const long plane = (long)g.n2 * g.n3;
+  const int xstride = (int)(plane * FFT_B);                   // 32-bit element offsets: n1 * plane * 16 < 2^31 (n <= 400)
   for (int i = tid; i < g.n1; i += blockDim.x) {
     tw[i] = g.tw[0][i];
-    sxsrc[i] = g.xsrc[i];
+    const int p = g.xsrc[i];
+    sxsrc[i] = p >= 0 ? p * xstride : -1;
   }
   __syncthreads();
-  const long plane = (long)g.n2 * g.n3;
-  const long nlines = (long)ngroups * plane;
-  int it = 0;
-  for (long line = blockIdx.x; line < nlines; line += gridDim.x, it++) {
-    const long yz = line % plane;
-    const int grp = (int)(line / plane);
+  const int iplane = (int)plane, step = (int)gridDim.x;
+  int grp = (int)blockIdx.x / iplane, yz = (int)blockIdx.x % iplane;       // advanced incrementally
+  for (int it = 0; grp < ngroups; it++) {
     double2* buf = bufs + (it & 1) * g.n1 * FFT_B;
     if (q < R2) {
       const double2* in = X + ((long)grp * g.n1 * plane + yz) * FFT_B + b;
       auto load = [&](int row) {
-        const double2 v = in[(long)row * plane * FFT_B];
+        const double2 v = in[row * xstride];
         return make_double2(v.x, -v.y);
       };
 #define P1(R) line_phase1<R>(buf, tw, R2, q, b, load)
@@ -997,13 +997,15 @@ fft_fwd_pass_x_kernel(FftGeom g, const double2* __restrict__ X, double2* __restr
     if (q < R1) {
       double2* out = T2 + ((long)grp * g.nplane * plane + yz) * FFT_B + b;
       auto store = [&](int row, double2 v) {
-        const int p = sxsrc[row];
-        if (p >= 0) out[(long)p * plane * FFT_B] = v;
+        const int o = sxsrc[row];
+        if (o >= 0) out[o] = v;
       };
 #define P2(R) line_phase2<R>(buf, R1, q, b, store)
       PAWB200_RADIX_SWITCH(R2, P2)
 #undef P2
     }
+    yz += step;
+    while (yz >= iplane) { yz -= iplane; grp++; }
   }
 }
 
@@ -1018,21 +1020,25 @@ fft_fwd_pass_y_kernel(FftGeom g, const double2* __restrict__ T2, double2* __rest
   const int R1 = g.r1[1], R2 = g.r2[1];
   for (int i = tid; i < g.n2; i += blockDim.x) tw[i] = g.tw[1][i];
   const int nzc = (g.n3 + FFT_ZC - 1) / FFT_ZC;
-  const long nunits = (long)ngroups * g.nplane * nzc;
+  const int nunits = ngroups * g.nplane * nzc;
+  const int colstride = g.n3 * FFT_B;
   int it = 0;
-  for (long unit = blockIdx.x; unit < nunits; unit += gridDim.x) {
-    const int zc = (int)(unit % nzc);
-    const int p = (int)((unit / nzc) % g.nplane);
-    const int grp = (int)(unit / ((long)nzc * g.nplane));
+  for (int unit = blockIdx.x; unit < nunits; unit += gridDim.x) {
+    const int zc = unit % nzc;
+    const int p = (unit / nzc) % g.nplane;
+    const int grp = unit / (nzc * g.nplane);
     __syncthreads();
-    for (int i = tid; i < g.n2; i += blockDim.x) ssrc[i] = g.ysrc[p * g.n2 + i];
+    for (int i = tid; i < g.n2; i += blockDim.x) {
+      const int c = g.ysrc[p * g.n2 + i];
+      ssrc[i] = c >= 0 ? c * colstride : -1;
+    }
     __syncthreads();
     const int z1 = min(g.n3, (zc + 1) * FFT_ZC);
     for (int z = zc * FFT_ZC; z < z1; z++, it++) {
       double2* buf = bufs + (it & 1) * g.n2 * FFT_B;
       if (q < R2) {
         const double2* in = T2 + ((((long)grp * g.nplane + p) * g.n2) * g.n3 + z) * FFT_B + b;
-        auto load = [&](int row) { return in[(long)row * g.n3 * FFT_B]; };
+        auto load = [&](int row) { return in[row * colstride]; };
 #define P1(R) line_phase1<R>(buf, tw, R2, q, b, load)
         PAWB200_RADIX_SWITCH(R1, P1)
 #undef P1
@@ -1041,8 +1047,8 @@ fft_fwd_pass_y_kernel(FftGeom g, const double2* __restrict__ T2, double2* __rest
       if (q < R1) {
         double2* out = T1 + ((long)grp * g.ncol * g.n3 + z) * FFT_B + b;
         auto store = [&](int row, double2 v) {
-          const int c = ssrc[row];
-          if (c >= 0) out[(long)c * g.n3 * FFT_B] = v;
+          const int o = ssrc[row];
+          if (o >= 0) out[o] = v;
         };
 #define P2(R) line_phase2<R>(buf, R1, q, b, store)
         PAWB200_RADIX_SWITCH(R2, P2)
@@ -1064,15 +1070,14 @@ fft_fwd_pass_z_kernel(FftGeom g, const double2* __restrict__ T1, float2* __restr
   const int R1 = g.r1[2], R2 = g.r2[2], n3 = g.n3;
   for (int i = tid; i < n3; i += blockDim.x) tw[i] = g.tw[2][i];
   __syncthreads();
-  const long nlines = (long)ngroups * g.ncol;
-  int it = 0;
-  for (long line = blockIdx.x; line < nlines; line += gridDim.x, it++) {
-    const int grp = (int)(line / g.ncol), col = (int)(line % g.ncol);
+  const int ncol = g.ncol, step = (int)gridDim.x;
+  int grp = (int)blockIdx.x / ncol, col = (int)blockIdx.x % ncol;
+  for (int it = 0; grp < ngroups; it++) {
     const int4 run = __ldg(g.col_run + col);
     double2* buf = bufs + (it & 1) * n3 * FFT_B;
     if (q < R2) {
       const double2* in = T1 + (((long)grp * g.ncol + col) * n3) * FFT_B + b;
-      auto load = [&](int row) { return in[(long)row * FFT_B]; };
+      auto load = [&](int row) { return in[row * FFT_B]; };
 #define P1(R) line_phase1<R>(buf, tw, R2, q, b, load)
       PAWB200_RADIX_SWITCH(R1, P1)
 #undef P1
@@ -1085,12 +1090,14 @@ fft_fwd_pass_z_kernel(FftGeom g, const double2* __restrict__ T1, float2* __restr
         if (d < 0) d += n3;
         if (d >= run.y) return;
         const int j = d < run.w ? run.y - run.w + d : d - run.w;
-        out[(long)j * FFT_B] = make_float2((float)(v.x * scale), (float)(-v.y * scale));
+        out[j * FFT_B] = make_float2((float)(v.x * scale), (float)(-v.y * scale));
       };
 #define P2(R) line_phase2<R>(buf, R1, q, b, store)
       PAWB200_RADIX_SWITCH(R2, P2)
 #undef P2
     }
+    col += step;
+    while (col >= ncol) { col -= ncol; grp++; }
   }
 }
 

@@ -596,14 +596,19 @@ phase_points_kernel(const double* __restrict__ path, long path_ld, long npts, do
 
 constexpr int PROJ_LDU = PROJ_KT + 4;   // double row stride of the real table tile (rows 0..3 cover all 32 banks)
 
+constexpr int PROJ_RSTAGES = 3;         // real-table kernel: 3 stages and no index list in shared memory -> 3 CTAs/SM
+
 template <int MT>
 inline size_t sphere_project_real_smem() {
-  return (size_t)PROJ_STAGES * (sizeof(double2) * (PROJ_KT * PROJ_LDB + PROJ_KT) + sizeof(double) * 8 * MT * PROJ_LDU);
+  return (size_t)PROJ_RSTAGES * (sizeof(double2) * (PROJ_KT * PROJ_LDB + PROJ_KT) + sizeof(double) * 8 * MT * PROJ_LDU);
 }
 
 // 8 warps per CTA: warps w and w + 4 work on the same 8 slots and split the k-steps of every stage between them
 // (even / odd), so an SM holds twice the warps for the same shared memory - the 4-warp version left the DMMA pipe idle
 // between the dependent issue slots of its two warps per scheduler (ncu r02: "wait" 44 % of the stall samples).
+// The sphere indices a warp needs for a stage (4 of them) are fetched one iteration ahead into a register of lanes
+// 0..3 and broadcast by shuffle, so no index list occupies shared memory: with 3 stages even the 18-channel tile
+// (74.5 KB) fits three times per SM = 24 warps.
 constexpr int PROJ_THREADS = 256;
 
 template <int MT>
@@ -612,21 +617,20 @@ sphere_project_real_kernel(const SiteDev* __restrict__ sites, const int* __restr
                            const int* __restrict__ idx, const double* __restrict__ ureal,
                            const double2* __restrict__ phk, const int* __restrict__ chan_m,
                            const double2* __restrict__ X, long ngrid, int nslot, int ngroups,
-                           double2* __restrict__ P, long ldp, int slot0, int idx_cap) {
+                           double2* __restrict__ P, long ldp, int slot0, int) {
   constexpr int IL = PROJ_IL;
+  constexpr int NS = PROJ_RSTAGES;
   const SiteDev sd = sites[site_list[blockIdx.y]];
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  double2* sB = reinterpret_cast<double2*>(smem_raw);                       // [ST][KT][LDB] samples
-  double2* sPh = sB + PROJ_STAGES * PROJ_KT * PROJ_LDB;                     // [ST][KT]      phase factors
-  double* sU = reinterpret_cast<double*>(sPh + PROJ_STAGES * PROJ_KT);      // [ST][8*MT][LDU] real table rows
-  int* sIdx = reinterpret_cast<int*>(sU + PROJ_STAGES * 8 * MT * PROJ_LDU); // [idx_cap] sphere index list
+  double2* sB = reinterpret_cast<double2*>(smem_raw);                       // [NS][KT][LDB] samples
+  double2* sPh = sB + NS * PROJ_KT * PROJ_LDB;                              // [NS][KT]      phase factors
+  double* sU = reinterpret_cast<double*>(sPh + NS * PROJ_KT);               // [NS][8*MT][LDU] real table rows
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wq = warp & 3;                          // slot octet of this warp
   const int wh = warp >> 2;                         // which half of the k-steps of a stage
   const int sbase = blockIdx.x * PROJ_NB;
   const int nk = sd.npts_pad / PROJ_KT;
-  for (int e = tid; e < sd.npts_pad && e < idx_cap; e += PROJ_THREADS) sIdx[e] = __ldg(idx + sd.pt_off + e);
-  for (int e = tid; e < PROJ_STAGES * 8 * MT * PROJ_LDU; e += PROJ_THREADS) {
+  for (int e = tid; e < NS * 8 * MT * PROJ_LDU; e += PROJ_THREADS) {
     const int row = (e / PROJ_LDU) % (8 * MT);
     if (row >= sd.nlm) sU[e] = 0.0;                 // channel padding rows, never overwritten
   }
@@ -634,14 +638,16 @@ sphere_project_real_kernel(const SiteDev* __restrict__ sites, const int* __restr
   int grp = (sbase + lane) / IL;
   if (grp >= ngroups) grp = ngroups - 1;          // tail CTA: duplicate the last group, discarded on store
   const double2* xsrc = X + (long)grp * ngrid * IL + (lane & (IL - 1));
+  const int* myidx = idx + sd.pt_off + warp + 8 * (lane & 3);               // lane q < 4: point warp + 8 q of a stage
 
-  auto issue = [&](int kt, int st) {
+  // sphere indices of this warp's four points of stage kt (valid in lanes 0..3)
+  auto fetch = [&](int kt) { return kt < nk ? __ldg(myidx + kt * PROJ_KT) : 0; };
+  auto issue = [&](int kt, int st, int gidx) {
     if (kt < nk) {
 #pragma unroll
       for (int q = 0; q < PROJ_KT / 8; q++) {
         const int pt = warp + 8 * q;
-        const int ip = kt * PROJ_KT + pt;
-        const int g = ip < idx_cap ? sIdx[ip] : __ldg(idx + sd.pt_off + ip);   // warp-uniform -> broadcast
+        const int g = __shfl_sync(0xffffffffu, gidx, q);
         cp_async16(sB + (st * PROJ_KT + pt) * PROJ_LDB + lane, xsrc + (long)g * IL);
       }
       // real table tile: nlm rows x 32 points (16 chunks of 16 B per row); a warp covers two rows per pass
@@ -657,12 +663,15 @@ sphere_project_real_kernel(const SiteDev* __restrict__ sites, const int* __restr
 #pragma unroll
   for (int m = 0; m < MT; m++) qr[m][0] = qr[m][1] = qi[m][0] = qi[m][1] = 0;
 #pragma unroll
-  for (int s = 0; s < PROJ_STAGES - 1; s++) issue(s, s);
+  for (int s = 0; s < NS - 1; s++) issue(s, s, fetch(s));
+  int gnext = fetch(NS - 1);                        // indices of the stage issued in iteration 0
   for (int kt = 0; kt < nk; kt++) {
-    cp_async_wait<PROJ_STAGES - 2>();
+    cp_async_wait<NS - 2>();
     __syncthreads();
-    issue(kt + PROJ_STAGES - 1, (kt + PROJ_STAGES - 1) % PROJ_STAGES);
-    const int st = kt % PROJ_STAGES;
+    const int gcur = gnext;
+    gnext = fetch(kt + NS);                         // one iteration ahead of its use
+    issue(kt + NS - 1, (kt + NS - 1) % NS, gcur);
+    const int st = kt % NS;
     const double2* tB = sB + st * PROJ_KT * PROJ_LDB;
     const double2* tP = sPh + st * PROJ_KT;
     const double* tU = sU + st * 8 * MT * PROJ_LDU;

@@ -2,6 +2,7 @@
 
   python scripts/ncu_summary.py launches <launches.csv> <out.md> "<command line>"
   python scripts/ncu_summary.py full <report.ncu-rep> [<report2.ncu-rep> ...] > section.md
+  python scripts/ncu_summary.py raw <report.raw.csv[.gz]> ... > section.md     (csv made on the GPU box by ncu_export.sh)
 
 `launches`: csv log of `ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file ...`.
 `full`: reports of `ncu --set full --clock-control none --import-source on -k regex:... -c N`; read with
@@ -57,9 +58,13 @@ def launches(path, out, cmd):
             f.write("| `%s` | %d | %.1f | %.1f%% |\n" % (k[:100], n, us, 100 * us / tot))
 
 
-def full(reports):
+def full(reports, from_csv=False):
     for rep in reports:
-        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        if from_csv:
+            import gzip
+            raw = (gzip.open(rep, "rt") if rep.endswith(".gz") else open(rep)).read()
+        else:
+            raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
         rows = list(csv.reader(io.StringIO(raw)))
         hdr, units, data = rows[0], rows[1], rows[2:]
         stall = [h for h in hdr if h.startswith("smsp__average_warps_issue_stalled") and h.endswith("per_issue_active.ratio")]
@@ -79,5 +84,7 @@ def full(reports):
 if __name__ == "__main__":
     if sys.argv[1] == "launches":
         launches(sys.argv[2], sys.argv[3], sys.argv[4])
+    elif sys.argv[1] == "raw":
+        full(sys.argv[2:], from_csv=True)
     else:
         full(sys.argv[2:])
