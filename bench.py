@@ -304,17 +304,30 @@ def ref_sample(w, simgs, plan, threads, collect=False, warm=False, timing=True):
         t0 = time.perf_counter()
         pr = rd.RefProjector(S, R, plan["cat"])
         t["overlap_setup"] = time.perf_counter() - t0
-        t0 = time.perf_counter()
-        ps = [S.pseudoprojection(b, R) for b in range(n_pair)]
-        t["pseudo"] = time.perf_counter() - t0
+        # the per-pair dot-product cost carries most of the modelled time and is host-memory-bandwidth bound, so it
+        # varies from run to run (r02: 1.4e-5 .. 2.8e-5 s per pair): repeat the rows and keep the FASTEST pass
+        # (the baseline least favourable to the B200 arm)
+        best, reps, tstart = None, 0, time.perf_counter()
+        while reps == 0 or (timing and reps < 8 and time.perf_counter() - tstart < 0.8):
+            t0 = time.perf_counter()
+            ps = [S.pseudoprojection(b, R) for b in range(n_pair)]
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+            reps += 1
+        t["pseudo"] = best
+        t["pseudo_reps"] = reps
         if timing:
             # per-call overhead of the two per-band entry points (OpenMP fork/join, ctypes), so that it is not
             # charged per pair: pseudoprojection against an 8-band basis, compensation_terms with empty site lists
             T8 = rd.RefWavefunction(simgs[2], kws)
-            t0 = time.perf_counter()
-            for b in range(n_pair):
-                S.pseudoprojection(b, T8)
-            t["pseudo_8band_basis"] = time.perf_counter() - t0
+            best = None
+            for _ in range(3):
+                t0 = time.perf_counter()
+                for b in range(n_pair):
+                    S.pseudoprojection(b, T8)
+                dt = time.perf_counter() - t0
+                best = dt if best is None else min(best, dt)
+            t["pseudo_8band_basis"] = best
             T8.free()
             empty = rd.RefProjector.__new__(rd.RefProjector)
             empty.wf, empty.basis, empty.recip = S, R, False
@@ -325,11 +338,14 @@ def ref_sample(w, simgs, plan, threads, collect=False, warm=False, timing=True):
             t["compensation_no_sites"] = time.perf_counter() - t0
         # compensation_terms is cheap per row on a site subset: time every wf band of the sample, repeated until
         # the timed region is long enough to trust
-        cp, reps, t0 = [], 0, time.perf_counter()
-        while reps == 0 or (timing and time.perf_counter() - t0 < 0.25 and reps < 64):
+        cp, reps, tstart, best = [], 0, time.perf_counter(), None
+        while reps == 0 or (timing and time.perf_counter() - tstart < 0.25 and reps < 64):
+            t0 = time.perf_counter()
             cp = [pr.add_augmentation_terms(np.zeros(nb, np.complex128), b) for b in range(nb)]
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
             reps += 1
-        t["compensation"] = (time.perf_counter() - t0) / reps
+        t["compensation"] = best
         cp = cp[:n_pair]
         if collect:
             nchk = min(nb, 8)

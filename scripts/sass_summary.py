@@ -13,7 +13,7 @@ import sys
 
 so = sys.argv[1] if len(sys.argv) > 1 else "pawpyseed_b200/libpawb200.so"
 txt = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
-cols = ["DMMA", "LDGSTS", "UTMALDG", "UBLKCP", "SYNCS", "DFMA", "DADD", "DMUL", "LDG", "STG", "LDS", "STS", "BAR",
+cols = ["DMMA", "LDGSTS", "UTMALDG", "UBLKCP", "UBLKPF", "CCTL", "SYNCS", "DFMA", "DADD", "DMUL", "LDG", "STG", "LDS", "STS", "BAR",
         "ATOM", "RED", "MEMBAR", "LDL", "STL"]
 kern = collections.OrderedDict()
 cur = None
