@@ -748,12 +748,18 @@ def measure_b200(args, w, rank, world, local, steps, warmup, scaling, e2e_steps)
     if warmup > 0:
         e2e_step()      # one untimed pass: side-stream / staging buffers of the asynchronous path are created here
     barrier()
+    tracing = bool(os.environ.get("PAWB200_TRACE"))
+    if tracing:
+        _lib.timers()       # flushes the device trace of the resident-input phase to stderr
+        sys.stderr.write("==== e2e steps (rank %d)\n" % rank)
     f0, f1 = torch.cuda.Event(True), torch.cuda.Event(True)
     f0.record()
     for _ in range(e2e_steps):
         e2e_step()
     f1.record()
     barrier()
+    if tracing:
+        _lib.timers()
     ms2 = torch.tensor([f0.elapsed_time(f1)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(ms2, op=dist.ReduceOp.MAX)

@@ -801,6 +801,74 @@ void box_order(KPointInfo& kp) {
 void interleave_rows(pawb200_pswf* wf, int kap, int band_lo, int band_hi, cudaStream_t st);
 void alloc_interleaved(pawb200_pswf* wf, int kap, cudaStream_t st);
 
+// One band chunk of one (k,spin) block on its way to the device: raw records -> staging slot (copy stream) ->
+// box-ordered rows + interleaved copy (unpack stream) -> `ready` event in wf->chunks.
+struct ChunkJob {
+  pawb200_pswf* wf;
+  int kap, b0, nb, per;
+  long ld, nrecl;
+  int nplane, half_len;
+  const unsigned char* from;        // first record of the block (host memory that outlives the copy)
+};
+// Asynchronous ingest from caller-owned memory issues only the FIRST block of a wavefunction at read time and defers
+// the others until some consumer asks for coefficients (wait_coeffs): by then the second wavefunction of a pair has
+// usually been read as well, and the deferred chunks of both are issued in (k,spin)-block order - basis block 1, wf
+// block 1, basis block 2, ... - so the pseudo GEMM of block k can start when 2(k+1) blocks have crossed the link
+// instead of waiting for every block of the basis first (e2e of the 8-block job on 2 GPUs: 968 -> see DESIGN 5).
+std::vector<ChunkJob> g_pending_chunks;
+
+void issue_chunk(const ChunkJob& j) {
+  IngestRing& ring = ingest_ring();
+  pawb200_pswf* wf = j.wf;
+  IngestRing::Slot& sl = ring.slots[ring.next++ % 3];
+  const size_t raw_bytes = (size_t)j.per * j.ld * sizeof(float2);
+  if (raw_bytes > sl.bytes) {
+    CUDA_OK(cudaStreamSynchronize(ring.copy));
+    CUDA_OK(cudaStreamSynchronize(ring.unpack));
+    if (sl.p) cudaFree(sl.p);
+    CUDA_OK(cudaMalloc(&sl.p, raw_bytes));
+    sl.bytes = raw_bytes;
+  }
+  CUDA_OK(cudaStreamWaitEvent(ring.copy, sl.free, 0));     // the slot's previous contents were unpacked
+  trace_mark("h2d chunk start k=" + std::to_string(j.kap) + " b0=" + std::to_string(j.b0), ring.copy);
+  {
+    ScopedStage tm(ST_H2D, ring.copy);
+    CUDA_OK(cudaMemcpy2DAsync(sl.p, j.ld * sizeof(float2), j.from + (size_t)j.b0 * j.nrecl, j.nrecl,
+                              (size_t)j.nplane * sizeof(float2), j.nb, cudaMemcpyHostToDevice, ring.copy));
+  }
+  CUDA_OK(cudaEventRecord(sl.filled, ring.copy));
+  trace_mark("h2d chunk done k=" + std::to_string(j.kap) + " b0=" + std::to_string(j.b0), ring.copy);
+  CUDA_OK(cudaStreamWaitEvent(ring.unpack, sl.filled, 0));
+  dim3 grid((j.half_len + 255) / 256, std::min(j.nb, 64));
+  permute_coeff_kernel<<<grid, 256, 0, ring.unpack>>>((const float2*)sl.p, wf->C[j.kap].as<float2>() + (long)j.b0 * j.ld,
+                                                   j.ld, j.nb, wf->ncl ? 2 : 1, j.half_len,
+                                                   wf->perm_dev[j.kap].as<int>());
+  count_launch();
+  check_launch();
+  interleave_rows(wf, j.kap, j.b0, j.b0 + j.nb, ring.unpack);
+  CUDA_OK(cudaEventRecord(sl.free, ring.unpack));
+  trace_mark("unpack done k=" + std::to_string(j.kap) + " b0=" + std::to_string(j.b0), ring.unpack);
+  pawb200_pswf::Chunk ck{j.kap, j.b0, j.b0 + j.nb, nullptr};
+  CUDA_OK(cudaEventCreateWithFlags(&ck.ready, cudaEventDisableTiming));
+  CUDA_OK(cudaEventRecord(ck.ready, ring.unpack));
+  wf->chunks.push_back(ck);
+}
+
+// Issue every deferred chunk, lowest (k,spin) block first, wavefunctions in the order they were read.
+void flush_pending_ingest() {
+  if (g_pending_chunks.empty()) return;
+  std::vector<ChunkJob> jobs;
+  jobs.swap(g_pending_chunks);
+  std::stable_sort(jobs.begin(), jobs.end(), [](const ChunkJob& a, const ChunkJob& b) { return a.kap < b.kap; });
+  for (auto& j : jobs) issue_chunk(j);
+}
+
+void drop_pending_ingest(const pawb200_pswf* wf) {
+  g_pending_chunks.erase(std::remove_if(g_pending_chunks.begin(), g_pending_chunks.end(),
+                                        [wf](const ChunkJob& j) { return j.wf == wf; }),
+                         g_pending_chunks.end());
+}
+
 pawb200_pswf* ingest(ByteSource src, const double* kws) {
   HostSection hs_("ingest");
   require_device();
@@ -844,6 +912,7 @@ pawb200_pswf* ingest(ByteSource src, const double* kws) {
   unsigned char* stage = nullptr;
   size_t stage_bytes = 0;
   IngestRing& ring = ingest_ring();
+  bool first_block = true;
   for (int kap = 0; kap < NK; kap++) {
     const long base = 2 + (long)kap * (1 + hd.nband);
     const size_t hdr_doubles = std::min<size_t>(hd.nrecl / 8, 4 + 3 * (size_t)hd.nband);
@@ -908,40 +977,14 @@ pawb200_pswf* ingest(ByteSource src, const double* kws) {
       // whole GEMM row tiles (64) per chunk when there are enough bands, else whole interleave groups (16)
       const int gran = nown >= 256 ? 64 : 16;
       const int per = ((nown + nchunk - 1) / nchunk + gran - 1) / gran * gran;
+      // asynchronous ingest from memory: the first resident block goes out now, the others when a consumer asks
+      const bool defer = g_async_ingest && src.mem && !first_block;
+      first_block = false;
       for (int b0 = wf->band_lo; b0 < wf->band_hi; b0 += per) {
         const int nb = std::min(per, wf->band_hi - b0);
-        IngestRing::Slot& sl = ring.slots[ring.next++ % 3];
-        const size_t raw_bytes = (size_t)per * ld * sizeof(float2);
-        if (raw_bytes > sl.bytes) {
-          CUDA_OK(cudaStreamSynchronize(ring.copy));
-          CUDA_OK(cudaStreamSynchronize(ring.unpack));
-          if (sl.p) cudaFree(sl.p);
-          CUDA_OK(cudaMalloc(&sl.p, raw_bytes));
-          sl.bytes = raw_bytes;
-        }
-        CUDA_OK(cudaStreamWaitEvent(ring.copy, sl.free, 0));     // the slot's previous contents were unpacked
-        trace_mark("h2d chunk start b0=" + std::to_string(b0), ring.copy);
-        {
-          ScopedStage tm(ST_H2D, ring.copy);
-          CUDA_OK(cudaMemcpy2DAsync(sl.p, ld * sizeof(float2), from + (size_t)b0 * hd.nrecl, hd.nrecl,
-                                    (size_t)kp.nplane * sizeof(float2), nb, cudaMemcpyHostToDevice, ring.copy));
-        }
-        CUDA_OK(cudaEventRecord(sl.filled, ring.copy));
-        trace_mark("h2d chunk done b0=" + std::to_string(b0), ring.copy);
-        CUDA_OK(cudaStreamWaitEvent(ring.unpack, sl.filled, 0));
-        dim3 grid((half_len + 255) / 256, std::min(nb, 64));
-        permute_coeff_kernel<<<grid, 256, 0, ring.unpack>>>((const float2*)sl.p, wf->C[kap].as<float2>() + (long)b0 * ld,
-                                                         ld, nb, wf->ncl ? 2 : 1, half_len,
-                                                         wf->perm_dev[kap].as<int>());
-        count_launch();
-        check_launch();
-        interleave_rows(wf.get(), kap, b0, b0 + nb, ring.unpack);
-        CUDA_OK(cudaEventRecord(sl.free, ring.unpack));
-        trace_mark("unpack done b0=" + std::to_string(b0), ring.unpack);
-        pawb200_pswf::Chunk ck{kap, b0, b0 + nb, nullptr};
-        CUDA_OK(cudaEventCreateWithFlags(&ck.ready, cudaEventDisableTiming));
-        CUDA_OK(cudaEventRecord(ck.ready, ring.unpack));
-        wf->chunks.push_back(ck);
+        ChunkJob job{wf.get(), kap, b0, nb, per, ld, hd.nrecl, kp.nplane, half_len, from};
+        if (defer) g_pending_chunks.push_back(job);
+        else issue_chunk(job);
       }
     }
   }
@@ -954,6 +997,7 @@ pawb200_pswf* ingest(ByteSource src, const double* kws) {
 
 // Make the main stream wait until the coefficient rows of bands [band_lo, band_hi) of `kap` have landed.
 void wait_coeffs(const pawb200_pswf* wf, int kap, int band_lo, int band_hi, cudaStream_t st = nullptr) {
+  flush_pending_ingest();             // deferred chunks (of every wavefunction) are issued before anybody waits
   for (auto& c : wf->chunks)
     if (c.kap == kap && c.band_lo < band_hi && c.band_hi > band_lo)
       CUDA_OK(cudaStreamWaitEvent(st ? st : g_stream, c.ready, 0));
@@ -1638,6 +1682,7 @@ void check_pair(const pawb200_pswf* S, const pawb200_pswf* R) {
 bool coeffs_in_flight(const pawb200_pswf* wf, int kap) {
   static const bool force = getenv("PAWB200_GEMM_CHUNKED") != nullptr;   // tests: take the chunked path always
   if (force) return true;
+  flush_pending_ingest();
   for (auto& c : wf->chunks)
     if (c.kap == kap && cudaEventQuery(c.ready) == cudaErrorNotReady) return true;
   return false;
@@ -1852,6 +1897,72 @@ void recip_block(pawb200_pswf* S, pawb200_pswf* R, const SiteLists& L, int kap, 
   }
 }
 
+// ---- pseudo GEMMs launched ahead of the projection work (asynchronous ingest) ---------------------------------
+// While coefficients are still crossing the host link the main stream sits behind transforms that wait for data,
+// and anything queued after them - the pseudo GEMMs of overlap_matrix - cannot start before the last block has been
+// projected (r02 trace, 4 blocks per rank: first GEMM at 455 ms of a 993 ms step).  The pseudo overlap needs nothing
+// but coefficients, so overlap_setup_real - the first call that sees both wavefunctions - queues the GEMM of every
+// resident block on the GEMM stream right away, per ingest chunk, into library-owned blocks; overlap_matrix later
+// joins, copies the block (64 MB device to device) and adds the augmentation onto it.
+struct PrelaunchedPseudo {
+  uint64_t s_id = 0, r_id = 0;
+  int nS = 0, nR = 0;
+  std::vector<int> slot_of_kap;               // -1: not prelaunched
+};
+PrelaunchedPseudo g_pre;
+std::vector<RawBuf> g_pre_blk;                // block buffers, kept across wavefunction pairs
+std::vector<cudaEvent_t> g_pre_done, g_pre_used;
+
+bool any_coeffs_in_flight(const pawb200_pswf* wf) {
+  for (auto& j : g_pending_chunks)
+    if (j.wf == wf) return true;
+  for (auto& c : wf->chunks)
+    if (cudaEventQuery(c.ready) == cudaErrorNotReady) return true;
+  return false;
+}
+
+void prelaunch_pseudo(pawb200_pswf* S, pawb200_pswf* R) {
+  g_pre = PrelaunchedPseudo();
+  static const bool off = getenv("PAWB200_PRELAUNCH") && atoi(getenv("PAWB200_PRELAUNCH")) == 0;
+  if (off || S->ncl || R->ncl || S->band_sharded() || R->band_sharded()) return;
+  if (!any_coeffs_in_flight(S) && !any_coeffs_in_flight(R)) return;      // resident inputs: nothing to gain
+  const int NK = S->nkappa();
+  const size_t blk_bytes = (size_t)S->nband * R->nband * sizeof(double2);
+  g_pre.s_id = S->id; g_pre.r_id = R->id; g_pre.nS = S->nband; g_pre.nR = R->nband;
+  g_pre.slot_of_kap.assign(NK, -1);
+  cudaStream_t st2 = gemm_stream();
+  int slot = 0;
+  for (int kap = 0; kap < NK; kap++) {
+    if (!S->resident[kap] || !R->resident[kap] || S->kp[kap].nplane != R->kp[kap].nplane) continue;
+    if ((int)g_pre_blk.size() <= slot) {
+      g_pre_blk.emplace_back();
+      cudaEvent_t a, b;
+      CUDA_OK(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+      CUDA_OK(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+      g_pre_done.push_back(a);
+      g_pre_used.push_back(b);
+    }
+    g_pre_blk[slot].ensure(blk_bytes);
+    CUDA_OK(cudaStreamWaitEvent(st2, g_pre_used[slot], 0));       // the previous pair's consumer of this buffer
+    pseudo_block(S, R, kap, 0, (double2*)g_pre_blk[slot].p, R->nband, st2, true);
+    CUDA_OK(cudaEventRecord(g_pre_done[slot], st2));
+    g_pre.slot_of_kap[kap] = slot++;
+  }
+}
+
+// the prelaunched pseudo block of (S, R, kap) copied into b on the main stream; false if there is none
+bool take_prelaunched(const pawb200_pswf* S, const pawb200_pswf* R, int kap, int flip, double2* b) {
+  if (flip || g_pre.s_id != S->id || g_pre.r_id != R->id || g_pre.nS != S->nband || g_pre.nR != R->nband) return false;
+  if (kap >= (int)g_pre.slot_of_kap.size() || g_pre.slot_of_kap[kap] < 0) return false;
+  const int slot = g_pre.slot_of_kap[kap];
+  const size_t blk_bytes = (size_t)S->nband * R->nband * sizeof(double2);
+  CUDA_OK(cudaStreamWaitEvent(g_stream, g_pre_done[slot], 0));
+  CUDA_OK(cudaMemcpyAsync(b, g_pre_blk[slot].p, blk_bytes, cudaMemcpyDeviceToDevice, g_stream));
+  CUDA_OK(cudaEventRecord(g_pre_used[slot], g_stream));
+  g_pre.slot_of_kap[kap] = -1;                                   // one use: the GEMM stream may refill the buffer
+  return true;
+}
+
 // dev_out: `out` is DEVICE memory [hi - lo][nbS][nbR]; the blocks are computed in place on the main stream and
 // nothing is copied or synchronised (the caller orders its own work after the main stream).
 void overlap_matrix(pawb200_pswf* S, pawb200_pswf* R, const SiteLists* L, int flip, int lo, int hi,
@@ -1879,6 +1990,21 @@ void overlap_matrix(pawb200_pswf* S, pawb200_pswf* R, const SiteLists* L, int fl
       continue;
     }
     double2* b;
+    if (pseudo && g_pre.s_id == S->id && kap < (int)g_pre.slot_of_kap.size() && g_pre.slot_of_kap[kap] >= 0) {
+      // the pseudo GEMM of this block was queued by overlap_setup_real (prelaunch_pseudo): join, copy, augment
+      DevBuf own;
+      if (dev_out) b = (double2*)dst;
+      else { own.alloc(blk_bytes); b = own.as<double2>(); }
+      if (take_prelaunched(S, R, kap, flip, b)) {
+        if (aug) aug_block(S, R, A, kap, flip, b, nR, true);
+        if (aug && recip) recip_block(S, R, *L, kap, flip, b, nR);
+        if (dev_out) continue;
+        ScopedStage tm(ST_D2H);
+        CUDA_OK(cudaMemcpyAsync(dst, b, blk_bytes, cudaMemcpyDeviceToHost, g_stream));
+        trace_mark("d2h block done", g_stream);
+        continue;
+      }
+    }
     if (side) {
       // pseudo block on the GEMM stream into a dedicated buffer (or the caller's device block); the main stream
       // joins before it adds the augmentation GEMM and copies the block out
@@ -2249,6 +2375,7 @@ pawb200_pswf_t* pawb200_read_wavefunctions_from_str(const char* start, const dou
 
 void pawb200_free_pswf(pawb200_pswf_t* wf) {
   if (!wf) return;
+  drop_pending_ingest(wf);            // deferred chunks that nobody asked for
   cudaStreamSynchronize(ingest_ring().copy);
   cudaStreamSynchronize(ingest_ring().unpack);
   if (g_stream2) cudaStreamSynchronize(g_stream2);
@@ -2604,6 +2731,7 @@ void pawb200_overlap_setup_real(pawb200_pswf_t* wf_R, pawb200_pswf_t* wf_S, cons
   wf_R->gen++;
   wf_S->gen++;
   wf_R->aug_cache.valid = wf_S->aug_cache.valid = false;
+  prelaunch_pseudo(wf_S, wf_R);        // asynchronous ingest: the pseudo GEMMs go out before the projection work
   wf_R->W.clear(); wf_S->W.clear();
   wf_R->wp_num = num_N_S; wf_S->wp_num = num_N_R;
   wf_R->wp_nlm.clear(); wf_S->wp_nlm.clear();
@@ -3210,6 +3338,10 @@ void pawb200_set_kappa_range(pawb200_pswf_t* wf, int lo, int hi) {
   bool any = false;
   for (int k = 0; k < wf->nkappa(); k++) any = any || ((k < lo || k >= hi) && wf->resident[k]);
   if (!any) return;
+  // deferred ingest chunks of the dropped blocks must never be issued (their buffers are about to be released)
+  g_pending_chunks.erase(std::remove_if(g_pending_chunks.begin(), g_pending_chunks.end(),
+                                        [&](const ChunkJob& j) { return j.wf == wf && (j.kap < lo || j.kap >= hi); }),
+                         g_pending_chunks.end());
   cudaStreamSynchronize(ingest_ring().copy);
   cudaStreamSynchronize(ingest_ring().unpack);
   if (g_stream2) cudaStreamSynchronize(g_stream2);
