@@ -221,27 +221,49 @@ void sync_arena_users() {
   CUDA_OK(cudaStreamSynchronize(g_stream));
   if (g_unpack_stream) CUDA_OK(cudaStreamSynchronize(g_unpack_stream));
 }
+// Two halves used alternately: when one fills up the arena moves to the other and only waits for the device work that
+// was queued when THAT half was left (an event per consuming stream) - normally long finished.  r02: the single
+// region of r01 synchronised the main stream on every wrap, which stalls the host for as long as queued transforms
+// wait for coefficients that are still crossing the host link (traced at 4 GPUs: 37 ms per build_site_tables call).
 struct PinnedArena {
   unsigned char* base = nullptr;
-  size_t cap = 0, used = 0;
+  size_t cap = 0, used = 0;          // cap: bytes per half
+  int cur = 0;
+  cudaEvent_t left_main[2] = {nullptr, nullptr}, left_unpack[2] = {nullptr, nullptr};
+  bool left_valid[2] = {false, false};
   void* take(size_t n) {
     n = (n + 255) / 256 * 256;
     if (n > cap) {   // grow: everything in flight must land first
       sync_arena_users();
       if (base) cudaFreeHost(base);
       cap = std::max<size_t>(n * 2, (size_t)64 << 20);
-      CUDA_OK(cudaMallocHost((void**)&base, cap));
+      CUDA_OK(cudaMallocHost((void**)&base, 2 * cap));
       used = 0;
+      cur = 0;
+      left_valid[0] = left_valid[1] = false;
     }
     if (used + n > cap) {
-      sync_arena_users();
+      if (!left_main[0])
+        for (int i = 0; i < 2; i++) {
+          CUDA_OK(cudaEventCreateWithFlags(&left_main[i], cudaEventDisableTiming));
+          CUDA_OK(cudaEventCreateWithFlags(&left_unpack[i], cudaEventDisableTiming));
+        }
+      CUDA_OK(cudaEventRecord(left_main[cur], g_stream));
+      if (g_unpack_stream) CUDA_OK(cudaEventRecord(left_unpack[cur], g_unpack_stream));
+      left_valid[cur] = true;
+      cur ^= 1;
+      if (left_valid[cur]) {          // readers of the half we are about to overwrite
+        CUDA_OK(cudaEventSynchronize(left_main[cur]));
+        if (g_unpack_stream) CUDA_OK(cudaEventSynchronize(left_unpack[cur]));
+        left_valid[cur] = false;
+      }
       used = 0;
     }
-    void* p = base + used;
+    void* p = base + (size_t)cur * cap + used;
     used += n;
     return p;
   }
-  void reset_after_sync() { used = 0; }
+  void reset_after_sync() { used = 0; left_valid[0] = left_valid[1] = false; }
 };
 PinnedArena g_arena;
 
@@ -926,13 +948,18 @@ pawb200_pswf* ingest(ByteSource src, const double* kws) {
     wf->weight[kap] = kws ? kws[kap % hd.nwk] : 1.0;
     const bool same_k = kap >= hd.nwk && kp.k[0] == wf->kp[kap - hd.nwk].k[0] &&
                         kp.k[1] == wf->kp[kap - hd.nwk].k[1] && kp.k[2] == wf->kp[kap - hd.nwk].k[2];
-    if (same_k) {   // second spin channel: same k, same list
+    const bool mine = kap % g_shard_world == g_shard_rank;
+    if (same_k && !wf->kp[kap - hd.nwk].G.empty()) {   // second spin channel: same k, same list
       kp.G = wf->kp[kap - hd.nwk].G;
       kp.perm = wf->kp[kap - hd.nwk].perm;
       kp.pos = wf->kp[kap - hd.nwk].pos;
-    } else {
+    } else if (mine) {
       kp.G = enumerate_g(hd, kp.k, wf->G_bounds);
       box_order(kp);
+    } else {
+      // sharded read, another rank's block: its plane-wave list is never used here (5-7 ms of host work per k-point
+      // that delayed the first H2D chunk of ranks whose own block comes late in the file)
+      continue;
     }
     const int ng = (int)(kp.G.size() / 3);
     if (2 * ng == kp.nplane) {
@@ -944,7 +971,7 @@ pawb200_pswf* ingest(ByteSource src, const double* kws) {
                                " stored (gamma-only WAVECARs are unsupported, as in the reference)");
     }
     if ((long)kp.nplane * 8 > hd.nrecl) throw std::runtime_error("record shorter than nplane");
-    if (kap % g_shard_world != g_shard_rank) continue;   // sharded ingest: not this rank's block
+    if (!mine) continue;   // sharded ingest: not this rank's block
     wf->resident[kap] = 1;
     const long ld = ((long)kp.nplane + 31) / 32 * 32;
     wf->ldc[kap] = ld;
@@ -987,6 +1014,13 @@ pawb200_pswf* ingest(ByteSource src, const double* kws) {
         else issue_chunk(job);
       }
     }
+  }
+  // A second wavefunction has been read while chunks of an earlier one are still deferred: this is the pair case,
+  // and from here on the copy engine should never idle - issue everything that is pending, in block order.
+  {
+    bool others = false;
+    for (auto& j : g_pending_chunks) others = others || j.wf != wf.get();
+    if (others) flush_pending_ingest();
   }
   // Unless the caller promised to keep its buffer alive (async ingest), wait for the copies - but not for
   // any compute - before returning
