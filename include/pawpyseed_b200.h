@@ -250,7 +250,10 @@ void *pawb200_get_device_buffer(pawb200_pswf_t *wf, int which, int kappa, long *
 /* With on != 0, pawb200_read_wavefunctions_from_str returns while the host->device copies are still in
  * flight: the CALLER MUST KEEP THE BUFFER ALIVE AND UNMODIFIED until the wavefunction has been used in a call
  * that returns results (or is freed). Later launches wait per band chunk, so the transfer overlaps the
- * transforms. Default off (the copy is complete on return, like the reference reader). */
+ * transforms. Only the first (k,spin) block is queued at read time; the copies of the other blocks are queued when a
+ * second wavefunction is read or a consumer asks for coefficients, in block order across the wavefunctions, and
+ * pawb200_overlap_setup_real queues the pseudo-overlap GEMMs of the pair on their own stream ahead of the projection
+ * work. Default off (the copy is complete on return, like the reference reader). */
 void pawb200_set_async_ingest(int on);
 /* OpenMP threads for the host-side setup (sphere geometry, NumSBT); launchers such as torchrun export
  * OMP_NUM_THREADS=1, which would serialise it. */

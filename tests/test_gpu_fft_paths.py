@@ -123,9 +123,37 @@ def test_sharded_and_async_ingest():
     assert rel(full, want) < TOL
 
 
+def test_async_pair_block_ordered_ingest_matches_oracle():
+    """Two different wavefunctions read asynchronously: each issues its first (k,spin) block at read time, the other
+    three are deferred and go out in block order across both when the second one is read (flush_pending_ingest);
+    the PAW-corrected matrix equals the oracle's, and a second projector on the same pair (nothing pending, nothing
+    prelaunched) gives bit-identical numbers."""
+    cR, cS = cases.small_case(seed=31, nband=12), cases.small_case(seed=32, nband=12, perturb=0.02)
+    oR, oS = oracle(cR), oracle(cS)
+    cat = [[0, 1], [0, 1], [2, 3], [2, 3], [2, 3], [2, 3]]
+    L = _lib.lib()
+    try:
+        L.pawb200_set_async_ingest(1)       # the images stay alive in cR / cS
+        R, S = gpu(cR), gpu(cS)
+        pr = pawpyc.CProjector(S, R)
+        pr._setup_overlap(cat, False)
+        got = pr._projection_matrix()
+        pr2 = pawpyc.CProjector(S, R)
+        pr2._setup_overlap(cat, False)
+        again = pr2._projection_matrix()
+    finally:
+        L.pawb200_set_async_ingest(0)
+    want = np.array([pn.Projector(oS, oR, cat).single_band_projection(b) for b in range(12)])
+    assert rel(got, want.reshape(12, 12, 4).transpose(2, 0, 1)) < TOL
+    assert np.array_equal(got, again)
+
+
 def test_chunked_side_stream_gemm_matches_single_gemm(tmp_path):
     """While wf coefficients are still arriving the pseudo-overlap GEMM runs per ingest chunk on its own stream
-    (PAWB200_GEMM_CHUNKED=1 forces that path): 300 bands = five 64-band chunks; same matrix as the one-shot GEMM."""
+    (PAWB200_GEMM_CHUNKED=1 forces that path): 300 bands = five 64-band chunks; same matrix as the one-shot GEMM.
+    Both runs ingest asynchronously, so the second (k,spin) block of each wavefunction is a deferred, block-ordered
+    copy; the forced run also takes the prelaunch path (overlap_setup_real queues the GEMMs of both blocks on the GEMM
+    stream, overlap_matrix joins and adds the augmentation)."""
     code = (
         "import sys, numpy as np; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
         "import cases; from pawpyseed_b200 import pawpyc, _lib\n"
