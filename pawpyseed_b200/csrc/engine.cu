@@ -1212,14 +1212,36 @@ bool factor_pair(int n, int& r1, int& r2) {
   return found;
 }
 
+// n = a * b * c with radices <= 10, as balanced as possible (smallest largest factor); the largest factor goes first
+// (phase 1 has the most tasks per thread otherwise)
+bool factor_triple(int n, int& r1, int& r2, int& r3) {
+  if (n > 420) return false;            // two exchange buffers of n x 256 B must fit the shared memory of an SM
+  int best = 1 << 30;
+  bool found = false;
+  for (int a = 2; a <= 10; a++)
+    for (int b = 2; b <= a; b++)
+      for (int c = 2; c <= b; c++)
+        if (a * b * c == n && a < best) {
+          best = a;
+          r1 = a; r2 = b; r3 = c;
+          found = true;
+        }
+  return found;
+}
+
 std::shared_ptr<PrunedPlan> build_pruned_plan_kp(const KPointInfo& kp, int npw, const int* fftg) {
   auto P = std::make_shared<PrunedPlan>();
   if (getenv("PAWB200_FFT") && std::string(getenv("PAWB200_FFT")) == "cufft") return P;
   FftGeom& g = P->g;
   g.n1 = fftg[0]; g.n2 = fftg[1]; g.n3 = fftg[2];
   g.pf = getenv("PAWB200_FFT_PF") ? atoi(getenv("PAWB200_FFT_PF")) : 1;
-  for (int d = 0; d < 3; d++)
-    if (!factor_pair(fftg[d], g.r1[d], g.r2[d])) return P;
+  for (int d = 0; d < 3; d++) {
+    g.r3[d] = 1;
+    if (factor_pair(fftg[d], g.r1[d], g.r2[d])) continue;
+    if (getenv("PAWB200_FFT3") && atoi(getenv("PAWB200_FFT3")) == 0) return P;
+    if (!factor_triple(fftg[d], g.r1[d], g.r2[d], g.r3[d])) return P;
+    g.three = 1;
+  }
   if (npw == 0) return P;
   std::vector<int> col_start, col_cnt, col_ypos, zpos(npw), plane_col0, plane_ncol, plane_xpos;
   int last1 = -1, last2 = -1, lastz = -1;
@@ -1308,6 +1330,7 @@ std::shared_ptr<PrunedPlan> build_pruned_plan_kp(const KPointInfo& kp, int npw, 
     g.tw[d] = P->tw[d].as<double2>();
   }
   init_small_twiddles();
+  if (g.three && !g.col_run) return P;      // the three-factor pass Z has no staged variant
   P->ok = true;
   return P;
 }
@@ -2674,7 +2697,7 @@ void compute_aug_freqs(pawb200_pswf* wf, const int* site_list, int nlist, const 
     double kc[3] = {wf->kp[kap].k[0], wf->kp[kap].k[1], wf->kp[kap].k[2]};
     frac_to_cart(kc, wf->reclattice);                                           // projector.c:288-292
     std::shared_ptr<PrunedPlan> plan = get_pruned_plan(wf, kap, fftg);
-    const bool pruned = plan->ok && plan->g.col_run && !getenv("PAWB200_DENSITY_GENERIC");
+    const bool pruned = plan->ok && plan->g.col_run && !plan->g.three && !getenv("PAWB200_DENSITY_GENERIC");
     // one site per launch, no atomics: sums over overlapping spheres are formed in site order (deterministic)
     auto add_sites = [&](double2* x, int b_first, int nbx, int interleaved) {
       for (int c0 = 0; c0 < nbx && T->total_pts; c0 += NBMAX) {
@@ -3260,7 +3283,7 @@ void pawb200_fwd_fft3d(pawb200_c128* x, const int*, const double* lattice, const
   {
     KPointInfo kp;
     std::shared_ptr<PrunedPlan> plan = plan_for_g_list(Gs, num_waves, fftg, kp);
-    if (plan->ok && plan->g.col_run) {
+    if (plan->ok && plan->g.col_run && !plan->g.three) {
       // forward transform pruned on the output side (fft_fwd_pass_*): the box goes into slot 0 of an interleave group
       const FftGeom& g = plan->g;
       ensure_group_scratch(g);

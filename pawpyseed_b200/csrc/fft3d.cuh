@@ -428,6 +428,158 @@ fft_pass_x_kernel(FftGeom g, const double2* __restrict__ T2, double2* __restrict
   }
 }
 
+// ---- three-factor lines: n = R1 * R2 * R3 (radices <= 10) -----------------------------------------------------
+// Line lengths without a two-factor split into radices <= 20 (175 = 5*5*7, 243 = 3*9*9, 384 = 6*8*8, ...):
+//   j = j1*M + j2*R3 + j3 (M = R2*R3),   k = k1 + R1*(k2 + R2*k3)
+//   phase 1, task m < M:        R1-point DFT over j1, twiddle w_n^(m k1)        -> A[k1*M + m]
+//   phase 2, task (k1, j3):     R2-point DFT over j2, twiddle w_n^(R1 j3 k2)    -> B[k1*M + k2*R3 + j3]
+//   phase 3, task (k1, k2):     R3-point DFT over j3                            -> X[k1 + R1*(k2 + R2*k3)]
+// Thread = (q, band) as in the two-factor passes; a thread loops over the tasks q, q + Q, ... of a phase.  Two
+// exchange buffers A and B and two barriers per line: the next line's phase 1 only writes A, which nobody reads
+// after the second barrier, and its phase 2 (the next writer of B) comes after a barrier every thread reaches only
+// when it has finished reading B.
+constexpr int FFT3_RMAX = 10;
+
+template <class Load, class Store>
+__device__ __forceinline__ void line3_transform(double2* __restrict__ A, double2* __restrict__ B,
+                                                const double2* __restrict__ tw, int R1, int R2, int R3, int q, int Q,
+                                                int b, Load load, Store store) {
+  constexpr int RMAX = FFT3_RMAX;
+  const int M = R2 * R3;
+  for (int m = q; m < M; m += Q) {
+#define T1(R)                                                        \
+  {                                                                  \
+    double2 v[R];                                                    \
+    _Pragma("unroll") for (int j1 = 0; j1 < R; j1++) v[j1] = load(j1 * M + m); \
+    SmallDFT<R, 1>::run(v);                                          \
+    _Pragma("unroll") for (int k1 = 0; k1 < R; k1++) {               \
+      double2 x = v[k1];                                             \
+      if (k1 > 0) x = cmulf(x, tw[m * k1]);                          \
+      A[(k1 * M + m) * FFT_B + b] = x;                               \
+    }                                                                \
+  }
+    PAWB200_RADIX_SWITCH(R1, T1)
+#undef T1
+  }
+  __syncthreads();
+  for (int t = q; t < R1 * R3; t += Q) {
+    const int k1 = t / R3, j3 = t - k1 * R3;
+#define T2(R)                                                        \
+  {                                                                  \
+    double2 v[R];                                                    \
+    _Pragma("unroll") for (int j2 = 0; j2 < R; j2++) v[j2] = A[(k1 * M + j2 * R3 + j3) * FFT_B + b]; \
+    SmallDFT<R, 1>::run(v);                                          \
+    _Pragma("unroll") for (int k2 = 0; k2 < R; k2++) {               \
+      double2 x = v[k2];                                             \
+      if (k2 > 0) x = cmulf(x, tw[R1 * j3 * k2]);                    \
+      B[(k1 * M + k2 * R3 + j3) * FFT_B + b] = x;                    \
+    }                                                                \
+  }
+    PAWB200_RADIX_SWITCH(R2, T2)
+#undef T2
+  }
+  __syncthreads();
+  for (int t = q; t < R1 * R2; t += Q) {
+    const int k1 = t / R2, k2 = t - k1 * R2;
+#define T3(R)                                                        \
+  {                                                                  \
+    double2 v[R];                                                    \
+    _Pragma("unroll") for (int j3 = 0; j3 < R; j3++) v[j3] = B[(k1 * M + k2 * R + j3) * FFT_B + b]; \
+    SmallDFT<R, 1>::run(v);                                          \
+    _Pragma("unroll") for (int k3 = 0; k3 < R; k3++) store(k1 + R1 * (k2 + R2 * k3), v[k3]); \
+  }
+    PAWB200_RADIX_SWITCH(R3, T3)
+#undef T3
+  }
+}
+
+// PASS: 2 = Z (coefficients -> T1), 1 = Y (T1 -> T2), 0 = X (T2 -> X); same work decomposition, inputs and outputs as
+// the two-factor kernels above, one line per iteration.
+template <int PASS>
+__global__ void __launch_bounds__(512, 1)
+fft3_pass_kernel(FftGeom g, const float2* __restrict__ Cil, long ldil, int slot0, int nslot, double scale,
+                 const double2* __restrict__ in_base, double2* __restrict__ out_base, int ngroups) {
+  extern __shared__ __align__(16) unsigned char fft_smem[];
+  const int n = PASS == 0 ? g.n1 : PASS == 1 ? g.n2 : g.n3;
+  double2* A = reinterpret_cast<double2*>(fft_smem);         // [n][FFT_B]
+  double2* B = A + n * FFT_B;                                // [n][FFT_B]
+  double2* tw = B + n * FFT_B;                               // [n]
+  int* ssrc = reinterpret_cast<int*>(tw + n);                // X: [n1] plane offsets; Y: [n2] column offsets
+  const int tid = threadIdx.x, q = tid / FFT_B, b = tid % FFT_B, Q = blockDim.x / FFT_B;
+  const int R1 = g.r1[PASS], R2 = g.r2[PASS], R3 = g.r3[PASS];
+  for (int i = tid; i < n; i += blockDim.x) tw[i] = g.tw[PASS][i];
+  const long plane = (long)g.n2 * g.n3;
+  if (PASS == 0)
+    for (int i = tid; i < g.n1; i += blockDim.x) {
+      const int p = g.xsrc[i];
+      ssrc[i] = p >= 0 ? p * (int)(plane * FFT_B) : -1;
+    }
+  __syncthreads();
+  if (PASS == 2) {
+    const long nlines = (long)ngroups * g.ncol;
+    for (long line = blockIdx.x; line < nlines; line += gridDim.x) {
+      const int grp = (int)(line / g.ncol), col = (int)(line % g.ncol);
+      const int4 cur = __ldg(g.col_run + col);
+      const int slot = slot0 + grp * FFT_B + b;
+      const int cnt = slot < slot0 + nslot ? cur.y : 0;
+      const float2* base = Cil + ((long)(slot >> 4) * ldil + cur.x) * FFT_B + (slot & 15);
+      const int n3 = g.n3;
+      auto load = [&](int row) {
+        int d = row - cur.z;
+        if (d < 0) d += n3;
+        if (d >= cnt) return make_double2(0, 0);
+        const int j = d < cur.w ? cur.y - cur.w + d : d - cur.w;
+        const float2 c = __ldg(base + j * FFT_B);
+        return make_double2(scale * (double)c.x, scale * (double)c.y);
+      };
+      double2* out = out_base + (((long)grp * g.ncol + col) * n3) * FFT_B + b;
+      auto store = [&](int row, double2 v) { out[row * FFT_B] = v; };
+      line3_transform(A, B, tw, R1, R2, R3, q, Q, b, load, store);
+    }
+  } else if (PASS == 1) {
+    const int colstride = g.n3 * FFT_B;
+    const long nlines = (long)ngroups * g.nplane * g.n3;
+    int cur_plane = -1;
+    for (long line = blockIdx.x; line < nlines; line += gridDim.x) {
+      const int z = (int)(line % g.n3);
+      const int p = (int)((line / g.n3) % g.nplane);
+      const int grp = (int)(line / ((long)g.n3 * g.nplane));
+      if (p != cur_plane) {                                  // (uniform) refresh the plane's row -> column offsets
+        __syncthreads();
+        for (int i = tid; i < g.n2; i += blockDim.x) {
+          const int c = g.ysrc[p * g.n2 + i];
+          ssrc[i] = c >= 0 ? c * colstride : -1;
+        }
+        cur_plane = p;
+        __syncthreads();
+      }
+      const double2* in = in_base + ((long)grp * g.ncol * g.n3 + z) * FFT_B + b;
+      auto load = [&](int row) {
+        const int o = ssrc[row];
+        return o >= 0 ? in[o] : make_double2(0, 0);
+      };
+      double2* out = out_base + ((((long)grp * g.nplane + p) * g.n2) * g.n3 + z) * FFT_B + b;
+      auto store = [&](int row, double2 v) { out[row * colstride] = v; };
+      line3_transform(A, B, tw, R1, R2, R3, q, Q, b, load, store);
+    }
+  } else {
+    const int xstride = (int)(plane * FFT_B);
+    const long nlines = (long)ngroups * plane;
+    for (long line = blockIdx.x; line < nlines; line += gridDim.x) {
+      const long yz = line % plane;
+      const int grp = (int)(line / plane);
+      const double2* in = in_base + ((long)grp * g.nplane * plane + yz) * FFT_B + b;
+      auto load = [&](int row) {
+        const int o = ssrc[row];
+        return o >= 0 ? in[o] : make_double2(0, 0);
+      };
+      double2* out = out_base + ((long)grp * g.n1 * plane + yz) * FFT_B + b;
+      auto store = [&](int row, double2 v) { out[row * xstride] = v; };
+      line3_transform(A, B, tw, R1, R2, R3, q, Q, b, load, store);
+    }
+  }
+}
+
 // ---- fused pass Y + X: T1 -> (L2-resident ring) -> X ----------------------------------------------------------
 // The stand-alone passes write the y-transformed planes T2 (0.68 N points per band) to HBM and read them back:
 // 45 % of the transform's traffic.  Here both passes run in ONE persistent kernel and T2 only ever exists for a few

@@ -90,6 +90,19 @@ void launch_pass_x(const FftGeom& g, int ng, const double2* T2, double2* X, int 
   fft_pass_x_kernel<RMAX><<<fft_grid_dim((long)ng * g.n2 * g.n3, occ, num_sms), threads, smem, st>>>(g, T2, X, ng);
 }
 
+// three-factor axis (fft3_pass_kernel<PASS>): Q = 16 or 32 task slots of 16 bands
+template <int PASS>
+void launch_pass3(const FftGeom& g, const FftInput& in, int s0, int ns, int ng, double scale, const double2* src,
+                  double2* dst, int num_sms, cudaStream_t st) {
+  const int n = PASS == 0 ? g.n1 : PASS == 1 ? g.n2 : g.n3;
+  const int threads = (n <= 220 ? 16 : 32) * FFT_B;
+  const size_t smem = (size_t)(2 * n * FFT_B + n) * sizeof(double2) + (size_t)std::max(g.n1, g.n2) * sizeof(int);
+  const int occ = cached_occupancy(fft3_pass_kernel<PASS>, threads, smem);
+  const long lines = PASS == 0 ? (long)ng * g.n2 * g.n3 : PASS == 1 ? (long)ng * g.nplane * g.n3 : (long)ng * g.ncol;
+  fft3_pass_kernel<PASS><<<fft_grid_dim(lines, occ, num_sms), threads, smem, st>>>(g, in.Cil, in.ldil, s0, ns, scale,
+                                                                                   src, dst, ng);
+}
+
 inline int yx_threads(const FftGeom& g) {
   return std::max(std::max(g.r1[0], g.r2[0]), std::max(g.r1[1], g.r2[1])) * FFT_B;
 }
@@ -200,7 +213,7 @@ TmaPlan plan_tma_pass(const FftGeom& g, int pass, int max_plane_cols) {
   // CTAs/SM with a 3-stage ring 12.9, ZL=2 12.0, single exchange buffer (three CTAs/SM) 10.9 - the passes are bound by
   // resident warps (issue / FP64 latency between the two phases of a line), not by bytes in flight, so shared memory
   // spent on stages costs more than the prefetch returns.
-  if (env_int("PAWB200_FFT_TMA", 0) == 0 || !tensor_map_encoder()) return p;
+  if (env_int("PAWB200_FFT_TMA", 0) == 0 || !tensor_map_encoder() || g.three) return p;
   if (pass == 1 && !g.plane_run) return p;
   const int n = pass == 0 ? g.n1 : g.n2;
   const int zl = std::max(1, std::min(8, env_int("PAWB200_TMA_ZL", 1)));
@@ -279,7 +292,7 @@ YxConfig plan_fused_yx(const FftGeom& g, int num_sms, size_t l2_budget_bytes) {
   // stand-alone passes (1.29 ms against 0.88 ms), which are latency- rather than bandwidth-bound.
   const char* e = getenv("PAWB200_FFT_FUSED");
   if (!e || atoi(e) == 0) return c;
-  if (!g.plane_run) return c;
+  if (!g.plane_run || g.three) return c;
   if (yx_smem(g) > (size_t)kFftSmemOptIn) return c;
   const int ryx = std::max(std::max(g.r1[0], g.r2[0]), std::max(g.r1[1], g.r2[1]));
   int occ = 1;
@@ -336,7 +349,7 @@ YxConfig plan_fused_yx(const FftGeom& g, int num_sms, size_t l2_budget_bytes) {
 
 int launch_pruned_forward(const FftGeom& g, int ng, const double2* X, const FftWork& w, float2* out_il, long ldil,
                           double scale, int num_sms, cudaStream_t st) {
-  if (!g.col_run) throw std::runtime_error("forward pruned transform needs single-run columns");
+  if (!g.col_run || g.three) throw std::runtime_error("forward pruned transform needs single-run columns and two-factor axes");
   const int rz = std::max(g.r1[2], g.r2[2]), ry = std::max(g.r1[1], g.r2[1]), rx = std::max(g.r1[0], g.r2[0]);
 #define FWD_X(R)                                                                                                    \
   {                                                                                                                 \
@@ -375,6 +388,26 @@ int launch_pruned_passes(const FftGeom& g, const FftInput& in, int s0, int ns, i
                          const FftWork& w, const YxConfig* yx, double2* X, int num_sms, cudaStream_t st,
                          int max_plane_cols) {
   const int rz = std::max(g.r1[2], g.r2[2]), ry = std::max(g.r1[1], g.r2[1]), rx = std::max(g.r1[0], g.r2[0]);
+  if (g.three) {
+    // some axis has three factors: per axis either the three-factor kernel or the two-factor one (no fused / TMA
+    // variants, and pass Z needs the run encoding + interleaved coefficients, which the plan guarantees here)
+#define PASS_Z(R) launch_pass_z<R>(g, in, s0, ns, ng, scale, w.T1, num_sms, st)
+#define PASS_Y(R) launch_pass_y<R>(g, ng, w.T1, w.T2, num_sms, st)
+#define PASS_X(R) launch_pass_x<R>(g, ng, w.T2, X, num_sms, st)
+    if (g.r3[2] > 1 && (!in.Cil || !g.col_run))
+      throw std::runtime_error("three-factor pass Z needs the interleaved coefficient copy and single-run columns");
+    if (g.r3[2] > 1) launch_pass3<2>(g, in, s0, ns, ng, scale, nullptr, w.T1, num_sms, st);
+    else PAWB200_AXIS_SWITCH(rz, PASS_Z);
+    if (g.r3[1] > 1) launch_pass3<1>(g, in, s0, ns, ng, scale, w.T1, w.T2, num_sms, st);
+    else PAWB200_AXIS_SWITCH(ry, PASS_Y);
+    if (g.r3[0] > 1) launch_pass3<0>(g, in, s0, ns, ng, scale, w.T2, X, num_sms, st);
+    else PAWB200_AXIS_SWITCH(rx, PASS_X);
+#undef PASS_Z
+#undef PASS_Y
+#undef PASS_X
+    FFT_CUDA_OK(cudaGetLastError());
+    return 3;
+  }
 #define PASS_Z(R) launch_pass_z<R>(g, in, s0, ns, ng, scale, w.T1, num_sms, st)
   PAWB200_AXIS_SWITCH(rz, PASS_Z);
 #undef PASS_Z

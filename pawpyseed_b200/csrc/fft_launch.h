@@ -13,6 +13,8 @@ constexpr int FFT_ZC = 9;          // z-lines per work unit of the stand-alone p
 struct FftGeom {            // device-side description of one (k-point, grid) pruned transform
   int n1, n2, n3;           // grid
   int r1[3], r2[3];         // n_d = r1[d] * r2[d] (index 0: x, 1: y, 2: z)
+  int r3[3];                // third factor (1 for two-factor axes): n_d = r1 * r2 * r3, all radices <= 10 then
+  int three;                // some axis has three factors (inverse passes only; forward transforms take the generic path)
   int ncol, nplane;         // active (g1,g2) columns / active g1 planes
   const int* col_start;     // [ncol] first sorted plane-wave index of the column
   const int* col_cnt;       // [ncol]

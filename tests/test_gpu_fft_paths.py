@@ -41,14 +41,22 @@ def oracle(c):
     (60, 42, 75),    # 6x10, 6x7, 5x15          (radix 10, 15) - non-cubic
     (162, 20, 36),   # 9x18, 4x5, 6x6           (radix 18: the 320-thread class)
     (20, 200, 18),   # 4x5, 10x20, 3x6          (radix 20)
+    (125, 18, 20),   # 5x5x5: three-factor x axis (no split into two radices <= 20)
+    (20, 147, 18),   # 7x7x3: three-factor y axis
+    (18, 20, 243),   # 9x9x3: three-factor z axis (the pass that reads the interleaved coefficients)
     (22, 26, 20),    # 2x11 / 2x13: unsupported radices -> generic cuFFT path
     (19, 20, 20),    # prime size -> generic path
 ])
 def test_projections_on_awkward_grids(dim):
     c = cases.small_case(seed=5, nband=5, encut=120.0, dim=dim)
+    _lib.reset_timers()
     wf, o = gpu(c), oracle(c)
     got = np.array([[wf._get_projections(b, k) for b in range(5)] for k in range(4)])
     assert rel(got, np.array(o.P)) < TOL
+    # which transform ran: the hand-written pruned passes never scatter into contiguous boxes
+    t = _lib.timers()
+    generic = dim in ((22, 26, 20), (19, 20, 20))
+    assert (t["boxes_scattered"] > 0) == generic and t["boxes_fft"] > 0
     assert rel(wf._get_realspace_state(2, 1, 0), o.realspace_state(2, 1)) < TOL
     # density on the same grid: pruned transform + interleaved accumulation where the grid factors, cuFFT otherwise
     wf.fdimv = np.array(dim, np.int32)
