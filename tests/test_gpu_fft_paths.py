@@ -44,6 +44,7 @@ def oracle(c):
     (125, 18, 20),   # 5x5x5: three-factor x axis (no split into two radices <= 20)
     (20, 147, 18),   # 7x7x3: three-factor y axis
     (18, 20, 243),   # 9x9x3: three-factor z axis (the pass that reads the interleaved coefficients)
+    (384, 18, 420),  # 8x8x6 and 10x7x6: the largest three-factor lines (512-thread CTAs, 223 KB of shared memory)
     (22, 26, 20),    # 2x11 / 2x13: unsupported radices -> generic cuFFT path
     (19, 20, 20),    # prime size -> generic path
 ])
