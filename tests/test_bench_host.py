@@ -32,6 +32,19 @@ def test_sample_plan_keeps_the_element_mix_and_site_lists_consistent():
     assert len(full["R_sub"]) == len(w["labels_R"]) and len(full["S_sub"]) == len(w["labels_S"])
 
 
+def test_blocks_debug_option_keeps_the_first_blocks_and_says_so():
+    """`--blocks n` (what one rank of an n-block job holds, for single-GPU traces of the e2e pipeline): the workload
+    shrinks to the first k-points / one spin and its name says so, so such a line cannot pass for the real config."""
+    w = bench.workload("tiny", blocks=1)
+    assert w["nk"] == 1 and w["nspin"] == 1 and "[debug: first 1 block(s)]" in w["name"]
+    assert bench.config_dict(w, 1, "strong")["kappa_blocks"] == 1
+    full = bench.workload("tiny")
+    assert full["nk"] * full["nspin"] == 4 and "debug" not in full["name"]
+    assert np.array_equal(w["gvecs"][0], full["gvecs"][0])          # block 0 is the same block
+    # level-1 / level-2 choice follows the block count
+    assert bench.shard_mode(full, 4) == "kappa" and bench.shard_mode(w, 2) == "bands"
+
+
 def test_config_dict_is_identical_for_both_arms():
     w = bench.workload("tiny")
     a = bench.config_dict(w, 1, "strong")
